@@ -1,0 +1,125 @@
+/*
+ * mpmae.h -- C ABI of the B200-native MP-MAE (FCMAE) pretraining step.
+ *
+ * Drop-in boundary.  The reference reaches its native code through the
+ * pybind module MinkowskiEngineBackend._C:
+ *     MinkowskiEngine/pybind/extern.hpp:118-145   DepthwiseConvolution{Forward,Backward}GPU
+ *     MinkowskiEngine/pybind/extern.hpp:610-625   py::class_/m.def registrations (GIL released)
+ *     MinkowskiEngine/MinkowskiEngine/MinkowskiDepthwiseConvolution.py:52-64   the call site
+ * and through ATen/cuBLAS for everything else in models/fcmae.py:FCMAE.forward (lines 414-456).
+ * This library replaces that whole forward+backward with two calls.  Plain C types only; every
+ * device buffer is allocated by the caller (torch caching allocator) and passed in; the library
+ * allocates no device memory, keeps no global state besides immutable constants, never
+ * synchronises the device and never throws across the boundary.
+ *
+ * All functions return 0 on success or a negative mpmae_status; mpmae_last_error() gives a
+ * thread-local message.
+ */
+#ifndef MPMAE_H
+#define MPMAE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPMAE_MAX_MOD 16
+
+typedef enum mpmae_status {
+  MPMAE_OK = 0,
+  MPMAE_ERR_INVALID = -1,     /* bad configuration / null pointer                     */
+  MPMAE_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were instantiated for */
+  MPMAE_ERR_CUDA = -3,        /* a CUDA launch or API call failed                     */
+  MPMAE_ERR_WORKSPACE = -4    /* workspace too small                                  */
+} mpmae_status;
+
+/* modality kinds, models/fcmae.py:281-403 */
+typedef enum mpmae_mod_kind {
+  MPMAE_PIXEL_CONTINUOUS = 0,  /* sentinel2, sentinel1, aster, canopy_height_eth : float [B,c,S,S]      */
+  MPMAE_PIXEL_CATEGORICAL = 1, /* dynamic_world, esa_worldcover                  : int64 [B,1,S,S], -1 = ignore */
+  MPMAE_IMAGE_CATEGORICAL = 2, /* biome, eco_region                              : int64 one-hot [B,c]  */
+  MPMAE_IMAGE_CONTINUOUS = 3   /* lat, lon, month, era5                          : float [B,c], NaN = ignore */
+} mpmae_mod_kind;
+
+/* Mirrors the FCMAE constructor (models/fcmae.py:30-43) + args.out_modalities / args.loss_aggr. */
+typedef struct mpmae_cfg {
+  int32_t batch;      /* per-GPU batch B                                   */
+  int32_t img_size;   /* 56 or 112 (img_size / patch_size = patch grid G)   */
+  int32_t patch_size; /* multiple of 8: 8 or 16                             */
+  int32_t in_chans;   /* sentinel-2 bands fed to the encoder (12)           */
+  int32_t depths[4];
+  int32_t dims[4];
+  int32_t dec_dim;       /* decoder_embed_dim                               */
+  int32_t dec_depth;     /* decoder_depth                                   */
+  float mask_ratio;      /* visible patches = (int)(L * (1 - mask_ratio))   */
+  int32_t loss_aggr;     /* 0 = unweighted, 1 = uncertainty                 */
+  int32_t n_mod;         /* output modalities, in args.out_modalities order */
+  int32_t mod_kind[MPMAE_MAX_MOD];
+  int32_t mod_chans[MPMAE_MAX_MOD];    /* out_chans (classes for categorical) */
+  int32_t mod_norm_pix[MPMAE_MAX_MOD]; /* per-patch target normalisation (sentinel2 && norm_pix_loss) */
+  int32_t gemm_backend;  /* 0 = fp32 SIMT tiles, 1 = tcgen05 (TF32x3, fp32-faithful), 2 = tcgen05 single-pass TF32 */
+} mpmae_cfg;
+
+typedef struct mpmae_plan mpmae_plan; /* opaque: parameter layout, workspace layout, launch plan */
+
+/* Per-step device pointers.  Everything is fp32 unless stated. */
+typedef struct mpmae_io {
+  const float *params;     /* flat parameter buffer, layout given by mpmae_param_info     */
+  float *grads;            /* flat gradient buffer, same layout; backward ACCUMULATES      */
+  void *workspace;         /* >= mpmae_workspace_bytes(plan), 256-byte aligned             */
+  size_t workspace_bytes;
+  const float *noise;      /* [B, L]  N(0,1) noise of gen_random_mask (fcmae.py:220)       */
+  const float *s2_input;   /* [B, in_chans, S, S] encoder input (before nan_to_num)        */
+  const void *targets[MPMAE_MAX_MOD]; /* per output modality, dtype/shape by kind          */
+  float *mask;             /* out [B, L]  0 keep / 1 remove                                 */
+  float *pred_pixel;       /* out [B*L, n_pix_cols] channels-last pixel-head predictions    */
+  float *pred_image;       /* out [B, n_img_cols] image-head predictions                    */
+  float *losses;           /* out [2*n_mod + 1]: per-modality loss, weighted loss, total    */
+  const float *grad_out;   /* backward only: d(total)/d(total) upstream scalar (device)     */
+  int32_t *flags;          /* out [4] device flags: [0] all-zero visible input pixels seen  */
+} mpmae_io;
+
+const char *mpmae_last_error(void);
+int mpmae_version(void);
+
+int mpmae_plan_create(const mpmae_cfg *cfg, mpmae_plan **out);
+void mpmae_plan_destroy(mpmae_plan *plan);
+
+/* parameter layout: reference state-dict names, shapes and offsets (floats) in the flat buffer */
+int64_t mpmae_param_total(const mpmae_plan *plan);
+int32_t mpmae_param_count(const mpmae_plan *plan);
+int mpmae_param_info(const mpmae_plan *plan, int32_t index, char *name, int32_t name_cap,
+                     int64_t shape[4], int32_t *ndim, int64_t *offset);
+
+size_t mpmae_workspace_bytes(const mpmae_plan *plan);
+int32_t mpmae_pred_pixel_cols(const mpmae_plan *plan);
+int32_t mpmae_pred_image_cols(const mpmae_plan *plan);
+/* column offset of modality m inside pred_pixel / pred_image (by kind) */
+int32_t mpmae_pred_col_offset(const mpmae_plan *plan, int32_t mod);
+
+/* named intermediate tensors inside the workspace (parity tests): offset in bytes, rows, cols */
+int mpmae_tap_info(const mpmae_plan *plan, const char *name, int64_t *byte_offset, int64_t *rows,
+                   int64_t *cols);
+
+/* number of kernels launched by one forward / backward call (bench.py "gpu_launches") */
+int32_t mpmae_launch_count(const mpmae_plan *plan, int32_t backward);
+
+/* FCMAE.forward: mask -> sparse encoder -> decoder -> heads -> losses.  Asynchronous on `stream`. */
+int mpmae_forward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
+/* hand-derived backward of the same step; accumulates into io->grads.  Must follow mpmae_forward
+ * on the same workspace. */
+int mpmae_backward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
+
+/* dense encoder features [B, C3, G, G] (zeros at masked cells) from the last forward */
+int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw, void *cuda_stream);
+
+/* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias) */
+int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
+                    int64_t M, int32_t N, int32_t K, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPMAE_H */

@@ -1,0 +1,395 @@
+// Mask / slot tables, row-wise LayerNorm, GRN statistics, weight folding, decoder entry and
+// pooled image-head kernels.  All are HBM-bound row kernels: one warp per row, float4 where the
+// channel count allows, warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace mpmae {
+
+// ------------------------------------------------------------------------------------------------
+// M0: mask and slot tables from the noise tensor (models/fcmae.py:214-231).
+//   rank(l) = position of patch l in the ascending (stable) sort of noise; kept iff rank < V.
+__global__ void mask_kernel(const float *__restrict__ noise, float *__restrict__ mask, int *__restrict__ slot_of,
+                            int *__restrict__ vis_patch, int L, int V) {
+  extern __shared__ float sm[];
+  float *nz = sm;
+  int *keep = reinterpret_cast<int *>(sm + L);
+  const int n = blockIdx.x;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) nz[l] = noise[n * L + l];
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const float v = nz[l];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float u = nz[j];
+      rank += (u < v) || (u == v && j < l);
+    }
+    keep[l] = rank < V;
+    mask[n * L + l] = rank < V ? 0.f : 1.f;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    int s = 0;
+    for (int j = 0; j < l; ++j) s += keep[j];
+    if (keep[l]) { slot_of[n * L + l] = s; vis_patch[n * V + s] = l; }
+    else slot_of[n * L + l] = -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm without affine: xhat = (x - mean) * rstd ; the affine part is folded into the
+// weights of the GEMM that consumes xhat (fold_kernel).  eps = 1e-6 (sparse_norm_layers.py:61-77).
+__global__ void ln_rows_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, float *__restrict__ rstd_out,
+                                   int64_t R, int C, float eps) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float *xr = x + r * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+  for (int c = lane; c < C; c += 32) xhat[r * C + c] = (xr[c] - mean) * rstd;
+  if (lane == 0) rstd_out[r] = rstd;
+}
+
+// dx = rstd * (dxhat - mean_C(dxhat) - xhat * mean_C(dxhat * xhat))  (+ add)
+__global__ void ln_rows_bwd_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
+                                   const float *__restrict__ rstd, const float *__restrict__ add,
+                                   float *__restrict__ dx, int64_t R, int C) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float g = dxhat[r * C + c];
+    s1 += g; s2 += g * xhat[r * C + c];
+  }
+  s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
+  const float rs = rstd[r];
+  for (int c = lane; c < C; c += 32) {
+    float v = rs * (dxhat[r * C + c] - s1 - xhat[r * C + c] * s2);
+    if (add) v += add[r * C + c];
+    dx[r * C + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRN (models/sparse_norm_layers.py:24-33 batch-global, eps 1e-6; models/norm_layers.py:41-44 per
+// sample, eps 1e-4).  gsq[g, d] = sum over the group's rows of h^2 comes from the pw1 epilogue.
+//   Gx = sqrt(gsq) ; Nx = Gx / (mean_d Gx + eps) ; scale s = 1 + gamma * Nx
+__global__ void grn_scale_kernel(const float *__restrict__ gsq, const float *__restrict__ gamma,
+                                 float *__restrict__ nx, float *__restrict__ scale, float *__restrict__ denom,
+                                 int D, float eps) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) s += sqrtf(gsq[(int64_t)g * D + d]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float den = red[0] / (float)D + eps;
+  if (threadIdx.x == 0) denom[g] = den;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float n = sqrtf(gsq[(int64_t)g * D + d]) / den;
+    nx[(int64_t)g * D + d] = n;
+    scale[(int64_t)g * D + d] = 1.f + gamma[d] * n;
+  }
+}
+
+// g = h * scale[group(r), d] + beta[d]
+__global__ void grn_apply_kernel(const float *__restrict__ h, const float *__restrict__ scale,
+                                 const float *__restrict__ beta, float *__restrict__ g, int64_t R, int D,
+                                 int group_rows) {
+  const int64_t n4 = R * (D >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (D >> 2);
+    const int d = (int)(i - r * (D >> 2)) * 4;
+    const int64_t grp = r / group_rows;
+    const float4 hv = *reinterpret_cast<const float4 *>(h + r * D + d);
+    const float4 sv = *reinterpret_cast<const float4 *>(scale + grp * D + d);
+    const float4 bv = *reinterpret_cast<const float4 *>(beta + d);
+    float4 o;
+    o.x = fmaf(hv.x, sv.x, bv.x); o.y = fmaf(hv.y, sv.y, bv.y);
+    o.z = fmaf(hv.z, sv.z, bv.z); o.w = fmaf(hv.w, sv.w, bv.w);
+    *reinterpret_cast<float4 *>(g + r * D + d) = o;
+  }
+}
+
+// Backward of the GRN statistic.  ds[g, d] = sum_rows dg * h (from the dg epilogue).
+//   dgamma[d] += sum_g Nx * ds ; dNx = gamma * ds ; dGx = dNx/den - (sum_j dNx_j Gx_j) / (D den^2)
+//   kg[g, d] = dGx / Gx   (so that dh += kg * h)
+__global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *__restrict__ nx,
+                                     const float *__restrict__ denom, const float *__restrict__ gamma,
+                                     float *__restrict__ dgamma, float *__restrict__ kg, int D) {
+  __shared__ float red[32];
+  const int g = blockIdx.x;
+  const float den = denom[g];
+  float s = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int64_t i = (int64_t)g * D + d;
+    s += gamma[d] * ds[i] * (nx[i] * den);  // dNx_j * Gx_j
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float cross = red[0] / ((float)D * den * den);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int64_t i = (int64_t)g * D + d;
+    const float dnx = gamma[d] * ds[i];
+    const float gx = nx[i] * den;
+    const float dgx = dnx / den - cross;
+    kg[i] = gx > 0.f ? dgx / gx : 0.f;
+    atomicAdd(&dgamma[d], nx[i] * ds[i]);
+  }
+}
+
+// da = (dg * scale[g, d] + kg[g, d] * h) * gelu'(a)   (in place over dg allowed)
+__global__ void grn_gelu_bwd_kernel(const float *dg, const float *__restrict__ h, const float *__restrict__ a,
+                                    const float *__restrict__ scale, const float *__restrict__ kg, float *da,
+                                    int64_t R, int D, int group_rows) {
+  const int64_t n4 = R * (D >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (D >> 2);
+    const int d = (int)(i - r * (D >> 2)) * 4;
+    const int64_t grp = r / group_rows;
+    const float4 gv = *reinterpret_cast<const float4 *>(dg + r * D + d);
+    const float4 hv = *reinterpret_cast<const float4 *>(h + r * D + d);
+    const float4 av = *reinterpret_cast<const float4 *>(a + r * D + d);
+    const float4 sv = *reinterpret_cast<const float4 *>(scale + grp * D + d);
+    const float4 kv = *reinterpret_cast<const float4 *>(kg + grp * D + d);
+    float4 o;
+    o.x = (gv.x * sv.x + kv.x * hv.x) * gelu_grad_f(av.x);
+    o.y = (gv.y * sv.y + kv.y * hv.y) * gelu_grad_f(av.y);
+    o.z = (gv.z * sv.z + kv.z * hv.z) * gelu_grad_f(av.z);
+    o.w = (gv.w * sv.w + kv.w * hv.w) * gelu_grad_f(av.w);
+    *reinterpret_cast<float4 *>(da + r * D + d) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight folding.  A LayerNorm affine (scale w, shift b over the K axis) in front of a linear map
+// y = (xhat*w + b) . W^T + bias  is absorbed into  Wf[n,k] = W[n,k]*w[k%SL],  bf[n] = bias[n] +
+// sum_k W[n,k]*b[k%SL].  Source W may be stored [N,K] (nn.Linear) or [K,N] (ME conv kernels) via
+// strides.  Emits Wf [N,K] and/or WfT [K,N].  One warp per output row n.
+struct FoldArgs {
+  const float *W; int64_t s_n, s_k;
+  const float *scale_k;  // [SL] or null
+  const float *shift_k;  // [SL] or null
+  const float *scale_n;  // [N] or null (row scale, e.g. per-modality loss seeds)
+  const float *bias;     // [N] or null
+  float *Wf;             // [N, K] or null
+  float *WfT;            // [K, N] or null
+  float *bf;             // [N] or null
+  int N, K, SL;
+};
+__global__ void fold_kernel(FoldArgs p) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= p.N) return;
+  const int lane = threadIdx.x & 31;
+  const float sn = p.scale_n ? p.scale_n[n] : 1.f;
+  float acc = 0.f;
+  for (int k = lane; k < p.K; k += 32) {
+    const float w = p.W[n * p.s_n + k * p.s_k];
+    const int j = k % p.SL;
+    const float wf = w * (p.scale_k ? p.scale_k[j] : 1.f) * sn;
+    if (p.Wf) p.Wf[(int64_t)n * p.K + k] = wf;
+    if (p.WfT) p.WfT[(int64_t)k * p.N + n] = wf;
+    if (p.shift_k) acc = fmaf(w, p.shift_k[j], acc);
+  }
+  if (p.bf) {
+    acc = warp_sum(acc);
+    if (lane == 0) p.bf[n] = (p.bias ? p.bias[n] : 0.f) + acc;
+  }
+}
+
+// Chain rule back through the fold:  given dWf [N,K] and dbf [N]
+//   dW[n,k]    += dWf[n,k]*scale[k%SL] + dbf[n]*shift[k%SL]
+//   dscale[j]  += sum_{n, k%SL==j} dWf[n,k]*W[n,k]
+//   dshift[j]  += sum_{n, k%SL==j} dbf[n]*W[n,k]
+//   dbias[n]   += dbf[n]
+// One CTA per k; threads stride n.
+struct UnfoldArgs {
+  const float *W; int64_t s_n, s_k;
+  const float *scale_k, *shift_k;
+  const float *dWf, *dbf;
+  float *dW;       // same strides as W
+  float *dscale, *dshift, *dbias;
+  int N, K, SL;
+};
+__global__ void unfold_kernel(UnfoldArgs p) {
+  __shared__ float r1[32], r2[32];
+  const int k = blockIdx.x;
+  const int j = k % p.SL;
+  const float sc = p.scale_k ? p.scale_k[j] : 1.f;
+  const float sh = p.shift_k ? p.shift_k[j] : 0.f;
+  float a1 = 0.f, a2 = 0.f;
+  for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+    const float w = p.W[n * p.s_n + k * p.s_k];
+    const float g = p.dWf[(int64_t)n * p.K + k];
+    const float gb = p.dbf ? p.dbf[n] : 0.f;
+    atomicAdd(&p.dW[n * p.s_n + k * p.s_k], g * sc + gb * sh);
+    a1 = fmaf(g, w, a1);
+    a2 = fmaf(gb, w, a2);
+    if (k == 0 && p.dbias) atomicAdd(&p.dbias[n], gb);
+  }
+  a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = a1; r2[threadIdx.x >> 5] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t1 = threadIdx.x < (blockDim.x >> 5) ? r1[threadIdx.x] : 0.f;
+    float t2 = threadIdx.x < (blockDim.x >> 5) ? r2[threadIdx.x] : 0.f;
+    t1 = warp_sum(t1); t2 = warp_sum(t2);
+    if (threadIdx.x == 0) {
+      if (p.dscale) atomicAdd(&p.dscale[j], t1);
+      if (p.dshift) atomicAdd(&p.dshift[j], t2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder entry (models/fcmae.py:251-255): dense cell rows from projected visible rows + mask token.
+//   xd[n*L + l, :] = slot>=0 ? z[n*V+slot, :] : token
+__global__ void scatter_token_kernel(const float *__restrict__ z, const float *__restrict__ token,
+                                     const int *__restrict__ slot_of, float *__restrict__ xd, int64_t cells, int L,
+                                     int V, int C) {
+  const int C4 = C >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells * C4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cell = i / C4;
+    const int c = (int)(i - cell * C4) * 4;
+    const int slot = slot_of[cell];
+    const int64_t n = cell / L;
+    const float4 v = slot >= 0 ? *reinterpret_cast<const float4 *>(z + (n * V + slot) * C + c)
+                               : *reinterpret_cast<const float4 *>(token + c);
+    *reinterpret_cast<float4 *>(xd + cell * C + c) = v;
+  }
+}
+// backward: dz[n*V+slot] = dxd[cell] for visible cells; dtoken += sum over masked cells
+__global__ void gather_token_bwd_kernel(const float *__restrict__ dxd, const int *__restrict__ slot_of,
+                                        float *__restrict__ dz, float *__restrict__ dtoken, int64_t cells, int L, int V,
+                                        int C) {
+  // grid.x strides cells, threads stride channels; masked-cell sums are accumulated per CTA first
+  extern __shared__ float tok[];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) tok[c] = 0.f;
+  __syncthreads();
+  for (int64_t cell = blockIdx.x; cell < cells; cell += gridDim.x) {
+    const int slot = slot_of[cell];
+    const int64_t n = cell / L;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float v = dxd[cell * C + c];
+      if (slot >= 0) dz[(n * V + slot) * C + c] = v;
+      else tok[c] += v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dtoken[c], tok[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Image-level heads: channel LayerNorm of every decoder cell (norm_layers.py:26-31, eps 1e-6) then
+// mean over the L cells (fcmae.py:259-262).  One CTA per sample; warp per cell; smem accumulation.
+__global__ void pool_ln_fwd_kernel(const float *__restrict__ d, const float *__restrict__ w, const float *__restrict__ b,
+                                   float *__restrict__ pooled, float *__restrict__ rstd_out, int L, int C, float eps) {
+  extern __shared__ float acc[];  // [C]
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  for (int l = warp; l < L; l += nw) {
+    const float *xr = d + ((int64_t)n * L + l) * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float t = xr[c] - mean; v += t * t; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    if (lane == 0) rstd_out[(int64_t)n * L + l] = rstd;
+    for (int c = lane; c < C; c += 32) atomicAdd(&acc[c], (xr[c] - mean) * rstd);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[(int64_t)n * C + c] = w[c] * (acc[c] / (float)L) + b[c];
+}
+// backward: dpooled [B,C] -> ddec[n,l,:] += LNbwd(dn = w*dpooled/L) ; dw += dpooled * mean_l(nhat) ; db += dpooled
+__global__ void pool_ln_bwd_kernel(const float *__restrict__ d, const float *__restrict__ rstd_in,
+                                   const float *__restrict__ w, const float *__restrict__ dpooled,
+                                   float *__restrict__ ddec, float *__restrict__ dw, float *__restrict__ db, int L, int C,
+                                   float eps) {
+  extern __shared__ float acc[];  // [C] sum_l nhat
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  for (int l = warp; l < L; l += nw) {
+    const int64_t row = (int64_t)n * L + l;
+    const float *xr = d + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    const float rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float nh = (xr[c] - mean) * rstd;
+      const float g = w[c] * dpooled[(int64_t)n * C + c] / (float)L;
+      s1 += g; s2 += g * nh;
+      atomicAdd(&acc[c], nh);
+    }
+    s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float nh = (xr[c] - mean) * rstd;
+      const float g = w[c] * dpooled[(int64_t)n * C + c] / (float)L;
+      ddec[row * C + c] += rstd * (g - s1 - nh * s2);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float dp = dpooled[(int64_t)n * C + c];
+    atomicAdd(&dw[c], dp * acc[c] / (float)L);
+    atomicAdd(&db[c], dp);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense encoder features [B, C, G, G] from the stage-3 rows (SparseTensor.dense(), zeros at masked cells)
+__global__ void densify_kernel(const float *__restrict__ x3, const int *__restrict__ slot_of, float *__restrict__ out,
+                               int B, int L, int V, int C) {
+  const int64_t total = (int64_t)B * C * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i % L);
+    const int c = (int)((i / L) % C);
+    const int64_t n = i / ((int64_t)L * C);
+    const int slot = slot_of[n * L + l];
+    out[i] = slot >= 0 ? x3[(n * V + slot) * C + c] : 0.f;
+  }
+}
+
+// column sums of a [R, C] matrix into out[C] (+=): bias gradients that have no GEMM to ride on
+__global__ void colsum_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t R, int C) {
+  // blockDim = (32, 8): x over channels, y over rows
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float red[8][33];
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < R; r += (int64_t)gridDim.y * 8) s += x[r * C + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(&out[c], t);
+  }
+}
+
+}  // namespace mpmae

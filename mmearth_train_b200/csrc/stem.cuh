@@ -1,0 +1,301 @@
+// Patch embedding of the sparse encoder (models/convnextv2_sparse.py:113-130):
+//   initial_conv = MinkowskiConvolution 3x3 (in_chans -> C0) + LayerNorm + GELU
+//   stem         = MinkowskiDepthwiseConvolution k = s = patch/8 + LayerNorm
+// evaluated on visible pixels only, reading the NCHW input directly (to_sparse is folded in:
+// MinkowskiOps.py:308-317).  The reference runs 9 gather-GEMM-scatter launches with atomics
+// (MinkowskiEngine/src/convolution_kernel.cu:114-180) plus a coordinate-map build.
+#pragma once
+#include "common.cuh"
+
+namespace mpmae {
+
+struct InitConvArgs {
+  const float *img;      // [B, Cin, S, S]
+  const float *kernel;   // [9, Cin, C0], k = kh + 3*kw
+  const float *bias;     // [C0]
+  float *chat;           // out [Rpre, C0] normalised conv output
+  float *rstd;           // out [Rpre]
+  const int *slot_of;    // [B*L]
+  const int *vis_patch;  // [B*V]
+  int32_t *flags;
+  Geo geo;
+  int S, Cin, C0, Ppre;  // Ppre = patch_size
+  float eps;
+};
+
+// stage the (8+2)^2 x Cin input window of an 8x8 pixel tile; masked patches and the image border read 0
+__device__ __forceinline__ void load_input_window(const InitConvArgs &p, int n, int gy0, int gx0, float *xin) {
+  for (int i = threadIdx.x; i < p.Cin * 100; i += blockDim.x) {
+    const int ci = i / 100, w = i - ci * 100;
+    const int wy = w / 10, wx = w - wy * 10;
+    const int gy = gy0 + wy - 1, gx = gx0 + wx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gx >= 0 && gy < p.S && gx < p.S) {
+      const int l = (gy / p.Ppre) * p.geo.G + gx / p.Ppre;
+      if (p.slot_of[n * p.geo.L + l] >= 0) v = p.img[(((int64_t)n * p.Cin + ci) * p.S + gy) * p.S + gx];
+    }
+    xin[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) initial_conv_fwd_kernel(InitConvArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int C0 = p.C0, Cin = p.Cin;
+  float *xin = smem;                       // [Cin][10][10]
+  float *wsm = xin + Cin * 100;            // [9*Cin][C0]
+  float *cbuf = wsm + 9 * Cin * C0;        // [64][C0+1]
+  const int tiles = (p.Ppre / 8) * (p.Ppre / 8);
+  const int pu = blockIdx.x / tiles, tile = blockIdx.x - pu * tiles;  // pu = n*V + slot
+  const int n = pu / p.geo.V;
+  const int l = p.vis_patch[pu];
+  int ty, tx;
+  morton_decode(tile, ty, tx);
+  const int gy0 = (l / p.geo.G) * p.Ppre + ty * 8, gx0 = (l % p.geo.G) * p.Ppre + tx * 8;
+  load_input_window(p, n, gy0, gx0, xin);
+  for (int i = threadIdx.x; i < 9 * Cin * C0; i += blockDim.x) wsm[i] = p.kernel[i];
+  __syncthreads();
+
+  const int pix = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  int iy, ix;
+  morton_decode(pix, iy, ix);
+  if (grp == 0) {
+    float s = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) s += fabsf(xin[ci * 100 + (iy + 1) * 10 + ix + 1]);
+    if (s == 0.f) atomicAdd(&p.flags[0], 1);
+  }
+  for (int q = grp; q * 8 < C0; q += 4) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = p.bias[q * 8 + j];
+    for (int kw = 0; kw < 3; ++kw)
+      for (int kh = 0; kh < 3; ++kh) {
+        const float *wk = wsm + (size_t)((kh + 3 * kw) * Cin) * C0 + q * 8;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float xv = xin[ci * 100 + (iy + kh) * 10 + ix + kw];
+          const float4 w0 = *reinterpret_cast<const float4 *>(wk + (size_t)ci * C0);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wk + (size_t)ci * C0 + 4);
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cbuf[pix * (C0 + 1) + q * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
+  for (int px = warp; px < 64; px += 8) {
+    const float *cr = cbuf + px * (C0 + 1);
+    float s = 0.f;
+    for (int c = lane; c < C0; c += 32) s += cr[c];
+    const float mean = warp_sum(s) / (float)C0;
+    float v = 0.f;
+    for (int c = lane; c < C0; c += 32) { const float d = cr[c] - mean; v += d * d; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C0 + p.eps);
+    for (int c = lane; c < C0; c += 32) p.chat[(row0 + px) * C0 + c] = (cr[c] - mean) * rstd;
+    if (lane == 0) p.rstd[row0 + px] = rstd;
+  }
+}
+
+// dW[k, ci, co] += sum_pix x[pix + off(k), ci] * dc[pix, co] ; db[co] += sum_pix dc[pix, co]
+struct InitConvWgradArgs {
+  InitConvArgs f;      // geometry + img + tables (kernel/bias/chat unused)
+  const float *dc;     // [Rpre, C0]
+  float *dkernel;      // [9, Cin, C0]
+  float *dbias;        // [C0]
+};
+__global__ void __launch_bounds__(256) initial_conv_wgrad_kernel(InitConvWgradArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const InitConvArgs &p = a.f;
+  const int C0 = p.C0, Cin = p.Cin;
+  float *xin = smem;                     // [Cin][100]
+  float *dcs = xin + Cin * 100;          // [64][C0]
+  float *dws = dcs + 64 * C0;            // [9*Cin + 1][C0]  (last row = bias)
+  const int nacc = (9 * Cin + 1) * C0;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) dws[i] = 0.f;
+  const int tiles = (p.Ppre / 8) * (p.Ppre / 8);
+  const int64_t units = (int64_t)p.geo.B * p.geo.V * tiles;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int pu = (int)(u / tiles), tile = (int)(u - (int64_t)pu * tiles);
+    const int n = pu / p.geo.V;
+    const int l = p.vis_patch[pu];
+    int ty, tx;
+    morton_decode(tile, ty, tx);
+    const int gy0 = (l / p.geo.G) * p.Ppre + ty * 8, gx0 = (l % p.geo.G) * p.Ppre + tx * 8;
+    __syncthreads();
+    load_input_window(p, n, gy0, gx0, xin);
+    const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
+    for (int i = threadIdx.x; i < 64 * C0; i += blockDim.x) dcs[i] = a.dc[row0 * C0 + i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nacc; idx += blockDim.x) {
+      const int kc = idx / C0, co = idx - kc * C0;
+      float acc = 0.f;
+      if (kc == 9 * Cin) {
+        for (int px = 0; px < 64; ++px) acc += dcs[px * C0 + co];
+      } else {
+        const int k = kc / Cin, ci = kc - k * Cin;
+        const int kh = k % 3, kw = k / 3;
+        for (int px = 0; px < 64; ++px) {
+          int iy, ix;
+          morton_decode(px, iy, ix);
+          acc = fmaf(xin[ci * 100 + (iy + kh) * 10 + ix + kw], dcs[px * C0 + co], acc);
+        }
+      }
+      dws[idx] += acc;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * Cin * C0; i += blockDim.x) atomicAdd(&a.dkernel[i], dws[i]);
+  for (int c = threadIdx.x; c < C0; c += blockDim.x) atomicAdd(&a.dbias[c], dws[9 * Cin * C0 + c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StemArgs {
+  const float *chat;   // [Rpre, C0]
+  const float *rstd_c; // [Rpre]
+  const float *ln0_w, *ln0_b;  // initial_conv.1.ln
+  const float *kernel; // [s*s, C0]
+  const float *bias;   // [C0]
+  const float *ln1_w, *ln1_b;  // stem.1.ln
+  float *shat;         // [R0, C0]
+  float *rstd_s;       // [R0]
+  float *x0;           // [R0, C0]
+  int64_t R0;
+  int C0, s2;          // s2 = s*s children per output pixel
+  float eps;
+};
+constexpr int kStemMaxPerLane = 4;  // C0 <= 128
+
+__global__ void stem_fwd_kernel(StemArgs p) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= p.R0) return;
+  const int lane = threadIdx.x & 31, C0 = p.C0;
+  float sv[kStemMaxPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < kStemMaxPerLane; ++q) {
+    const int c = lane + 32 * q;
+    sv[q] = 0.f;
+    if (c < C0) {
+      float acc = p.bias[c];
+      for (int j = 0; j < p.s2; ++j) {
+        const float t = p.chat[(r * p.s2 + j) * C0 + c] * p.ln0_w[c] + p.ln0_b[c];
+        acc = fmaf(gelu_f(t), p.kernel[j * C0 + c], acc);
+      }
+      sv[q] = acc; sum += acc;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C0;
+  float var = 0.f;
+#pragma unroll
+  for (int q = 0; q < kStemMaxPerLane; ++q)
+    if (lane + 32 * q < C0) { const float d = sv[q] - mean; var += d * d; }
+  const float rstd = rsqrtf(warp_sum(var) / (float)C0 + p.eps);
+#pragma unroll
+  for (int q = 0; q < kStemMaxPerLane; ++q) {
+    const int c = lane + 32 * q;
+    if (c < C0) {
+      const float nh = (sv[q] - mean) * rstd;
+      p.shat[r * C0 + c] = nh;
+      p.x0[r * C0 + c] = nh * p.ln1_w[c] + p.ln1_b[c];
+    }
+  }
+  if (lane == 0) p.rstd_s[r] = rstd;
+}
+
+struct StemBwdArgs {
+  StemArgs f;
+  const float *dx0;   // [R0, C0]
+  float *dc;          // out [Rpre, C0] gradient at the initial conv output (pre-LN)
+  float *d_ln0_w, *d_ln0_b, *d_kernel, *d_bias, *d_ln1_w, *d_ln1_b;
+};
+// per-lane partial column sums: [0]=d_ln1_w [1]=d_ln1_b [2]=d_bias [3]=d_ln0_w [4]=d_ln0_b [5..5+s2)=d_kernel[j]
+__global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
+  extern __shared__ float red[];  // [(5 + s2)][C0]
+  const StemArgs &p = a.f;
+  const int C0 = p.C0, s2 = p.s2, nvec = 5 + s2;
+  for (int i = threadIdx.x; i < nvec * C0; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float part[9][kStemMaxPerLane];
+#pragma unroll
+  for (int v = 0; v < 9; ++v)
+#pragma unroll
+    for (int q = 0; q < kStemMaxPerLane; ++q) part[v][q] = 0.f;
+
+  for (int64_t r = (int64_t)blockIdx.x * nw + warp; r < p.R0; r += (int64_t)gridDim.x * nw) {
+    // LN1 backward
+    float dsh[kStemMaxPerLane], nh[kStemMaxPerLane];
+    float s1 = 0.f, s2s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kStemMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      dsh[q] = 0.f; nh[q] = 0.f;
+      if (c < C0) {
+        const float g = a.dx0[r * C0 + c];
+        nh[q] = p.shat[r * C0 + c];
+        part[0][q] += g * nh[q];
+        part[1][q] += g;
+        dsh[q] = g * p.ln1_w[c];
+        s1 += dsh[q]; s2s += dsh[q] * nh[q];
+      }
+    }
+    s1 = warp_sum(s1) / (float)C0; s2s = warp_sum(s2s) / (float)C0;
+    const float rs = p.rstd_s[r];
+    float ds[kStemMaxPerLane];
+#pragma unroll
+    for (int q = 0; q < kStemMaxPerLane; ++q) {
+      ds[q] = (lane + 32 * q < C0) ? rs * (dsh[q] - s1 - nh[q] * s2s) : 0.f;
+      part[2][q] += ds[q];
+    }
+    // children
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= s2) break;
+      const int64_t rc = r * s2 + j;
+      float dch[kStemMaxPerLane], ch[kStemMaxPerLane];
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < kStemMaxPerLane; ++q) {
+        const int c = lane + 32 * q;
+        dch[q] = 0.f; ch[q] = 0.f;
+        if (c < C0) {
+          ch[q] = p.chat[rc * C0 + c];
+          const float t = ch[q] * p.ln0_w[c] + p.ln0_b[c];
+          const float gj = gelu_f(t);
+          part[5 + j][q] += ds[q] * gj;  // d_kernel[j]; s2 <= 4 (patch 8 or 16)
+          const float dt = ds[q] * p.kernel[j * C0 + c] * gelu_grad_f(t);
+          part[3][q] += dt * ch[q];
+          part[4][q] += dt;
+          dch[q] = dt * p.ln0_w[c];
+          t1 += dch[q]; t2 += dch[q] * ch[q];
+        }
+      }
+      t1 = warp_sum(t1) / (float)C0; t2 = warp_sum(t2) / (float)C0;
+      const float rc_std = p.rstd_c[rc];
+#pragma unroll
+      for (int q = 0; q < kStemMaxPerLane; ++q) {
+        const int c = lane + 32 * q;
+        if (c < C0) a.dc[rc * C0 + c] = rc_std * (dch[q] - t1 - ch[q] * t2);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 9; ++v)
+#pragma unroll
+    for (int q = 0; q < kStemMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      if (v < nvec && c < C0) atomicAdd(&red[v * C0 + c], part[v][q]);
+    }
+  __syncthreads();
+  float *dst[5] = {a.d_ln1_w, a.d_ln1_b, a.d_bias, a.d_ln0_w, a.d_ln0_b};
+  for (int i = threadIdx.x; i < nvec * C0; i += blockDim.x) {
+    const int v = i / C0, c = i - v * C0;
+    if (v < 5) atomicAdd(&dst[v][c], red[i]);
+    else atomicAdd(&a.d_kernel[(v - 5) * C0 + c], red[i]);
+  }
+}
+
+}  // namespace mpmae
