@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""MP-MAE pretraining throughput (samples/s) -- BASELINE.json metric, contract in the task statement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config cfg2]
+
+One "step" = the whole hot path for one batch: FCMAE forward + hand-derived backward (+ flat-buffer gradient
+all-reduce when N > 1) + fused AdamW, through the reference-facing module API (model(samples) ->
+loss.backward() -> optimizer.step()).  `value` is measured with batches resident in HBM, `e2e` with host
+(pinned) batches copied in every step and the loss read back.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {  # BASELINE.json configs (per-GPU batch, weak scaling)
+    "cfg1": dict(model="convnextv2_atto", img_size=56, patch_size=8, out_modalities=["sentinel2"], loss_aggr="unweighted", batch=8),
+    "cfg2": dict(model="convnextv2_atto", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty", batch=256),
+    "cfg3": dict(model="convnextv2_atto", img_size=112, patch_size=16, out_modalities=None, loss_aggr="uncertainty", batch=128),
+    "cfg4": dict(model="convnextv2_tiny", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty", batch=64),
+}
+# algorithmic work per sample (fwd+bwd): GFLOP, MB
+ALGO = {"cfg1": (2.078, 38.67), "cfg2": (2.389, 30.93), "cfg3": (3.756, 39.57), "cfg4": (11.573, 100.62)}
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except Exception:
+    METRIC = "pretrain samples/sec (12\u00d756\u00d756, atto) at 1/2/4/8 B200; loss match vs ref"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_throughput(cfg, steps, warmup, max_seconds=25.0, bs=8):
+    """The CPU restatement of the reference path (oracle port) on the host cores: fwd + bwd + AdamW at bs 8."""
+    import torch
+    from oracle import fcmae_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
+    orc = fo.build_oracle(model=cfg["model"], img_size=cfg["img_size"], patch_size=cfg["patch_size"],
+                          out_modalities=cfg["out_modalities"], loss_aggr=cfg["loss_aggr"])
+    fo.init_like_reference(orc, seed=3)
+    seen, params = set(), []
+    for p in orc.parameters():
+        if id(p) not in seen:
+            seen.add(id(p)); params.append(p)
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    batch = fo.synthetic_batch(bs, cfg["img_size"], cfg["out_modalities"], seed=1234)
+
+    def step():
+        loss = orc(batch, mask_ratio=0.6)[0]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0, n = time.perf_counter(), 0
+    while n < steps and (n == 0 or time.perf_counter() - t0 < max_seconds):
+        step(); n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=bs * n / dt, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"oracle (CPU restatement of the reference FCMAE sparse path) fwd+bwd+AdamW, bs {bs}, {n} steps, "
+                       f"{dt / n * 1e3:.0f} ms/step; the reference itself cannot run here (MinkowskiEngine GPU-only/unbuildable)"), dt / n * 1e3, n
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[a.config]
+    cb, ms, n = oracle_cpu_throughput(cfg, a.steps, max(a.warmup, 1), max_seconds=150.0)
+    line = {"metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": a.gpus, "steps": n, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{a.config}: {cfg['model']} S2->{'all' if cfg['out_modalities'] is None else '+'.join(cfg['out_modalities'])} "
+                                   f"{cfg['img_size']}/p{cfg['patch_size']} {cfg['loss_aggr']}, bounded CPU sample bs 8"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    import mmearth_train_b200 as mp
+    from mmearth_train_b200.optim import FlatAdamW
+    from oracle import fcmae_oracle as fo   # synthetic_batch / make_args only (data + config helpers, not compute)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[a.config]
+    B = cfg["batch"]
+    K, W = a.steps, max(a.warmup, 3)
+
+    args = fo.make_args(cfg["out_modalities"], cfg["loss_aggr"])
+    torch.manual_seed(0 + rank)                                       # main_pretrain.py:202-203
+    lf = mp.UncertaintyWeightingStrategy(len(args.out_modalities)) if cfg["loss_aggr"] == "uncertainty" else None
+    model = getattr(mp, cfg["model"])(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True,
+                                      patch_size=cfg["patch_size"], img_size=cfg["img_size"], args=args, loss_fn=lf,
+                                      gemm_backend=a.backend).to(dev)
+    if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's, main_pretrain.py:306-310)
+        dist.broadcast(model.flat_params, 0)
+    opt = FlatAdamW(model, lr=1.5e-4 * B * world / 256, betas=(0.9, 0.95), weight_decay=0.05)
+
+    NB = 4
+    host = [fo.synthetic_batch(B, cfg["img_size"], cfg["out_modalities"], seed=1234 + rank * 100 + i) for i in range(NB)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step_resident(i):
+        loss = model(resident[i % NB], mask_ratio=0.6)[0]
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def step_e2e(i):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % NB].items()}
+        loss = model(b, mask_ratio=0.6)[0]
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item()                                            # D2H read of the step's result
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for i in range(W):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, K)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, K)
+    loss_val = step_e2e(0)
+    flags = model.input_flags()
+
+    # ---- per-kernel device times (CUDA events on the launching stream inside the library), rank 0
+    plan = model.last_run["plan"]
+    prof_steps = 3
+    torch.cuda.synchronize()
+    plan.profile_begin()
+    for i in range(prof_steps):
+        step_resident(i)
+    rows = plan.profile_report()
+    launches_per_step = plan.launches(False) + plan.launches(True) + 1   # + fused AdamW
+
+    if rank == 0:
+        pk = peaks()
+        gf, mb = ALGO[a.config]
+        sps = B * world * K / (ms / 1e3)
+        sps_e2e = B * world * K / (ms_e2e / 1e3)
+        tot_ms = sum(r[2] for r in rows)
+        kern = [r for r in rows if r[0] != "memset"]
+        top = max(kern, key=lambda r: r[2])
+        t_s = top[2] / top[1] / 1e3                                      # average launch duration
+        hbm_time = top[3] / top[1] / (pk["hbm"] * 1e9)
+        tf32_peak = pk["bf16_sustained"] / 2                            # TF32 dense = 1/2 bf16
+        tc_time = top[4] / top[1] / (tf32_peak * 1e12)
+        if tc_time > hbm_time:
+            roof = {"bound": "tensor", "achieved": top[4] / top[1] / t_s / 1e12, "peak": tf32_peak, "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": top[3] / top[1] / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof.update({"traffic": None, "kernel": top[0], "launches_per_step": top[1] // prof_steps,
+                     "avg_launch_ms": top[2] / top[1], "share_of_step": top[2] / tot_ms, "peak_source": pk["src"],
+                     "step_hbm_frac": (mb * 1e6 * B * K / (ms / 1e3)) / (pk["hbm"] * 1e9) / 1.0,
+                     "step_tf32_frac": (gf * 1e9 * B * K / (ms / 1e3)) / (tf32_peak * 1e12),
+                     "kernels": [{"name": r[0], "launches": r[1] // prof_steps, "ms_per_step": r[2] / prof_steps,
+                                  "GBps": (r[3] / (r[2] / 1e3) / 1e9) if r[2] > 0 else None,
+                                  "TFLOPs": (r[4] / (r[2] / 1e3) / 1e12) if r[2] > 0 else None}
+                                 for r in sorted(rows, key=lambda r: -r[2])[:12]]})
+        if world == 1 and not a.no_cpu_baseline:
+            cb, _, _ = oracle_cpu_throughput(cfg, 12, 1, max_seconds=20.0)
+        else:
+            cb = None
+        line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{a.config}: {cfg['model']} S2->{'all_mod' if cfg['out_modalities'] is None else '+'.join(cfg['out_modalities'])} "
+                                       f"{cfg['img_size']}x{cfg['img_size']} patch{cfg['patch_size']} mask 0.6 {cfg['loss_aggr']} loss, "
+                                       f"bs {B}/GPU, step = fwd + bwd" + (" + flat NCCL all-reduce" if world > 1 else "") + " + fused AdamW",
+                           "global_batch": B * world, "gemm_backend": model.gemm_backend,
+                           "l2": f"{NB} rotating resident batches ({h2d_bytes * NB / 1e6:.0f} MB) and a {plan.workspace_bytes / 1e9:.2f} GB "
+                                 "activation workspace, both >> 126 MB L2; no explicit flush",
+                           "parallelism": f"dp{world}"},
+                "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+                "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "loss": loss_val, "input_flags": flags}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

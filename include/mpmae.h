@@ -92,6 +92,11 @@ int64_t mpmae_param_total(const mpmae_plan *plan);
 int32_t mpmae_param_count(const mpmae_plan *plan);
 int mpmae_param_info(const mpmae_plan *plan, int32_t index, char *name, int32_t name_cap,
                      int64_t shape[4], int32_t *ndim, int64_t *offset);
+/* 1 if AdamW weight decay applies to parameter `index` under the rule the reference uses
+ * (timm param_groups_weight_decay, main_pretrain.py:312-319: no decay for ndim <= 1 or "*.bias") */
+int32_t mpmae_param_decay(const mpmae_plan *plan, int32_t index);
+/* visible patches per sample = int(L * (1 - mask_ratio)), models/fcmae.py:216-217 */
+int32_t mpmae_visible_patches(const mpmae_plan *plan);
 
 size_t mpmae_workspace_bytes(const mpmae_plan *plan);
 int32_t mpmae_pred_pixel_cols(const mpmae_plan *plan);
@@ -103,11 +108,24 @@ int32_t mpmae_pred_col_offset(const mpmae_plan *plan, int32_t mod);
 int mpmae_tap_info(const mpmae_plan *plan, const char *name, int64_t *byte_offset, int64_t *rows,
                    int64_t *cols);
 
+int32_t mpmae_tap_count(const mpmae_plan *plan);
+int mpmae_tap_name(const mpmae_plan *plan, int32_t index, char *name, int32_t name_cap);
+
 /* number of kernels launched by one forward / backward call (bench.py "gpu_launches") */
 int32_t mpmae_launch_count(const mpmae_plan *plan, int32_t backward);
 
+/* Per-launch device timing (bench.py roofline leg): after mpmae_profile_begin every launch of
+ * mpmae_forward / mpmae_backward is bracketed by CUDA events on the caller's stream; mpmae_profile_report
+ * synchronises on the last event, stops profiling and writes CSV "name,launches,ms,alg_bytes,alg_flops"
+ * (algorithmic bytes/flops per SURVEY.md section 8d) aggregated by kernel call site. */
+int mpmae_profile_begin(mpmae_plan *plan);
+int mpmae_profile_report(mpmae_plan *plan, char *buf, int32_t cap);
+
 /* FCMAE.forward: mask -> sparse encoder -> decoder -> heads -> losses.  Asynchronous on `stream`. */
 int mpmae_forward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
+/* FCMAE.forward_encoder (models/fcmae.py:242-247): mask + sparse encoder only; needs params, workspace,
+ * noise, s2_input, mask, flags.  Read the features with mpmae_encoder_features. */
+int mpmae_forward_encoder(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
 /* hand-derived backward of the same step; accumulates into io->grads.  Must follow mpmae_forward
  * on the same workspace. */
 int mpmae_backward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
@@ -118,6 +136,13 @@ int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw
 /* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias) */
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
                     int64_t M, int32_t N, int32_t K, void *cuda_stream);
+
+/* Fused AdamW over flat buffers (torch.optim.AdamW semantics; the reference builds its optimizer at
+ * main_pretrain.py:312-320).  decay_mask: one byte per element (null = decay everything);
+ * grad_scale_inv multiplies the gradient first (GradScaler unscale, helpers.py:485-497); step >= 1. */
+int mpmae_adamw_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                     const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int64_t step, float grad_scale_inv, void *cuda_stream);
 
 #ifdef __cplusplus
 }

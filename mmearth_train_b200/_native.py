@@ -1,0 +1,171 @@
+"""ctypes binding of the C-ABI library ``lib/libmpmae.so`` (``include/mpmae.h``).
+
+The library is the product: there is no Python / PyTorch fallback.  If it has not been built
+(``python -c "import __graft_entry__ as g; g.build()"`` or ``mmearth_train_b200.build.build()``)
+importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_MOD = 16
+PIXEL_CONTINUOUS, PIXEL_CATEGORICAL, IMAGE_CATEGORICAL, IMAGE_CONTINUOUS = 0, 1, 2, 3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmpmae.so")
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("img_size", C.c_int32), ("patch_size", C.c_int32), ("in_chans", C.c_int32),
+        ("depths", C.c_int32 * 4), ("dims", C.c_int32 * 4), ("dec_dim", C.c_int32), ("dec_depth", C.c_int32),
+        ("mask_ratio", C.c_float), ("loss_aggr", C.c_int32), ("n_mod", C.c_int32),
+        ("mod_kind", C.c_int32 * MAX_MOD), ("mod_chans", C.c_int32 * MAX_MOD), ("mod_norm_pix", C.c_int32 * MAX_MOD),
+        ("gemm_backend", C.c_int32),
+    ]
+
+
+class IO(C.Structure):
+    _fields_ = [
+        ("params", C.c_void_p), ("grads", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("noise", C.c_void_p), ("s2_input", C.c_void_p), ("targets", C.c_void_p * MAX_MOD),
+        ("mask", C.c_void_p), ("pred_pixel", C.c_void_p), ("pred_image", C.c_void_p), ("losses", C.c_void_p),
+        ("grad_out", C.c_void_p), ("flags", C.c_void_p),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built.  Run `python -c \"import "
+            "__graft_entry__ as g; g.build()\"` at the repository root (needs nvcc).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    P, I32, I64, F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sig = {
+        "mpmae_last_error": (C.c_char_p, []),
+        "mpmae_version": (C.c_int, []),
+        "mpmae_plan_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(P)]),
+        "mpmae_plan_destroy": (None, [P]),
+        "mpmae_param_total": (I64, [P]),
+        "mpmae_param_count": (I32, [P]),
+        "mpmae_param_info": (C.c_int, [P, I32, C.c_char_p, I32, C.POINTER(I64), C.POINTER(I32), C.POINTER(I64)]),
+        "mpmae_param_decay": (I32, [P, I32]),
+        "mpmae_visible_patches": (I32, [P]),
+        "mpmae_workspace_bytes": (C.c_size_t, [P]),
+        "mpmae_pred_pixel_cols": (I32, [P]),
+        "mpmae_pred_image_cols": (I32, [P]),
+        "mpmae_pred_col_offset": (I32, [P, I32]),
+        "mpmae_tap_info": (C.c_int, [P, C.c_char_p, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
+        "mpmae_tap_count": (I32, [P]),
+        "mpmae_tap_name": (C.c_int, [P, I32, C.c_char_p, I32]),
+        "mpmae_launch_count": (I32, [P, I32]),
+        "mpmae_profile_begin": (C.c_int, [P]),
+        "mpmae_profile_report": (C.c_int, [P, C.c_char_p, I32]),
+        "mpmae_forward": (C.c_int, [P, C.POINTER(IO), P]),
+        "mpmae_forward_encoder": (C.c_int, [P, C.POINTER(IO), P]),
+        "mpmae_backward": (C.c_int, [P, C.POINTER(IO), P]),
+        "mpmae_encoder_features": (C.c_int, [P, C.POINTER(IO), P, P]),
+        "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P]),
+        "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan_destroy", "mpmae_param_total",
+           "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
+           "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
+           "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
+           "mpmae_forward_encoder", "mpmae_backward", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_adamw_step"]
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise NativeError(f"{what}: mpmae error {rc}: {lib.mpmae_last_error().decode()}")
+
+
+class Plan:
+    """Owning wrapper of ``mpmae_plan``: parameter layout, workspace layout and launch plan."""
+
+    def __init__(self, cfg: Cfg):
+        self.cfg = cfg
+        h = C.c_void_p()
+        check(lib.mpmae_plan_create(C.byref(cfg), C.byref(h)), "mpmae_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h and lib is not None:          # lib is None during interpreter shutdown
+            lib.mpmae_plan_destroy(h)
+            self.handle = None
+
+    def params(self):
+        """[(name, shape, offset, decay)] -- reference state-dict names (heads as ``pred_dict.#<i>``)."""
+        out = []
+        name = C.create_string_buffer(192)
+        shape = (C.c_int64 * 4)()
+        nd, off = C.c_int32(), C.c_int64()
+        for i in range(lib.mpmae_param_count(self.handle)):
+            check(lib.mpmae_param_info(self.handle, i, name, 192, shape, C.byref(nd), C.byref(off)), "param_info")
+            out.append((name.value.decode(), tuple(shape[: nd.value]), off.value, lib.mpmae_param_decay(self.handle, i)))
+        return out
+
+    @property
+    def param_total(self) -> int:
+        return lib.mpmae_param_total(self.handle)
+
+    @property
+    def workspace_bytes(self) -> int:
+        return lib.mpmae_workspace_bytes(self.handle)
+
+    @property
+    def visible(self) -> int:
+        return lib.mpmae_visible_patches(self.handle)
+
+    @property
+    def npix(self) -> int:
+        return lib.mpmae_pred_pixel_cols(self.handle)
+
+    @property
+    def nimg(self) -> int:
+        return lib.mpmae_pred_image_cols(self.handle)
+
+    def col_offset(self, mod: int) -> int:
+        return lib.mpmae_pred_col_offset(self.handle, mod)
+
+    def tap(self, name: str):
+        off, rows, cols = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.mpmae_tap_info(self.handle, name.encode(), C.byref(off), C.byref(rows), C.byref(cols)), "tap_info")
+        return off.value, rows.value, cols.value
+
+    def tap_names(self):
+        buf = C.create_string_buffer(128)
+        out = []
+        for i in range(lib.mpmae_tap_count(self.handle)):
+            check(lib.mpmae_tap_name(self.handle, i, buf, 128), "tap_name")
+            out.append(buf.value.decode())
+        return out
+
+    def profile_begin(self) -> None:
+        check(lib.mpmae_profile_begin(self.handle), "profile_begin")
+
+    def profile_report(self):
+        """[(name, launches, ms, alg_bytes, alg_flops)] since profile_begin; stops profiling."""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib.mpmae_profile_report(self.handle, buf, len(buf)), "profile_report")
+        rows = []
+        for line in buf.value.decode().strip().split("\n")[1:]:
+            n, c, ms, b, f = line.split(",")
+            rows.append((n, int(c), float(ms), float(b), float(f)))
+        return rows
+
+    def launches(self, backward: bool) -> int:
+        return lib.mpmae_launch_count(self.handle, 1 if backward else 0)

@@ -392,4 +392,16 @@ __global__ void colsum_kernel(const float *__restrict__ x, float *__restrict__ o
   }
 }
 
+// out[b, k] = sum_n A[b, n] * cs[n] * W[n, k]   (image-head dX: nimg is ragged, e.g. 878, so this tiny
+// product does not go through the tiled GEMMs).  One thread per output, coalesced over k.
+__global__ void small_gemm_nt_kernel(const float *__restrict__ A, const float *__restrict__ W, const float *__restrict__ cs,
+                                     float *__restrict__ out, int Brows, int Kout, int Nred) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)Brows * Kout) return;
+  const int b = (int)(t / Kout), k = (int)(t - (int64_t)b * Kout);
+  float acc = 0.f;
+  for (int n = 0; n < Nred; ++n) acc = fmaf(A[(int64_t)b * Nred + n] * cs[n], W[(int64_t)n * Kout + k], acc);
+  out[t] = acc;
+}
+
 }  // namespace mpmae

@@ -1,0 +1,1067 @@
+// C ABI of the B200-native MP-MAE (FCMAE) pretraining step: plan, forward, hand-derived backward.
+//
+// Replaces models/fcmae.py:FCMAE.forward (414-456) + autograd backward of the reference:
+//   mask (fcmae.py:214-231) -> SparseConvNeXtV2 (convnextv2_sparse.py:191-220) -> proj + mask token
+//   + shared decoder block + heads (fcmae.py:249-265) -> losses (fcmae.py:267-412, custom_loss.py:19-30)
+// The step is a fixed launch sequence on the caller's stream; the library allocates no device
+// memory, never synchronises and reports errors by return code (include/mpmae.h).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mpmae.h"
+#include "common.cuh"
+#include "dwconv.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "loss.cuh"
+#include "misc_kernels.cuh"
+#include "optim.cuh"
+#include "stem.cuh"
+
+using namespace mpmae;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct ParamRef {
+  std::string name;
+  int64_t shape[4];
+  int ndim;
+  int64_t off, numel;
+  int decay;  // AdamW weight decay applies (timm rule: ndim > 1 and not *.bias)
+};
+struct BlockP { int64_t dw_k, dw_b, ln_w, ln_b, w1, b1, gamma, beta, w2, b2; };
+struct DsP { int64_t ln_w, ln_b, k, b; };
+struct Tap { int64_t off_bytes, rows, cols; };
+
+// per-block saved activations / statistics (float offsets into the workspace)
+struct BlockW { int64_t vhat, rstd, a, h, g, y, gsq, nx, scale, denom; };
+
+}  // namespace
+
+struct mpmae_plan {
+  mpmae_cfg cfg;
+  Geo geo;
+  int S, Ppre, s_stem, P[4], D;
+  int64_t R[4], Rpre, cells;
+  std::vector<ParamRef> params;
+  int64_t n_params = 0;
+  int64_t ic_k, ic_b, ic_lnw, ic_lnb, st_k, st_b, st_lnw, st_lnb;
+  DsP ds[3];
+  std::vector<BlockP> blk[4];
+  int64_t proj_w, proj_b, tok;
+  std::vector<BlockP> dec;
+  int64_t pixw = -1, pixb = -1, imgw = -1, imgb = -1, lnt_w = -1, lnt_b = -1, logv = -1;
+  int npix = 0, nimg = 0;
+  int col_off[MPMAE_MAX_MOD], col_len[MPMAE_MAX_MOD], is_img[MPMAE_MAX_MOD];
+  // workspace
+  std::map<std::string, Tap> taps;
+  int64_t ws_floats = 0;
+  int64_t o_slot, o_vis, o_chat, o_rstd_c, o_shat, o_rstd_s, o_x0;
+  int64_t o_ds_xhat[3], o_ds_rstd[3], o_ds_out[3];
+  std::vector<BlockW> bw[4];
+  std::vector<BlockW> dw;
+  int64_t o_z, o_xd, o_pooled, o_pool_rstd, o_dpix, o_dimg, o_acc, o_cs_pix, o_cs_img, o_dpooled;
+  int64_t o_zero_begin, o_zero_end;  // statistics region cleared at the start of forward
+  int64_t o_wf, o_wft, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
+  int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
+  int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
+  int launches_fwd = 0, launches_bwd = 0;
+  // optional per-launch CUDA-event profile (bench.py roofline leg)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<const char *> prof_name;
+  std::vector<double> prof_bytes, prof_flops;
+  int prof_n = 0;
+};
+
+namespace {
+
+int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int64_t add_param(mpmae_plan *pl, const std::string &name, std::initializer_list<int64_t> shape) {
+  ParamRef r;
+  r.name = name;
+  r.ndim = (int)shape.size();
+  r.numel = 1;
+  int i = 0;
+  for (int64_t s : shape) { r.shape[i++] = s; r.numel *= s; }
+  for (; i < 4; ++i) r.shape[i] = 1;
+  r.off = pl->n_params;
+  const bool is_bias = name.size() >= 5 && name.compare(name.size() - 5, 5, ".bias") == 0;
+  r.decay = (r.ndim > 1 && !is_bias) ? 1 : 0;
+  pl->n_params = align_up(pl->n_params + r.numel, 4);
+  pl->params.push_back(r);
+  return r.off;
+}
+
+int64_t ws_alloc(mpmae_plan *pl, const char *name, int64_t rows, int64_t cols) {
+  const int64_t off = pl->ws_floats;
+  pl->ws_floats = align_up(pl->ws_floats + rows * cols, 64);  // 256-byte granularity
+  if (name) pl->taps[name] = Tap{off * 4, rows, cols};
+  return off;
+}
+
+void build_params(mpmae_plan *pl) {
+  const mpmae_cfg &c = pl->cfg;
+  const int *dm = c.dims;
+  char nm[160];
+  pl->ic_k = add_param(pl, "encoder.initial_conv.0.kernel", {9, c.in_chans, dm[0]});
+  pl->ic_b = add_param(pl, "encoder.initial_conv.0.bias", {1, dm[0]});
+  pl->ic_lnw = add_param(pl, "encoder.initial_conv.1.ln.weight", {dm[0]});
+  pl->ic_lnb = add_param(pl, "encoder.initial_conv.1.ln.bias", {dm[0]});
+  pl->st_k = add_param(pl, "encoder.stem.0.kernel", {pl->s_stem * pl->s_stem, dm[0]});
+  pl->st_b = add_param(pl, "encoder.stem.0.bias", {1, dm[0]});
+  pl->st_lnw = add_param(pl, "encoder.stem.1.ln.weight", {dm[0]});
+  pl->st_lnb = add_param(pl, "encoder.stem.1.ln.bias", {dm[0]});
+  for (int i = 0; i < 3; ++i) {
+    snprintf(nm, sizeof nm, "encoder.downsample_layers.%d.0.ln.weight", i);
+    pl->ds[i].ln_w = add_param(pl, nm, {dm[i]});
+    snprintf(nm, sizeof nm, "encoder.downsample_layers.%d.0.ln.bias", i);
+    pl->ds[i].ln_b = add_param(pl, nm, {dm[i]});
+    snprintf(nm, sizeof nm, "encoder.downsample_layers.%d.1.kernel", i);
+    pl->ds[i].k = add_param(pl, nm, {4, dm[i], dm[i + 1]});
+    snprintf(nm, sizeof nm, "encoder.downsample_layers.%d.1.bias", i);
+    pl->ds[i].b = add_param(pl, nm, {1, dm[i + 1]});
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < c.depths[i]; ++j) {
+      const int C = dm[i];
+      BlockP b;
+      auto N = [&](const char *leaf) {
+        snprintf(nm, sizeof nm, "encoder.stages.%d.%d.%s", i, j, leaf);
+        return std::string(nm);
+      };
+      b.dw_k = add_param(pl, N("dwconv.kernel"), {49, C});
+      b.dw_b = add_param(pl, N("dwconv.bias"), {1, C});
+      b.ln_w = add_param(pl, N("norm.ln.weight"), {C});
+      b.ln_b = add_param(pl, N("norm.ln.bias"), {C});
+      b.w1 = add_param(pl, N("pwconv1.linear.weight"), {4 * C, C});
+      b.b1 = add_param(pl, N("pwconv1.linear.bias"), {4 * C});
+      b.gamma = add_param(pl, N("grn.gamma"), {1, 4 * C});
+      b.beta = add_param(pl, N("grn.beta"), {1, 4 * C});
+      b.w2 = add_param(pl, N("pwconv2.linear.weight"), {C, 4 * C});
+      b.b2 = add_param(pl, N("pwconv2.linear.bias"), {C});
+      pl->blk[i].push_back(b);
+    }
+  const int D = c.dec_dim;
+  pl->proj_w = add_param(pl, "proj.weight", {D, dm[3], 1, 1});
+  pl->proj_b = add_param(pl, "proj.bias", {D});
+  pl->tok = add_param(pl, "mask_token", {1, D, 1, 1});
+  for (int k = 0; k < c.dec_depth; ++k) {
+    BlockP b;
+    auto N = [&](const char *leaf) {
+      snprintf(nm, sizeof nm, "decoder.%d.%s", k, leaf);  // aliased decoder_dict.<mod>.<k>.* on the host side
+      return std::string(nm);
+    };
+    b.dw_k = add_param(pl, N("dwconv.weight"), {D, 1, 7, 7});
+    b.dw_b = add_param(pl, N("dwconv.bias"), {D});
+    b.ln_w = add_param(pl, N("norm.weight"), {D});
+    b.ln_b = add_param(pl, N("norm.bias"), {D});
+    b.w1 = add_param(pl, N("pwconv1.weight"), {4 * D, D});
+    b.b1 = add_param(pl, N("pwconv1.bias"), {4 * D});
+    b.gamma = add_param(pl, N("grn.gamma"), {1, 1, 1, 4 * D});
+    b.beta = add_param(pl, N("grn.beta"), {1, 1, 1, 4 * D});
+    b.w2 = add_param(pl, N("pwconv2.weight"), {D, 4 * D});
+    b.b2 = add_param(pl, N("pwconv2.bias"), {D});
+    pl->dec.push_back(b);
+  }
+  // heads: weights of all pixel heads contiguous (one [npix, D] matrix), then their biases; same for image heads
+  const int p2 = c.patch_size * c.patch_size;
+  for (int pass = 0; pass < 4; ++pass) {
+    const bool img = pass >= 2, bias = pass & 1;
+    for (int m = 0; m < c.n_mod; ++m) {
+      const bool m_img = c.mod_kind[m] == MPMAE_IMAGE_CATEGORICAL || c.mod_kind[m] == MPMAE_IMAGE_CONTINUOUS;
+      if (m_img != img) continue;
+      const int64_t n = m_img ? c.mod_chans[m] : (int64_t)p2 * c.mod_chans[m];
+      snprintf(nm, sizeof nm, "pred_dict.#%d.%s", m, bias ? "bias" : "weight");
+      int64_t off;
+      if (bias) {
+        off = add_param(pl, nm, {n});
+      } else if (m_img) {
+        off = add_param(pl, nm, {n, D});
+      } else {
+        off = add_param(pl, nm, {n, D, 1, 1});
+      }
+      // heads are packed without the 4-float alignment so that they form one matrix / one vector
+      pl->params.back().off = off;
+      if (!bias) {
+        if (m_img) { if (pl->imgw < 0) pl->imgw = off; }
+        else { if (pl->pixw < 0) pl->pixw = off; }
+      } else {
+        if (m_img) { if (pl->imgb < 0) pl->imgb = off; }
+        else { if (pl->pixb < 0) pl->pixb = off; }
+      }
+      // undo the alignment padding inside a group (weights: n*D is a multiple of 4; biases may not be)
+      pl->n_params = off + n * (bias ? 1 : D);
+    }
+    pl->n_params = align_up(pl->n_params, 4);
+  }
+  if (pl->nimg > 0) {
+    pl->lnt_w = add_param(pl, "layer_norm_tmp.weight", {D});
+    pl->lnt_b = add_param(pl, "layer_norm_tmp.bias", {D});
+  }
+  if (c.loss_aggr == 1) pl->logv = add_param(pl, "loss_fn.log_vars", {c.n_mod});
+}
+
+void note_wf(mpmae_plan *pl, int64_t n, int64_t k) {
+  if (n * k > pl->max_wf) pl->max_wf = n * k;
+  if (n > pl->max_n) pl->max_n = n;
+  if (k > pl->max_n) pl->max_n = k;
+}
+
+void build_workspace(mpmae_plan *pl) {
+  const mpmae_cfg &c = pl->cfg;
+  const int *dm = c.dims;
+  const int64_t B = c.batch, L = pl->geo.L, V = pl->geo.V, D = c.dec_dim;
+  char nm[96];
+  pl->o_slot = ws_alloc(pl, "slot_of", B * L, 1);
+  pl->o_vis = ws_alloc(pl, "vis_patch", B * V, 1);
+  pl->o_chat = ws_alloc(pl, "initial.chat", pl->Rpre, dm[0]);
+  pl->o_rstd_c = ws_alloc(pl, "initial.rstd", pl->Rpre, 1);
+  pl->o_shat = ws_alloc(pl, "stem.shat", pl->R[0], dm[0]);
+  pl->o_rstd_s = ws_alloc(pl, "stem.rstd", pl->R[0], 1);
+  pl->o_x0 = ws_alloc(pl, "stem.out", pl->R[0], dm[0]);
+  pl->max_rc = pl->Rpre * dm[0];
+  for (int i = 0; i < 4; ++i) {
+    const int64_t R = pl->R[i], C = dm[i];
+    if (R * C > pl->max_rc) pl->max_rc = R * C;
+    if (R * 4 * C > pl->max_rd) pl->max_rd = R * 4 * C;
+    if (i > 0) {
+      snprintf(nm, sizeof nm, "down%d.xhat", i);
+      pl->o_ds_xhat[i - 1] = ws_alloc(pl, nm, pl->R[i - 1], dm[i - 1]);
+      snprintf(nm, sizeof nm, "down%d.rstd", i);
+      pl->o_ds_rstd[i - 1] = ws_alloc(pl, nm, pl->R[i - 1], 1);
+      snprintf(nm, sizeof nm, "down%d.out", i);
+      pl->o_ds_out[i - 1] = ws_alloc(pl, nm, R, C);
+      note_wf(pl, C, 4 * dm[i - 1]);
+    }
+    note_wf(pl, 4 * C, C);
+    for (int j = 0; j < c.depths[i]; ++j) {
+      BlockW w;
+      auto N = [&](const char *leaf) { snprintf(nm, sizeof nm, "stage%d.block%d.%s", i, j, leaf); return nm; };
+      w.vhat = ws_alloc(pl, N("vhat"), R, C);
+      w.rstd = ws_alloc(pl, N("rstd"), R, 1);
+      w.a = ws_alloc(pl, N("a"), R, 4 * C);
+      w.h = ws_alloc(pl, N("h"), R, 4 * C);
+      w.g = -1;
+      w.y = ws_alloc(pl, N("y"), R, C);
+      w.nx = ws_alloc(pl, N("nx"), 1, 4 * C);
+      w.scale = ws_alloc(pl, N("scale"), 1, 4 * C);
+      w.denom = ws_alloc(pl, N("denom"), 1, 1);
+      pl->bw[i].push_back(w);
+    }
+  }
+  pl->o_z = ws_alloc(pl, "proj.z", B * V, D);
+  pl->o_xd = ws_alloc(pl, "decoder.in", pl->cells, D);
+  note_wf(pl, D, dm[3]);
+  note_wf(pl, 4 * D, D);
+  if (pl->cells * D > pl->max_rc) pl->max_rc = pl->cells * D;
+  if (pl->cells * 4 * D > pl->max_rd) pl->max_rd = pl->cells * 4 * D;
+  for (int k = 0; k < c.dec_depth; ++k) {
+    BlockW w;
+    auto N = [&](const char *leaf) { snprintf(nm, sizeof nm, "decoder.block%d.%s", k, leaf); return nm; };
+    w.vhat = ws_alloc(pl, N("vhat"), pl->cells, D);
+    w.rstd = ws_alloc(pl, N("rstd"), pl->cells, 1);
+    w.a = ws_alloc(pl, N("a"), pl->cells, 4 * D);
+    w.h = ws_alloc(pl, N("h"), pl->cells, 4 * D);
+    w.g = ws_alloc(pl, N("g"), pl->cells, 4 * D);
+    w.y = ws_alloc(pl, N("y"), pl->cells, D);
+    w.nx = ws_alloc(pl, N("nx"), B, 4 * D);
+    w.scale = ws_alloc(pl, N("scale"), B, 4 * D);
+    w.denom = ws_alloc(pl, N("denom"), B, 1);
+    pl->dw.push_back(w);
+  }
+  pl->o_pooled = ws_alloc(pl, "pooled", B, D);
+  pl->o_pool_rstd = ws_alloc(pl, "pool.rstd", pl->cells, 1);
+  pl->o_dpooled = ws_alloc(pl, nullptr, B, D);
+  pl->o_dpix = ws_alloc(pl, "dpix", pl->cells, pl->npix > 0 ? pl->npix : 1);
+  pl->o_dimg = ws_alloc(pl, "dimg", B, pl->nimg > 0 ? pl->nimg : 1);
+  pl->o_cs_pix = ws_alloc(pl, nullptr, 1, pl->npix + 4);
+  pl->o_cs_img = ws_alloc(pl, nullptr, 1, pl->nimg + 4);
+  if (pl->npix) note_wf(pl, pl->npix, D);
+  if (pl->nimg) note_wf(pl, pl->nimg, D);
+  // statistics accumulated with atomics in forward: one contiguous region, cleared by one memset
+  pl->o_zero_begin = pl->ws_floats;
+  pl->o_acc = ws_alloc(pl, "loss.acc", 1, 2 * MPMAE_MAX_MOD);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < c.depths[i]; ++j) {
+      snprintf(nm, sizeof nm, "stage%d.block%d.gsq", i, j);
+      pl->bw[i][j].gsq = ws_alloc(pl, nm, 1, 4 * dm[i]);
+    }
+  for (int k = 0; k < c.dec_depth; ++k) {
+    snprintf(nm, sizeof nm, "decoder.block%d.gsq", k);
+    pl->dw[k].gsq = ws_alloc(pl, nm, B, 4 * D);
+  }
+  pl->o_zero_end = pl->ws_floats;
+  // weight-fold scratch + backward temporaries
+  pl->o_wf = ws_alloc(pl, nullptr, 1, pl->max_wf);
+  pl->o_wft = ws_alloc(pl, nullptr, 1, pl->max_wf);
+  pl->o_bf = ws_alloc(pl, nullptr, 1, pl->max_n);
+  pl->o_dwf = ws_alloc(pl, nullptr, 1, pl->max_wf);
+  pl->o_dbf = ws_alloc(pl, nullptr, 1, pl->max_n);
+  pl->o_dsv = ws_alloc(pl, nullptr, B, pl->max_n);
+  pl->o_kg = ws_alloc(pl, nullptr, B, pl->max_n);
+  pl->o_g0 = ws_alloc(pl, nullptr, 1, pl->max_rc);
+  pl->o_g1 = ws_alloc(pl, nullptr, 1, pl->max_rc);
+  pl->o_gdv = ws_alloc(pl, nullptr, 1, pl->max_rc);
+  pl->o_gdu = ws_alloc(pl, nullptr, 1, pl->max_rc);
+  pl->o_gda = ws_alloc(pl, nullptr, 1, pl->max_rd);
+}
+
+// ---------------------------------------------------------------------------------------- launch context
+struct Ctx {
+  mpmae_plan *pl;
+  const mpmae_io *io;
+  cudaStream_t st;
+  float *ws;
+  const float *P;  // params
+  float *G;        // grads
+  int launches = 0;
+  cudaError_t err = cudaSuccess;
+  const char *where = "";
+  double pend_bytes = 0, pend_flops = 0;
+  float *w(int64_t off) const { return ws + off; }
+  const float *p(int64_t off) const { return P + off; }
+  float *g(int64_t off) const { return G + off; }
+  bool ok() const { return err == cudaSuccess; }
+  // algorithmic bytes / flops of the NEXT launch (SURVEY.md 8d accounting; read by the profiler only)
+  void acct(double bytes, double flops) { pend_bytes = bytes; pend_flops = flops; }
+  void mark(const char *what) {
+    if (!pl->prof_on) { pend_bytes = pend_flops = 0; return; }
+    if (pl->prof_n >= (int)pl->prof_ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pl->prof_ev.push_back(e);
+      pl->prof_name.push_back(what);
+      pl->prof_bytes.push_back(0);
+      pl->prof_flops.push_back(0);
+    }
+    pl->prof_name[pl->prof_n] = what;
+    pl->prof_bytes[pl->prof_n] = pend_bytes;
+    pl->prof_flops[pl->prof_n] = pend_flops;
+    cudaEventRecord(pl->prof_ev[pl->prof_n], st);
+    ++pl->prof_n;
+    pend_bytes = pend_flops = 0;
+  }
+  void check(cudaError_t e, const char *what, bool kernel = true) {
+    if (kernel) ++launches;
+    if (err == cudaSuccess && e != cudaSuccess) { err = e; where = what; }
+    mark(what);
+  }
+  void post(const char *what) { check(cudaGetLastError(), what); }
+  void zero(float *ptr, int64_t n, const char *what) {
+    acct(4.0 * n, 0);
+    check(cudaMemsetAsync(ptr, 0, n * sizeof(float), st), "memset", false);
+    (void)what;
+  }
+};
+
+template <int MODE>
+void gemm(Ctx &c, const GemmArgs &a, const char *what) {
+  if (!c.ok() || a.M <= 0) return;
+  {
+    const double mn = (double)a.M * a.N, io_mn = (MODE == EPI_STORE ? 1 + (a.resid ? 1 : 0) : MODE == EPI_GELU_SQ ? 2
+                                                  : MODE == EPI_DG ? 2 : 3);
+    c.acct(4.0 * ((double)a.M * a.K + (double)a.N * a.K + mn * io_mn), 2.0 * mn * a.K);
+  }
+  if (c.pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a)) {
+    c.check(launch_gemm_rows_tc<MODE>(a, c.pl->cfg.gemm_backend, c.st), what);
+  } else {
+    c.check(launch_gemm_rows_simt<MODE>(a, c.st), what);
+  }
+}
+void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
+  if (!c.ok()) return;
+  c.acct(4.0 * ((double)a.R * a.N + (double)a.R * a.K + (double)a.N * a.K), 2.0 * (double)a.R * a.N * a.K);
+  c.check(launch_gemm_wgrad(a, c.st), what);
+}
+void fold(Ctx &c, FoldArgs a, const char *what) {
+  if (!c.ok()) return;
+  fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
+  c.post(what);
+}
+void unfold(Ctx &c, UnfoldArgs a, const char *what) {
+  if (!c.ok()) return;
+  unfold_kernel<<<a.K, 256, 0, c.st>>>(a);
+  c.post(what);
+}
+int ew_grid(int64_t n4) {
+  int64_t g = cdiv64(n4, 256);
+  return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+// One ConvNeXt-V2 block forward (sparse: convnextv2_sparse.py:47-56; dense decoder: convnextv2.py:42-55).
+//   dense = per-sample GRN over L cells (eps 1e-4), torch conv weight layout; sparse = batch-global GRN (eps 1e-6)
+void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, int64_t R, int C, int P, bool dense) {
+  mpmae_plan *pl = c.pl;
+  const int D4 = 4 * C;
+  DwArgs d{};
+  d.x = x; d.w = c.p(bp.dw_k); d.bias = c.p(bp.dw_b); d.resid = nullptr;
+  if (dense) { d.w_sc = 49; d.w_skh = 7; d.w_skw = 1; } else { d.w_sc = 1; d.w_skh = C; d.w_skw = 7 * C; }
+  d.out = c.w(bw.vhat); d.rstd = c.w(bw.rstd);
+  d.slot_of = dense ? nullptr : reinterpret_cast<const int *>(c.w(pl->o_slot));
+  d.geo = pl->geo;
+  if (dense) d.geo.V = pl->geo.L;
+  d.P = P; d.C = C; d.flip = 0; d.do_ln = 1; d.eps = 1e-6f;
+  c.acct(4.0 * (2.0 * R * C + R + 50.0 * C), 2.0 * 49 * (double)R * C);
+  if (c.ok()) c.check(launch_dwconv_fwd(d, c.st), "dwconv_fwd");
+
+  FoldArgs f{};
+  f.W = c.p(bp.w1); f.s_n = C; f.s_k = 1; f.scale_k = c.p(bp.ln_w); f.shift_k = c.p(bp.ln_b);
+  f.bias = c.p(bp.b1); f.Wf = c.w(pl->o_wf); f.bf = c.w(pl->o_bf); f.N = D4; f.K = C; f.SL = C;
+  fold(c, f, "fold_pw1");
+
+  const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
+  const int groups = dense ? pl->geo.B : 1;
+  GemmArgs g1{};
+  g1.A = c.w(bw.vhat); g1.Bw = c.w(pl->o_wf); g1.bias = c.w(pl->o_bf);
+  g1.out = c.w(bw.a); g1.out2 = c.w(bw.h); g1.colsum = c.w(bw.gsq);
+  g1.M = R; g1.N = D4; g1.K = C; g1.group_rows = group_rows;
+  gemm<EPI_GELU_SQ>(c, g1, "pw1");
+
+  if (c.ok()) {
+    grn_scale_kernel<<<groups, 256, 0, c.st>>>(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom),
+                                               D4, dense ? 1e-4f : 1e-6f);
+    c.post("grn_scale");
+  }
+  GemmArgs g2{};
+  g2.out = c.w(bw.y); g2.resid = x; g2.M = R; g2.N = C; g2.K = D4; g2.group_rows = group_rows;
+  if (dense) {
+    if (c.ok()) {
+      c.acct(4.0 * 2.0 * R * D4, 0);
+      grn_apply_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(c.w(bw.h), c.w(bw.scale), c.p(bp.beta), c.w(bw.g), R, D4,
+                                                               group_rows);
+      c.post("grn_apply");
+    }
+    g2.A = c.w(bw.g); g2.Bw = c.p(bp.w2); g2.bias = c.p(bp.b2);
+  } else {
+    // GRN is affine in h per channel: fold s = 1 + gamma*Nx into W2's columns and beta into the bias
+    FoldArgs f2{};
+    f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.scale_k = c.w(bw.scale); f2.shift_k = c.p(bp.beta);
+    f2.bias = c.p(bp.b2); f2.Wf = c.w(pl->o_wf); f2.bf = c.w(pl->o_bf); f2.N = C; f2.K = D4; f2.SL = D4;
+    fold(c, f2, "fold_pw2");
+    g2.A = c.w(bw.h); g2.Bw = c.w(pl->o_wf); g2.bias = c.w(pl->o_bf);
+  }
+  gemm<EPI_STORE>(c, g2, "pw2");
+}
+
+// Backward of one block.  dy -> dx (both [R, C]); parameter grads accumulate.
+void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, const float *dy, float *dx, int64_t R,
+                    int C, int P, bool dense) {
+  mpmae_plan *pl = c.pl;
+  const int D4 = 4 * C;
+  const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
+  const int groups = dense ? pl->geo.B : 1;
+  float *da = c.w(pl->o_gda);
+  float *dsv = c.w(pl->o_dsv), *kg = c.w(pl->o_kg), *dwf = c.w(pl->o_dwf), *dbf = c.w(pl->o_dbf);
+
+  if (dense) {
+    // dg = dy . W2 ; A[g,d] = sum dg*h ; dbeta = sum dg
+    FoldArgs ft{};
+    ft.W = c.p(bp.w2); ft.s_n = D4; ft.s_k = 1; ft.WfT = c.w(pl->o_wft); ft.N = C; ft.K = D4; ft.SL = D4;
+    fold(c, ft, "w2T");
+    c.zero(dsv, (int64_t)groups * D4, "zero_ds");
+    GemmArgs gd{};
+    gd.A = dy; gd.Bw = c.w(pl->o_wft); gd.out = da; gd.aux = c.w(bw.h); gd.colsum = dsv; gd.colsum2 = c.g(bp.beta);
+    gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
+    gemm<EPI_DG>(c, gd, "dg");
+    // dW2 += dy^T . g ; db2 += sum dy
+    WgradArgs wg{};
+    wg.X = dy; wg.Y = c.w(bw.g); wg.dW = c.g(bp.w2); wg.db = c.g(bp.b2); wg.R = R; wg.N = C; wg.K = D4;
+    wgrad(c, wg, "dW2");
+    if (c.ok()) {
+      grn_bwd_scale_kernel<<<groups, 256, 0, c.st>>>(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
+      c.post("grn_bwd_scale");
+      c.acct(4.0 * 4.0 * R * D4, 0);
+      grn_gelu_bwd_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(da, c.w(bw.h), c.w(bw.a), c.w(bw.scale), kg, da, R, D4,
+                                                                  group_rows);
+      c.post("grn_gelu_bwd");
+    }
+  } else {
+    // folded pw2:  dW2f = dy^T . h, db2f = sum dy  ->  dW2, ds (= A), dbeta, db2 by the chain rule of the fold
+    c.zero(dwf, (int64_t)C * D4, "zero_dwf");
+    c.zero(dbf, C, "zero_dbf");
+    c.zero(dsv, D4, "zero_ds");
+    WgradArgs wg{};
+    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf; wg.db = dbf; wg.R = R; wg.N = C; wg.K = D4;
+    wgrad(c, wg, "dW2f");
+    UnfoldArgs u{};
+    u.W = c.p(bp.w2); u.s_n = D4; u.s_k = 1; u.scale_k = c.w(bw.scale); u.shift_k = c.p(bp.beta);
+    u.dWf = dwf; u.dbf = dbf; u.dW = c.g(bp.w2); u.dscale = dsv; u.dshift = c.g(bp.beta); u.dbias = c.g(bp.b2);
+    u.N = C; u.K = D4; u.SL = D4;
+    unfold(c, u, "unfold_pw2");
+    if (c.ok()) {
+      grn_bwd_scale_kernel<<<1, 256, 0, c.st>>>(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
+      c.post("grn_bwd_scale");
+    }
+    // da = (dy . W2f + kg*h) * gelu'(a)
+    FoldArgs f2{};
+    f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.scale_k = c.w(bw.scale); f2.WfT = c.w(pl->o_wft);
+    f2.N = C; f2.K = D4; f2.SL = D4;
+    fold(c, f2, "fold_pw2T");
+    GemmArgs gd{};
+    gd.A = dy; gd.Bw = c.w(pl->o_wft); gd.out = da; gd.aux = c.w(bw.h); gd.aux2 = c.w(bw.a); gd.kg = kg;
+    gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
+    gemm<EPI_DH_GELU>(c, gd, "da");
+  }
+  // pw1 (LN affine folded): dW1f = da^T . vhat, db1f = sum da
+  c.zero(dwf, (int64_t)D4 * C, "zero_dwf");
+  c.zero(dbf, D4, "zero_dbf");
+  WgradArgs w1{};
+  w1.X = da; w1.Y = c.w(bw.vhat); w1.dW = dwf; w1.db = dbf; w1.R = R; w1.N = D4; w1.K = C;
+  wgrad(c, w1, "dW1f");
+  UnfoldArgs u1{};
+  u1.W = c.p(bp.w1); u1.s_n = C; u1.s_k = 1; u1.scale_k = c.p(bp.ln_w); u1.shift_k = c.p(bp.ln_b);
+  u1.dWf = dwf; u1.dbf = dbf; u1.dW = c.g(bp.w1); u1.dscale = c.g(bp.ln_w); u1.dshift = c.g(bp.ln_b);
+  u1.dbias = c.g(bp.b1); u1.N = D4; u1.K = C; u1.SL = C;
+  unfold(c, u1, "unfold_pw1");
+  // dvhat = da . W1f
+  FoldArgs f1{};
+  f1.W = c.p(bp.w1); f1.s_n = C; f1.s_k = 1; f1.scale_k = c.p(bp.ln_w); f1.WfT = c.w(pl->o_wft);
+  f1.N = D4; f1.K = C; f1.SL = C;
+  fold(c, f1, "fold_pw1T");
+  float *dv = c.w(pl->o_gdv), *du = c.w(pl->o_gdu);
+  GemmArgs gv{};
+  gv.A = da; gv.Bw = c.w(pl->o_wft); gv.out = dv; gv.M = R; gv.N = C; gv.K = D4; gv.group_rows = group_rows;
+  gemm<EPI_STORE>(c, gv, "dvhat");
+  if (c.ok()) {
+    c.acct(4.0 * (3.0 * R * C + R), 0);
+    ln_rows_bwd_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, c.st>>>(dv, c.w(bw.vhat), c.w(bw.rstd), nullptr, du, R, C);
+    c.post("ln_bwd");
+  }
+  // depthwise: dx = flipped stencil over du + dy (residual) ; dW, db
+  DwArgs d{};
+  d.x = du; d.w = c.p(bp.dw_k); d.bias = nullptr; d.resid = dy;
+  if (dense) { d.w_sc = 49; d.w_skh = 7; d.w_skw = 1; } else { d.w_sc = 1; d.w_skh = C; d.w_skw = 7 * C; }
+  d.out = dx; d.rstd = nullptr;
+  d.slot_of = dense ? nullptr : reinterpret_cast<const int *>(c.w(pl->o_slot));
+  d.geo = pl->geo;
+  if (dense) d.geo.V = pl->geo.L;
+  d.P = P; d.C = C; d.flip = 1; d.do_ln = 0; d.eps = 0.f;
+  c.acct(4.0 * (3.0 * R * C + 49.0 * C), 2.0 * 49 * (double)R * C);
+  if (c.ok()) c.check(launch_dwconv_fwd(d, c.st), "dwconv_dx");
+  DwWgradArgs dwg{};
+  dwg.x = x; dwg.du = du; dwg.dw = c.g(bp.dw_k); dwg.w_skh = d.w_skh; dwg.w_skw = d.w_skw; dwg.w_sc = d.w_sc;
+  dwg.dbias = c.g(bp.dw_b); dwg.slot_of = d.slot_of; dwg.geo = d.geo; dwg.P = P; dwg.C = C;
+  c.acct(4.0 * (2.0 * R * C + 50.0 * C), 2.0 * 50 * (double)R * C);
+  if (c.ok()) c.check(launch_dwconv_wgrad(dwg, c.st), "dwconv_wgrad");
+}
+
+InitConvArgs init_args(Ctx &c) {
+  mpmae_plan *pl = c.pl;
+  InitConvArgs a{};
+  a.img = c.io->s2_input; a.kernel = c.p(pl->ic_k); a.bias = c.p(pl->ic_b);
+  a.chat = c.w(pl->o_chat); a.rstd = c.w(pl->o_rstd_c);
+  a.slot_of = reinterpret_cast<const int *>(c.w(pl->o_slot));
+  a.vis_patch = reinterpret_cast<const int *>(c.w(pl->o_vis));
+  a.flags = c.io->flags;
+  a.geo = pl->geo; a.S = pl->S; a.Cin = pl->cfg.in_chans; a.C0 = pl->cfg.dims[0]; a.Ppre = pl->Ppre; a.eps = 1e-6f;
+  return a;
+}
+StemArgs stem_args(Ctx &c) {
+  mpmae_plan *pl = c.pl;
+  StemArgs s{};
+  s.chat = c.w(pl->o_chat); s.rstd_c = c.w(pl->o_rstd_c);
+  s.ln0_w = c.p(pl->ic_lnw); s.ln0_b = c.p(pl->ic_lnb); s.kernel = c.p(pl->st_k); s.bias = c.p(pl->st_b);
+  s.ln1_w = c.p(pl->st_lnw); s.ln1_b = c.p(pl->st_lnb);
+  s.shat = c.w(pl->o_shat); s.rstd_s = c.w(pl->o_rstd_s); s.x0 = c.w(pl->o_x0);
+  s.R0 = pl->R[0]; s.C0 = pl->cfg.dims[0]; s.s2 = pl->s_stem * pl->s_stem; s.eps = 1e-6f;
+  return s;
+}
+
+LossArgs loss_args(Ctx &c) {
+  mpmae_plan *pl = c.pl;
+  LossArgs a{};
+  a.n_mod = pl->cfg.n_mod;
+  for (int m = 0; m < a.n_mod; ++m) {
+    a.mod[m].kind = pl->cfg.mod_kind[m];
+    a.mod[m].chans = pl->cfg.mod_chans[m];
+    a.mod[m].col_off = pl->col_off[m];
+    a.mod[m].norm_pix = pl->cfg.mod_norm_pix[m];
+    a.mod[m].target = c.io->targets[m];
+  }
+  a.pred_pix = c.io->pred_pixel; a.npix = pl->npix;
+  a.pred_img = c.io->pred_image; a.nimg = pl->nimg;
+  a.mask = c.io->mask;
+  a.dpix = c.w(pl->o_dpix); a.dimg = c.w(pl->o_dimg); a.acc = c.w(pl->o_acc);
+  a.B = pl->geo.B; a.L = pl->geo.L; a.G = pl->geo.G; a.p = pl->cfg.patch_size; a.S = pl->S;
+  return a;
+}
+
+int check_io(const mpmae_plan *pl, const mpmae_io *io, bool backward, bool encoder_only = false) {
+  if (!pl || !io) return fail(MPMAE_ERR_INVALID, "null plan/io");
+  if (!io->params || !io->workspace || !io->noise || !io->s2_input || !io->mask || !io->flags)
+    return fail(MPMAE_ERR_INVALID, "null device pointer in mpmae_io");
+  if (!encoder_only) {
+    if (!io->losses) return fail(MPMAE_ERR_INVALID, "losses is null");
+    if (pl->npix > 0 && !io->pred_pixel) return fail(MPMAE_ERR_INVALID, "pred_pixel is null");
+    if (pl->nimg > 0 && !io->pred_image) return fail(MPMAE_ERR_INVALID, "pred_image is null");
+    for (int m = 0; m < pl->cfg.n_mod; ++m)
+      if (!io->targets[m]) return fail(MPMAE_ERR_INVALID, "target %d is null", m);
+  }
+  if (io->workspace_bytes < (size_t)pl->ws_floats * 4) return fail(MPMAE_ERR_WORKSPACE, "workspace too small");
+  if ((reinterpret_cast<uintptr_t>(io->workspace) & 255) != 0) return fail(MPMAE_ERR_INVALID, "workspace not 256-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(io->params) & 15) != 0) return fail(MPMAE_ERR_INVALID, "params not 16-byte aligned");
+  if (backward && (!io->grads || (reinterpret_cast<uintptr_t>(io->grads) & 15) != 0))
+    return fail(MPMAE_ERR_INVALID, "grads null or misaligned");
+  return MPMAE_OK;
+}
+
+int finish(Ctx &c, int *count_slot) {
+  if (!c.ok()) return fail(MPMAE_ERR_CUDA, "%s: %s", c.where, cudaGetErrorString(c.err));
+  *count_slot = c.launches;
+  return MPMAE_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *mpmae_last_error(void) { return g_err; }
+int mpmae_version(void) { return 100; }
+
+int mpmae_plan_create(const mpmae_cfg *cfg, mpmae_plan **out) {
+  if (!cfg || !out) return fail(MPMAE_ERR_INVALID, "null cfg/out");
+  const mpmae_cfg &c = *cfg;
+  if (c.batch <= 0 || c.patch_size <= 0 || c.patch_size % 8 != 0 || c.img_size % c.patch_size != 0)
+    return fail(MPMAE_ERR_INVALID, "bad geometry: batch %d img %d patch %d", c.batch, c.img_size, c.patch_size);
+  if (c.patch_size != 8 && c.patch_size != 16)
+    return fail(MPMAE_ERR_UNSUPPORTED, "patch_size %d: kernels are instantiated for 8 and 16", c.patch_size);
+  if (c.n_mod <= 0 || c.n_mod > MPMAE_MAX_MOD) return fail(MPMAE_ERR_INVALID, "n_mod %d", c.n_mod);
+  if (c.dec_depth < 1 || c.dec_dim % 32 != 0) return fail(MPMAE_ERR_INVALID, "decoder depth/dim");
+  for (int i = 0; i < 4; ++i) {
+    if (c.depths[i] < 1 || c.dims[i] % 8 != 0) return fail(MPMAE_ERR_UNSUPPORTED, "dims must be multiples of 8");
+    if (i > 0 && c.dims[i] < c.dims[i - 1]) return fail(MPMAE_ERR_UNSUPPORTED, "dims must be non-decreasing");
+  }
+  if (c.dims[0] > 128) return fail(MPMAE_ERR_UNSUPPORTED, "dims[0] > 128: stem kernels hold <= 4 channels per lane");
+  auto *pl = new mpmae_plan();
+  pl->cfg = c;
+  pl->S = c.img_size;
+  pl->geo.B = c.batch;
+  pl->geo.G = c.img_size / c.patch_size;
+  pl->geo.L = pl->geo.G * pl->geo.G;
+  pl->geo.V = (int)(pl->geo.L * (1.0 - (double)c.mask_ratio));  // int(L * (1 - mask_ratio)), fcmae.py:216-217
+  {  // python evaluates L * (1 - mask_ratio) in double with mask_ratio a python float
+    const double mr = (double)c.mask_ratio;
+    // the float -> double round trip of e.g. 0.6f is 0.60000002384; recover the decimal the caller meant
+    const double mr_dec = (double)((long long)(mr * 1e6 + 0.5)) / 1e6;
+    pl->geo.V = (int)(pl->geo.L * (1.0 - mr_dec));
+  }
+  if (pl->geo.V < 1 || pl->geo.V > pl->geo.L) { delete pl; return fail(MPMAE_ERR_INVALID, "no visible patches"); }
+  if (pl->geo.L > 1024) { delete pl; return fail(MPMAE_ERR_UNSUPPORTED, "patch grid too large"); }
+  pl->Ppre = c.patch_size;
+  pl->s_stem = c.patch_size / 8;
+  pl->D = c.dec_dim;
+  int P = 8;
+  for (int i = 0; i < 4; ++i) { pl->P[i] = P; pl->R[i] = (int64_t)c.batch * pl->geo.V * P * P; P /= 2; }
+  pl->Rpre = (int64_t)c.batch * pl->geo.V * pl->Ppre * pl->Ppre;
+  pl->cells = (int64_t)c.batch * pl->geo.L;
+  const int p2 = c.patch_size * c.patch_size;
+  for (int m = 0; m < c.n_mod; ++m) {
+    const int k = c.mod_kind[m];
+    if (k < 0 || k > 3 || c.mod_chans[m] <= 0) { delete pl; return fail(MPMAE_ERR_INVALID, "modality %d", m); }
+    pl->is_img[m] = (k == MPMAE_IMAGE_CATEGORICAL || k == MPMAE_IMAGE_CONTINUOUS);
+    if (pl->is_img[m]) { pl->col_off[m] = pl->nimg; pl->col_len[m] = c.mod_chans[m]; pl->nimg += c.mod_chans[m]; }
+    else { pl->col_off[m] = pl->npix; pl->col_len[m] = p2 * c.mod_chans[m]; pl->npix += p2 * c.mod_chans[m]; }
+  }
+  build_params(pl);
+  build_workspace(pl);
+  *out = pl;
+  return MPMAE_OK;
+}
+
+void mpmae_plan_destroy(mpmae_plan *plan) { delete plan; }
+
+int64_t mpmae_param_total(const mpmae_plan *plan) { return plan ? plan->n_params : 0; }
+int32_t mpmae_param_count(const mpmae_plan *plan) { return plan ? (int32_t)plan->params.size() : 0; }
+int mpmae_param_info(const mpmae_plan *plan, int32_t index, char *name, int32_t name_cap, int64_t shape[4],
+                     int32_t *ndim, int64_t *offset) {
+  if (!plan || index < 0 || index >= (int32_t)plan->params.size()) return fail(MPMAE_ERR_INVALID, "param index");
+  const ParamRef &r = plan->params[index];
+  if (name && name_cap > 0) { strncpy(name, r.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = r.shape[i];
+  if (ndim) *ndim = r.ndim;
+  if (offset) *offset = r.off;
+  return MPMAE_OK;
+}
+int32_t mpmae_param_decay(const mpmae_plan *plan, int32_t index) {
+  if (!plan || index < 0 || index >= (int32_t)plan->params.size()) return -1;
+  return plan->params[index].decay;
+}
+
+size_t mpmae_workspace_bytes(const mpmae_plan *plan) { return plan ? (size_t)plan->ws_floats * 4 : 0; }
+int32_t mpmae_pred_pixel_cols(const mpmae_plan *plan) { return plan ? plan->npix : 0; }
+int32_t mpmae_pred_image_cols(const mpmae_plan *plan) { return plan ? plan->nimg : 0; }
+int32_t mpmae_pred_col_offset(const mpmae_plan *plan, int32_t mod) {
+  if (!plan || mod < 0 || mod >= plan->cfg.n_mod) return -1;
+  return plan->col_off[mod];
+}
+int32_t mpmae_visible_patches(const mpmae_plan *plan) { return plan ? plan->geo.V : 0; }
+
+int mpmae_tap_info(const mpmae_plan *plan, const char *name, int64_t *byte_offset, int64_t *rows, int64_t *cols) {
+  if (!plan || !name) return fail(MPMAE_ERR_INVALID, "null");
+  auto it = plan->taps.find(name);
+  if (it == plan->taps.end()) return fail(MPMAE_ERR_INVALID, "no tap named %s", name);
+  if (byte_offset) *byte_offset = it->second.off_bytes;
+  if (rows) *rows = it->second.rows;
+  if (cols) *cols = it->second.cols;
+  return MPMAE_OK;
+}
+int32_t mpmae_tap_count(const mpmae_plan *plan) { return plan ? (int32_t)plan->taps.size() : 0; }
+int mpmae_tap_name(const mpmae_plan *plan, int32_t index, char *name, int32_t name_cap) {
+  if (!plan || index < 0 || index >= (int32_t)plan->taps.size() || !name || name_cap <= 0)
+    return fail(MPMAE_ERR_INVALID, "tap index");
+  auto it = plan->taps.begin();
+  std::advance(it, index);
+  strncpy(name, it->first.c_str(), name_cap - 1);
+  name[name_cap - 1] = 0;
+  return MPMAE_OK;
+}
+
+int32_t mpmae_launch_count(const mpmae_plan *plan, int32_t backward) {
+  if (!plan) return 0;
+  return backward ? plan->launches_bwd : plan->launches_fwd;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, bool encoder_only) {
+  int rc = check_io(pl, io, false, encoder_only);
+  if (rc) return rc;
+  Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
+  c.mark("start");
+  const mpmae_cfg &cf = pl->cfg;
+  const int *dm = cf.dims;
+  const Geo geo = pl->geo;
+  int *slot_of = reinterpret_cast<int *>(c.w(pl->o_slot));
+  int *vis = reinterpret_cast<int *>(c.w(pl->o_vis));
+
+  c.zero(c.w(pl->o_zero_begin), pl->o_zero_end - pl->o_zero_begin, "zero_stats");
+  c.check(cudaMemsetAsync(io->flags, 0, 4 * sizeof(int32_t), c.st), "memset", false);
+  mask_kernel<<<geo.B, 64, (size_t)geo.L * 8, c.st>>>(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
+  c.post("mask");
+
+  {  // patch embedding: 3x3 conv + LN (+GELU, stem depthwise, LN)
+    InitConvArgs a = init_args(c);
+    const size_t sm = ((size_t)a.Cin * 100 + 9 * (size_t)a.Cin * a.C0 + 64 * (size_t)(a.C0 + 1)) * 4;
+    static size_t configured = 0;
+    if (sm > 48 * 1024 && sm > configured) {
+      c.check(cudaFuncSetAttribute(initial_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr");
+      configured = sm;
+    }
+    const int tiles = (pl->Ppre / 8) * (pl->Ppre / 8);
+    initial_conv_fwd_kernel<<<geo.B * geo.V * tiles, 256, sm, c.st>>>(a);
+    c.post("initial_conv");
+    StemArgs s = stem_args(c);
+    stem_fwd_kernel<<<(unsigned)cdiv64(s.R0, 8), 256, 0, c.st>>>(s);
+    c.post("stem");
+  }
+  const float *x = c.w(pl->o_x0);
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) {  // downsample: LN + 2x2 stride-2 conv == [R/4, 4Cin] x [4Cin, Cout] on Z-ordered rows
+      const int Ci = dm[i - 1], Co = dm[i];
+      ln_rows_fwd_kernel<<<(unsigned)cdiv64(pl->R[i - 1], 8), 256, 0, c.st>>>(x, c.w(pl->o_ds_xhat[i - 1]),
+                                                                           c.w(pl->o_ds_rstd[i - 1]), pl->R[i - 1], Ci, 1e-6f);
+      c.post("ds_ln");
+      FoldArgs f{};
+      f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w);
+      f.shift_k = c.p(pl->ds[i - 1].ln_b); f.bias = c.p(pl->ds[i - 1].b);
+      f.Wf = c.w(pl->o_wf); f.bf = c.w(pl->o_bf); f.N = Co; f.K = 4 * Ci; f.SL = Ci;
+      fold(c, f, "fold_ds");
+      GemmArgs g{};
+      g.A = c.w(pl->o_ds_xhat[i - 1]); g.Bw = c.w(pl->o_wf); g.bias = c.w(pl->o_bf); g.out = c.w(pl->o_ds_out[i - 1]);
+      g.M = pl->R[i]; g.N = Co; g.K = 4 * Ci; g.group_rows = 0x7fffffff;
+      gemm<EPI_STORE>(c, g, "ds_conv");
+      x = c.w(pl->o_ds_out[i - 1]);
+    }
+    for (int j = 0; j < cf.depths[i]; ++j) {
+      block_forward(c, pl->blk[i][j], pl->bw[i][j], x, pl->R[i], dm[i], pl->P[i], false);
+      x = c.w(pl->bw[i][j].y);
+    }
+  }
+  if (encoder_only) {
+    int dummy = 0;
+    return finish(c, &dummy);
+  }
+  // decoder entry: proj on visible rows, mask token elsewhere (fcmae.py:251-255)
+  const int D = cf.dec_dim;
+  {
+    GemmArgs g{};
+    g.A = x; g.Bw = c.p(pl->proj_w); g.bias = c.p(pl->proj_b); g.out = c.w(pl->o_z);
+    g.M = (int64_t)geo.B * geo.V; g.N = D; g.K = dm[3]; g.group_rows = 0x7fffffff;
+    gemm<EPI_STORE>(c, g, "proj");
+    scatter_token_kernel<<<ew_grid(pl->cells * (D / 4)), 256, 0, c.st>>>(c.w(pl->o_z), c.p(pl->tok), slot_of, c.w(pl->o_xd),
+                                                                      pl->cells, geo.L, geo.V, D);
+    c.post("scatter_token");
+  }
+  const float *d = c.w(pl->o_xd);
+  for (int k = 0; k < cf.dec_depth; ++k) {
+    block_forward(c, pl->dec[k], pl->dw[k], d, pl->cells, D, 1, true);
+    d = c.w(pl->dw[k].y);
+  }
+  if (pl->npix > 0) {
+    GemmArgs g{};
+    g.A = d; g.Bw = c.p(pl->pixw); g.bias = c.p(pl->pixb); g.out = io->pred_pixel;
+    g.M = pl->cells; g.N = pl->npix; g.K = D; g.group_rows = 0x7fffffff;
+    gemm<EPI_STORE>(c, g, "pixel_heads");
+  }
+  if (pl->nimg > 0) {
+    pool_ln_fwd_kernel<<<geo.B, 256, (size_t)D * 4, c.st>>>(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
+                                                          c.w(pl->o_pool_rstd), geo.L, D, 1e-6f);
+    c.post("pool_ln");
+    GemmArgs g{};
+    g.A = c.w(pl->o_pooled); g.Bw = c.p(pl->imgw); g.bias = c.p(pl->imgb); g.out = io->pred_image;
+    g.M = geo.B; g.N = pl->nimg; g.K = D; g.group_rows = 0x7fffffff;
+    if (c.ok()) c.check(launch_gemm_rows_simt<EPI_STORE>(g, c.st), "image_heads");
+  }
+  {
+    LossArgs a = loss_args(c);
+    if (pl->npix > 0) { pixel_loss_kernel<<<(unsigned)pl->cells, 256, 0, c.st>>>(a); c.post("pixel_loss"); }
+    if (pl->nimg > 0) { image_loss_kernel<<<geo.B, 256, 0, c.st>>>(a); c.post("image_loss"); }
+    loss_finalize_kernel<<<1, 32, 0, c.st>>>(c.w(pl->o_acc), pl->logv >= 0 ? c.p(pl->logv) : nullptr, cf.n_mod,
+                                             cf.loss_aggr, io->losses);
+    c.post("loss_finalize");
+  }
+  return finish(c, &pl->launches_fwd);
+}
+
+int mpmae_forward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) { return forward_impl(pl, io, cuda_stream, false); }
+int mpmae_forward_encoder(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
+  return forward_impl(pl, io, cuda_stream, true);
+}
+
+// -------------------------------------------------------------------------------------------------
+int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
+  int rc = check_io(pl, io, true);
+  if (rc) return rc;
+  Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
+  c.mark("start");
+  const mpmae_cfg &cf = pl->cfg;
+  const int *dm = cf.dims;
+  const Geo geo = pl->geo;
+  const int D = cf.dec_dim;
+  const int *slot_of = reinterpret_cast<const int *>(c.w(pl->o_slot));
+  float *g0 = c.w(pl->o_g0), *g1 = c.w(pl->o_g1);
+
+  {  // seeds: d total / d L_i / denominator_i per prediction column ; d total / d log_vars
+    SeedArgs s{};
+    s.acc = c.w(pl->o_acc); s.log_vars = pl->logv >= 0 ? c.p(pl->logv) : nullptr; s.losses = io->losses;
+    s.grad_out = io->grad_out; s.d_log_vars = pl->logv >= 0 ? c.g(pl->logv) : nullptr;
+    s.colscale_pix = c.w(pl->o_cs_pix); s.colscale_img = c.w(pl->o_cs_img);
+    s.n_mod = cf.n_mod; s.uncertainty = cf.loss_aggr;
+    for (int m = 0; m < cf.n_mod; ++m) { s.col_off[m] = pl->col_off[m]; s.col_len[m] = pl->col_len[m]; s.is_img[m] = pl->is_img[m]; }
+    loss_seed_kernel<<<cf.n_mod, 256, 0, c.st>>>(s);
+    c.post("loss_seed");
+  }
+  const float *dec_out = c.w(pl->dw[cf.dec_depth - 1].y);
+  float *dd = g0;  // gradient at the decoder output [cells, D]
+  if (pl->npix > 0) {
+    FoldArgs f{};
+    f.W = c.p(pl->pixw); f.s_n = D; f.s_k = 1; f.scale_n = c.w(pl->o_cs_pix); f.WfT = c.w(pl->o_wft);
+    f.N = pl->npix; f.K = D; f.SL = D;
+    fold(c, f, "fold_pixT");
+    GemmArgs g{};
+    g.A = c.w(pl->o_dpix); g.Bw = c.w(pl->o_wft); g.out = dd; g.M = pl->cells; g.N = D; g.K = pl->npix; g.group_rows = 0x7fffffff;
+    gemm<EPI_STORE>(c, g, "d_dec_pix");
+    WgradArgs w{};
+    w.X = c.w(pl->o_dpix); w.Y = dec_out; w.rs = c.w(pl->o_cs_pix); w.dW = c.g(pl->pixw); w.db = c.g(pl->pixb);
+    w.R = pl->cells; w.N = pl->npix; w.K = D;
+    wgrad(c, w, "dW_pix");
+  } else {
+    c.zero(dd, pl->cells * D, "zero_dd");
+  }
+  if (pl->nimg > 0) {
+    if (c.ok()) {
+      small_gemm_nt_kernel<<<(unsigned)cdiv64((int64_t)geo.B * D, 256), 256, 0, c.st>>>(
+          c.w(pl->o_dimg), c.p(pl->imgw), c.w(pl->o_cs_img), c.w(pl->o_dpooled), geo.B, D, pl->nimg);
+      c.post("d_pooled");
+    }
+    WgradArgs w{};
+    w.X = c.w(pl->o_dimg); w.Y = c.w(pl->o_pooled); w.rs = c.w(pl->o_cs_img); w.dW = c.g(pl->imgw); w.db = c.g(pl->imgb);
+    w.R = geo.B; w.N = pl->nimg; w.K = D;
+    wgrad(c, w, "dW_img");
+    if (c.ok()) {
+      pool_ln_bwd_kernel<<<geo.B, 256, (size_t)D * 4, c.st>>>(dec_out, c.w(pl->o_pool_rstd), c.p(pl->lnt_w), c.w(pl->o_dpooled),
+                                                            dd, c.g(pl->lnt_w), c.g(pl->lnt_b), geo.L, D, 1e-6f);
+      c.post("pool_ln_bwd");
+    }
+  }
+  float *cur = g0, *nxt = g1;
+  for (int k = cf.dec_depth - 1; k >= 0; --k) {
+    const float *xin = k > 0 ? c.w(pl->dw[k - 1].y) : c.w(pl->o_xd);
+    block_backward(c, pl->dec[k], pl->dw[k], xin, cur, nxt, pl->cells, D, 1, true);
+    std::swap(cur, nxt);
+  }
+  // decoder entry backward: visible cells -> proj rows, masked cells -> mask token
+  const int64_t BV = (int64_t)geo.B * geo.V;
+  const float *x3 = c.w(pl->bw[3][cf.depths[3] - 1].y);
+  {
+    float *dz = c.w(pl->o_gdv);
+    if (c.ok()) {
+      gather_token_bwd_kernel<<<148 * 2, 128, (size_t)D * 4, c.st>>>(cur, slot_of, dz, c.g(pl->tok), pl->cells, geo.L, geo.V, D);
+      c.post("gather_token_bwd");
+    }
+    WgradArgs w{};
+    w.X = dz; w.Y = x3; w.dW = c.g(pl->proj_w); w.db = c.g(pl->proj_b); w.R = BV; w.N = D; w.K = dm[3];
+    wgrad(c, w, "dW_proj");
+    FoldArgs f{};
+    f.W = c.p(pl->proj_w); f.s_n = dm[3]; f.s_k = 1; f.WfT = c.w(pl->o_wft); f.N = D; f.K = dm[3]; f.SL = dm[3];
+    fold(c, f, "projT");
+    GemmArgs g{};
+    g.A = dz; g.Bw = c.w(pl->o_wft); g.out = nxt; g.M = BV; g.N = dm[3]; g.K = D; g.group_rows = 0x7fffffff;
+    gemm<EPI_STORE>(c, g, "d_x3");
+    std::swap(cur, nxt);
+  }
+  for (int i = 3; i >= 0; --i) {
+    for (int j = cf.depths[i] - 1; j >= 0; --j) {
+      const float *xin = j > 0 ? c.w(pl->bw[i][j - 1].y) : (i > 0 ? c.w(pl->o_ds_out[i - 1]) : c.w(pl->o_x0));
+      block_backward(c, pl->blk[i][j], pl->bw[i][j], xin, cur, nxt, pl->R[i], dm[i], pl->P[i], false);
+      std::swap(cur, nxt);
+    }
+    if (i > 0) {
+      const int Ci = dm[i - 1], Co = dm[i];
+      float *dwf = c.w(pl->o_dwf), *dbf = c.w(pl->o_dbf);
+      c.zero(dwf, (int64_t)Co * 4 * Ci, "zero_dwf");
+      c.zero(dbf, Co, "zero_dbf");
+      WgradArgs w{};
+      w.X = cur; w.Y = c.w(pl->o_ds_xhat[i - 1]); w.dW = dwf; w.db = dbf; w.R = pl->R[i]; w.N = Co; w.K = 4 * Ci;
+      wgrad(c, w, "dW_ds");
+      UnfoldArgs u{};
+      u.W = c.p(pl->ds[i - 1].k); u.s_n = 1; u.s_k = Co; u.scale_k = c.p(pl->ds[i - 1].ln_w); u.shift_k = c.p(pl->ds[i - 1].ln_b);
+      u.dWf = dwf; u.dbf = dbf; u.dW = c.g(pl->ds[i - 1].k); u.dscale = c.g(pl->ds[i - 1].ln_w);
+      u.dshift = c.g(pl->ds[i - 1].ln_b); u.dbias = c.g(pl->ds[i - 1].b); u.N = Co; u.K = 4 * Ci; u.SL = Ci;
+      unfold(c, u, "unfold_ds");
+      FoldArgs f{};
+      f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w); f.WfT = c.w(pl->o_wft);
+      f.N = Co; f.K = 4 * Ci; f.SL = Ci;
+      fold(c, f, "fold_dsT");
+      float *dxh = c.w(pl->o_gdv);
+      GemmArgs g{};
+      g.A = cur; g.Bw = c.w(pl->o_wft); g.out = dxh; g.M = pl->R[i]; g.N = 4 * Ci; g.K = Co; g.group_rows = 0x7fffffff;
+      gemm<EPI_STORE>(c, g, "d_ds_in");
+      if (c.ok()) {
+        ln_rows_bwd_kernel<<<(unsigned)cdiv64(pl->R[i - 1], 8), 256, 0, c.st>>>(dxh, c.w(pl->o_ds_xhat[i - 1]),
+                                                                              c.w(pl->o_ds_rstd[i - 1]), nullptr, nxt,
+                                                                              pl->R[i - 1], Ci);
+        c.post("ds_ln_bwd");
+      }
+      std::swap(cur, nxt);
+    }
+  }
+  {  // stem + initial conv
+    StemBwdArgs sb{};
+    sb.f = stem_args(c);
+    sb.dx0 = cur; sb.dc = nxt;
+    sb.d_ln0_w = c.g(pl->ic_lnw); sb.d_ln0_b = c.g(pl->ic_lnb); sb.d_kernel = c.g(pl->st_k); sb.d_bias = c.g(pl->st_b);
+    sb.d_ln1_w = c.g(pl->st_lnw); sb.d_ln1_b = c.g(pl->st_lnb);
+    if (c.ok()) {
+      stem_bwd_kernel<<<148 * 4, 256, (size_t)(5 + sb.f.s2) * sb.f.C0 * 4, c.st>>>(sb);
+      c.post("stem_bwd");
+    }
+    InitConvWgradArgs iw{};
+    iw.f = init_args(c);
+    iw.dc = nxt; iw.dkernel = c.g(pl->ic_k); iw.dbias = c.g(pl->ic_b);
+    const size_t sm = ((size_t)iw.f.Cin * 100 + 64 * (size_t)iw.f.C0 + (9 * (size_t)iw.f.Cin + 1) * iw.f.C0) * 4;
+    static size_t configured = 0;
+    if (sm > 48 * 1024 && sm > configured) {
+      c.check(cudaFuncSetAttribute(initial_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr");
+      configured = sm;
+    }
+    if (c.ok()) {
+      initial_conv_wgrad_kernel<<<148 * 2, 256, sm, c.st>>>(iw);
+      c.post("initial_conv_wgrad");
+    }
+  }
+  return finish(c, &pl->launches_bwd);
+}
+
+int mpmae_profile_begin(mpmae_plan *pl) {
+  if (!pl) return fail(MPMAE_ERR_INVALID, "null plan");
+  pl->prof_on = true;
+  pl->prof_n = 0;
+  return MPMAE_OK;
+}
+
+int mpmae_profile_report(mpmae_plan *pl, char *buf, int32_t cap) {
+  if (!pl || !buf || cap <= 0) return fail(MPMAE_ERR_INVALID, "null");
+  pl->prof_on = false;
+  struct Agg { int count = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  if (pl->prof_n > 0) {
+    cudaError_t e = cudaEventSynchronize(pl->prof_ev[pl->prof_n - 1]);
+    if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "profile sync: %s", cudaGetErrorString(e));
+  }
+  for (int i = 1; i < pl->prof_n; ++i) {
+    if (strcmp(pl->prof_name[i], "start") == 0) continue;   // interval spans host time between calls
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pl->prof_ev[i - 1], pl->prof_ev[i]);
+    auto it = agg.find(pl->prof_name[i]);
+    if (it == agg.end()) { order.push_back(pl->prof_name[i]); it = agg.emplace(pl->prof_name[i], Agg()).first; }
+    it->second.count += 1; it->second.ms += ms; it->second.bytes += pl->prof_bytes[i]; it->second.flops += pl->prof_flops[i];
+  }
+  int pos = snprintf(buf, cap, "name,launches,ms,alg_bytes,alg_flops\n");
+  for (const auto &n : order) {
+    const Agg &a = agg[n];
+    if (pos >= cap - 1) break;
+    pos += snprintf(buf + pos, cap - pos, "%s,%d,%.6f,%.0f,%.0f\n", n.c_str(), a.count, a.ms, a.bytes, a.flops);
+  }
+  pl->prof_n = 0;
+  return MPMAE_OK;
+}
+
+int mpmae_encoder_features(mpmae_plan *pl, const mpmae_io *io, float *out_nchw, void *cuda_stream) {
+  if (!pl || !io || !io->workspace || !out_nchw) return fail(MPMAE_ERR_INVALID, "null");
+  float *ws = static_cast<float *>(io->workspace);
+  const int C3 = pl->cfg.dims[3];
+  const float *x3 = ws + pl->bw[3][pl->cfg.depths[3] - 1].y;
+  const int64_t total = (int64_t)pl->geo.B * C3 * pl->geo.L;
+  densify_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      x3, reinterpret_cast<const int *>(ws + pl->o_slot), out_nchw, pl->geo.B, pl->geo.L, pl->geo.V, C3);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "densify: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out, int64_t M, int32_t N,
+                    int32_t K, void *cuda_stream) {
+  if (!a || !b || !out || M < 0 || N <= 0 || K <= 0 || K % 8 != 0) return fail(MPMAE_ERR_INVALID, "gemm args");
+  GemmArgs g{};
+  g.A = a; g.Bw = b; g.bias = bias; g.out = out; g.M = M; g.N = N; g.K = K; g.group_rows = 0x7fffffff;
+  cudaError_t e;
+  if (backend != 0) {
+    if (!tc_gemm_supported(EPI_STORE, g)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
+    e = launch_gemm_rows_tc<EPI_STORE>(g, backend, static_cast<cudaStream_t>(cuda_stream));
+  } else {
+    e = launch_gemm_rows_simt<EPI_STORE>(g, static_cast<cudaStream_t>(cuda_stream));
+  }
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "gemm: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+int mpmae_adamw_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, const uint8_t *decay_mask,
+                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                     float grad_scale_inv, void *cuda_stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(MPMAE_ERR_INVALID, "adamw args");
+  cudaError_t e = launch_adamw(params, grads, exp_avg, exp_avg_sq, decay_mask, n, lr, beta1, beta2, eps, weight_decay, step,
+                               grad_scale_inv, static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "adamw: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+}  // extern "C"

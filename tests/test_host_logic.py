@@ -1,0 +1,91 @@
+"""Host side of the drop-in (mmearth_train_b200/fcmae.py) -- everything that does not need a GPU."""
+import pytest
+import torch
+
+from oracle import fcmae_oracle as fo
+from tests import golden_util as gu
+
+
+def _model(native_lib, **kw):
+    import mmearth_train_b200 as mp
+    args = fo.make_args(kw.pop("out_modalities", None), kw.get("loss_aggr", "uncertainty"))
+    args.loss_aggr = kw.pop("loss_aggr", "uncertainty")
+    lf = mp.UncertaintyWeightingStrategy(len(args.out_modalities)) if args.loss_aggr == "uncertainty" else None
+    return mp.convnextv2_atto(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True,
+                              patch_size=kw.pop("patch_size", 8), img_size=kw.pop("img_size", 56), args=args, loss_fn=lf)
+
+
+def test_state_dict_surface_and_aliases(native_lib):
+    m = _model(native_lib)
+    z, meta = gu.load("atto_p8_all_unc")
+    sd = m.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == meta["state_keys"]
+    # the 12 decoders are one block (models/fcmae.py:119-121,137,145): same storage under every alias
+    a = sd["decoder_dict.sentinel2.0.pwconv1.weight"]
+    b = sd["decoder_dict.esa_worldcover.0.pwconv1.weight"]
+    assert a.data_ptr() == b.data_ptr()
+    assert sum(p.numel() for n, p in m.named_parameters() if n != "_ddp_token") == 7580674
+
+
+def test_parameters_are_views_of_one_flat_buffer(native_lib):
+    m = _model(native_lib)
+    flat = m.flat_params
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+    for n, p in m.named_parameters():
+        if n == "_ddp_token":
+            continue
+        assert lo <= p.data_ptr() < hi, n
+    orc = fo.build_oracle()
+    fo.init_like_reference(orc, seed=3)
+    m.load_state_dict(orc.state_dict())
+    off, numel, shape = m._param_slices[5]
+    assert torch.equal(flat[off:off + numel].view(shape), m._param_list[5].detach())
+    sd = m.state_dict()
+    for k, v in orc.state_dict().items():
+        assert torch.equal(sd[k], v), k
+    # dtype conversion is refused, float32 round trip keeps the views
+    m2 = m.to(torch.float32)
+    assert m2._param_list[0].data_ptr() == m2.flat_params.data_ptr()
+    with pytest.raises(TypeError):
+        m.half()
+
+
+def test_weight_decay_mask_follows_timm_rule(native_lib):
+    m = _model(native_lib)
+    mask = m.decay_mask()
+    for (name, shape, off, decay), (_o, numel, _s) in zip(m._layout, m._param_slices):
+        expect = int(len(shape) > 1 and not name.endswith(".bias"))
+        assert int(mask[off]) == expect and int(mask[off + numel - 1]) == expect, name
+    # ME biases are [1, C] but named *.bias -> no decay; GRN gamma/beta [1, 4C] ARE decayed
+    names = {n: d for n, _s, _o, d in m._layout}
+    assert names["encoder.stages.0.0.dwconv.bias"] == 0 and names["encoder.stages.0.0.grn.gamma"] == 1
+
+
+def test_no_cpu_fallback(native_lib):
+    m = _model(native_lib)
+    batch = fo.synthetic_batch(2, 56)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(batch, mask_ratio=0.6)
+
+
+def test_constructor_errors_mirror_reference_scope(native_lib):
+    import mmearth_train_b200 as mp
+    args = fo.make_args()
+    with pytest.raises(NotImplementedError):
+        mp.convnextv2_atto(args=args, loss_fn=mp.UncertaintyWeightingStrategy(12), sparse=False, img_size=56, patch_size=8)
+    with pytest.raises(ValueError):
+        mp.convnextv2_atto(args=args, loss_fn=None, img_size=56, patch_size=8)
+
+
+def test_gen_random_mask_and_patchify_match_oracle(native_lib):
+    m = _model(native_lib)
+    x = torch.randn(3, 12, 56, 56)
+    torch.manual_seed(7)
+    mask = m.gen_random_mask(x, 0.6)
+    torch.manual_seed(7)
+    noise = torch.randn(3, 49)
+    assert torch.equal(mask, fo.OracleFCMAE.mask_from_noise(noise, 0.6))
+    assert mask.sum(1).tolist() == [30.0] * 3
+    orc = fo.build_oracle()
+    t = torch.randn(2, 8, 56, 56)
+    assert torch.equal(m.patchify(t, "sentinel1"), orc.patchify(t, 8))

@@ -1,0 +1,60 @@
+"""The stand-alone oracle (oracle/fcmae_oracle.py) against the golden fixtures produced by the unmodified
+reference, and -- when /root/reference is present (build container) -- against the reference itself, live."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_harness
+from tests import golden_util as gu
+
+TOL = 2e-5   # fp32 CPU vs fp32 CPU, different summation order only
+
+
+@pytest.mark.parametrize("case", gu.CASES)
+def test_oracle_matches_golden(case):
+    z, meta, orc, batch, noise = gu.inputs(case)
+    loss, pred, mask, loss_dict, log_vars, weighted = orc(batch, mask_ratio=0.6, noise=noise)
+    assert np.array_equal(mask.numpy().astype(np.uint8), z["mask"]), "mask indices must be bit-exact"
+    assert abs(float(loss) - float(z["loss"])) <= TOL * abs(float(z["loss"]))
+    assert gu.max_rel(orc.encoder(batch["sentinel2"], mask), z["encoder_features"]) < TOL
+    for m in meta["modalities"]:
+        assert gu.max_rel(pred[m], z[f"pred.{m}"]) < TOL, m
+        assert abs(float(loss_dict[m]) - float(z[f"loss.{m}"])) <= TOL * abs(float(z[f"loss.{m}"])), m
+    if weighted is not None:
+        assert gu.max_rel(weighted, z["weighted"]) < TOL
+    # state-dict surface
+    sd = orc.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == meta["state_keys"]
+    # sampled gradients
+    grads = gu.oracle_grads(orc, loss)
+    from oracle.make_golden import sample_index
+    checked = 0
+    for pname in meta["grad_params"]:
+        g = grads[pname].reshape(-1)
+        idx = sample_index(g.numel())
+        ref_norm = float(z[f"grad.{pname}.norm"])
+        assert abs(float(g.double().norm()) - ref_norm) <= 1e-4 * ref_norm + 1e-7, pname
+        scale = ref_norm / max(1.0, g.numel() ** 0.5) + 1e-7
+        assert np.max(np.abs(g[idx].numpy() - z[f"grad.{pname}.sample"])) <= 2e-3 * scale + 1e-4 * np.max(
+            np.abs(z[f"grad.{pname}.sample"])) + 1e-7, pname
+        checked += 1
+    assert checked == len(meta["grad_params"]) and checked > 100
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference only exists in the build container")
+def test_oracle_matches_live_reference_full_gradients():
+    from oracle import make_golden as mg
+    cfg = dict(mg.CASES["atto_p8_all_unc"])
+    orc, ref, batch, noise, out = mg.run_reference(cfg)
+    loss, pred, mask, loss_dict, log_vars, weighted = orc(batch, mask_ratio=0.6, noise=noise)
+    assert torch.equal(mask, out["mask"])
+    assert abs(float(loss) - float(out["loss"])) < TOL * abs(float(out["loss"]))
+    grads = gu.oracle_grads(orc, loss)
+    seen, n = set(), 0
+    for pname, p in ref.named_parameters():
+        if id(p) in seen or p.grad is None:
+            continue
+        seen.add(id(p))
+        assert gu.rel_err(grads[pname], p.grad) < 5e-4, pname
+        n += 1
+    assert n > 150
