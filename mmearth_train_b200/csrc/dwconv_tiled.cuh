@@ -1,0 +1,421 @@
+// Register-tiled depthwise 7x7 kernels (forward + LayerNorm, transposed stencil for dX, weight gradient).
+//
+// Same maths as dwconv.cuh (which stays as the generic fallback); what changes is the mapping:
+//   * "patch" flavour (P = 8, 4, 2): one CTA per visible patch; the (P+6)^2 halo window is staged in shared
+//     memory ([pixel][C], zeros for masked / out-of-image pixels); ONE THREAD = one channel x a strip of TR
+//     output rows, its 49 taps live in registers and the inputs slide through a (P+6)-wide register row, so the
+//     inner loop is pure FMA (TR*P*49 FMAs for (TR+6)*(P+6) shared loads) instead of 2 shared loads per FMA.
+//   * "grid" flavour (P = 1, the 7x7 stage-3 / decoder maps): one CTA per sample, one thread per channel holding
+//     the channel's whole 7x7 input AND its 49 taps in registers; masked cells are skipped by warp-uniform
+//     branches (the mask is per sample).
+// LayerNorm over C runs from a shared [pixels][C] tile (warp per pixel), then the tile -- contiguous in the
+// Z-ordered row layout -- leaves with coalesced float4 stores.
+//
+// Replaces MinkowskiEngine/src/depthwise_convolution_kernel.cu:27-52 (fwd) and :69-122 (bwd).
+#pragma once
+#include "dwconv.cuh"
+
+namespace mpmae {
+
+__device__ __forceinline__ int zorder3(int py, int px) {
+  auto spread = [](int b) { return (b & 1) | ((b & 2) << 1) | ((b & 4) << 2); };
+  return spread(py) | (spread(px) << 1);
+}
+
+struct DwTiledArgs {
+  DwArgs a;
+  const int *vis_patch;  // [B*V] patch index of every slot (null in dense mode)
+};
+
+// stage the halo window of visible patch `pu` = n*V + slot:  win[(wy*W + wx)*C + c]
+template <int P>
+__device__ __forceinline__ void load_patch_window(const float *__restrict__ x, const int *nb, int n, int V, int C,
+                                                  float *win, int nthreads) {
+  constexpr int W = P + 6, NBR = (3 + P - 1) / P, NBW = 2 * NBR + 1;
+  const int C4 = C >> 2;
+  for (int i = threadIdx.x; i < W * W * C4; i += nthreads) {
+    const int wp = i / C4, c4 = i - wp * C4;
+    const int wy = wp / W, wx = wp - wy * W;
+    const int ry = wy - 3 + NBR * P, rx = wx - 3 + NBR * P;  // >= 0
+    const int by = ry / P, bx = rx / P;
+    const int slot = nb[by * NBW + bx];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slot >= 0) {
+      const int64_t row = ((int64_t)n * V + slot) * (P * P) + zorder3(ry - by * P, rx - bx * P);
+      v = __ldg(reinterpret_cast<const float4 *>(x + row * C) + c4);
+    }
+    *reinterpret_cast<float4 *>(win + (size_t)wp * C + c4 * 4) = v;
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void load_neighbour_slots(const int *slot_of, const Geo &g, int n, int l, int *nb) {
+  constexpr int NBR = (3 + P - 1) / P, NBW = 2 * NBR + 1;
+  if (threadIdx.x < NBW * NBW) {
+    const int qy = l / g.G + (int)threadIdx.x / NBW - NBR, qx = l % g.G + (int)threadIdx.x % NBW - NBR;
+    nb[threadIdx.x] = (qy >= 0 && qx >= 0 && qy < g.G && qx < g.G) ? slot_of[n * g.L + qy * g.G + qx] : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ patch flavour
+template <int P, int TR>
+__global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
+  constexpr int W = P + 6, TILES = P / TR;
+  const DwArgs &p = t.a;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int nb[25];
+  const int C = p.C, V = p.geo.V;
+  float *win = smem;                         // [W*W][C]
+  float *ubuf = win + (size_t)W * W * C;     // [P*P][C]
+  const int pu = blockIdx.x, n = pu / V;
+  const int l = t.vis_patch[pu];
+  const int nthreads = blockDim.x;
+  load_neighbour_slots<P>(p.slot_of, p.geo, n, l, nb);
+  __syncthreads();
+  load_patch_window<P>(p.x, nb, n, V, C, win, nthreads);
+
+  const int item = threadIdx.x;
+  const bool active = item < C * TILES;
+  const int c = item % C, y0 = (item / C) * TR;
+  float wreg[49];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 49; ++k) {
+      const int kh = k / 7, kw = k % 7;
+      const int a = p.flip ? 6 - kh : kh, b = p.flip ? 6 - kw : kw;
+      wreg[k] = __ldg(p.w + a * p.w_skh + b * p.w_skw + c * p.w_sc);
+    }
+  }
+  __syncthreads();
+  if (active) {
+    float acc[TR][P];
+    const float b0 = p.bias ? __ldg(p.bias + c) : 0.f;
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+      for (int ox = 0; ox < P; ++ox) acc[r][ox] = b0;
+#pragma unroll
+    for (int iy = 0; iy < TR + 6; ++iy) {
+      float in[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) in[j] = win[(size_t)((y0 + iy) * W + j) * C + c];
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const int kh = iy - r;
+        if (kh >= 0 && kh < 7) {
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+            for (int ox = 0; ox < P; ++ox) acc[r][ox] = fmaf(in[ox + kw], wreg[kh * 7 + kw], acc[r][ox]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+      for (int ox = 0; ox < P; ++ox) ubuf[(size_t)zorder3(y0 + r, ox) * C + c] = acc[r][ox];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+  const int64_t row0 = (int64_t)pu * (P * P);
+  if (p.do_ln) {
+    for (int o = warp; o < P * P; o += nw) {
+      float *ur = ubuf + (size_t)o * C;
+      float s = 0.f;
+      for (int cc = lane; cc < C; cc += 32) s += ur[cc];
+      const float mean = warp_sum(s) / (float)C;
+      float v = 0.f;
+      for (int cc = lane; cc < C; cc += 32) { const float d = ur[cc] - mean; v += d * d; }
+      const float rstd = rsqrtf(warp_sum(v) / (float)C + p.eps);
+      for (int cc = lane; cc < C; cc += 32) ur[cc] = (ur[cc] - mean) * rstd;
+      if (lane == 0) p.rstd[row0 + o] = rstd;
+    }
+    __syncthreads();
+  }
+  // the patch's rows are contiguous: coalesced float4 copy-out (+ residual)
+  const int n4 = P * P * C / 4;
+  float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+  const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+  for (int i = threadIdx.x; i < n4; i += nthreads) {
+    float4 v = reinterpret_cast<const float4 *>(ubuf)[i];
+    if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    dst[i] = v;
+  }
+}
+
+// dW[tap, c] += sum du[o, c] * x[o + off(tap), c] ; db[c] += sum du[o, c].  Persistent CTAs: every thread keeps its
+// channel's 49 partial sums in registers across all the patches it visits.
+template <int P, int TR>
+__global__ void __launch_bounds__(512) dwconv_patch_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+  constexpr int W = P + 6, TILES = P / TR;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int nb[25];
+  const int C = p.C, V = p.geo.V;
+  float *win = smem;                         // [W*W][C]   x halo window
+  float *dus = win + (size_t)W * W * C;      // [P*P][C]   du of the patch (Z-order) ; reused for the final reduction
+  const int nthreads = blockDim.x;
+  const int item = threadIdx.x;
+  const bool active = item < C * TILES;
+  const int c = item % C, y0 = (item / C) * TR;
+  float dw[49];
+  float db = 0.f;
+#pragma unroll
+  for (int k = 0; k < 49; ++k) dw[k] = 0.f;
+  const int units = p.geo.B * V;
+  for (int pu = blockIdx.x; pu < units; pu += gridDim.x) {
+    const int n = pu / V, l = vis_patch[pu];
+    __syncthreads();
+    load_neighbour_slots<P>(p.slot_of, p.geo, n, l, nb);
+    __syncthreads();
+    load_patch_window<P>(p.x, nb, n, V, C, win, nthreads);
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(p.du + (int64_t)pu * (P * P) * C);
+      for (int i = threadIdx.x; i < P * P * C / 4; i += nthreads) reinterpret_cast<float4 *>(dus)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (active) {
+      float d[TR][P];
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int ox = 0; ox < P; ++ox) { d[r][ox] = dus[(size_t)zorder3(y0 + r, ox) * C + c]; db += d[r][ox]; }
+#pragma unroll
+      for (int iy = 0; iy < TR + 6; ++iy) {
+        float in[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) in[j] = win[(size_t)((y0 + iy) * W + j) * C + c];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          const int kh = iy - r;
+          if (kh >= 0 && kh < 7) {
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+              for (int ox = 0; ox < P; ++ox) dw[kh * 7 + kw] = fmaf(d[r][ox], in[ox + kw], dw[kh * 7 + kw]);
+          }
+        }
+      }
+    }
+  }
+  // reduce the TILES strips of each channel in shared memory, then one atomic per (tap, channel) per CTA
+  __syncthreads();
+  float *red = smem;  // [50][C]
+  for (int i = threadIdx.x; i < 50 * C; i += nthreads) red[i] = 0.f;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 49; ++k) atomicAdd(&red[k * C + c], dw[k]);
+    atomicAdd(&red[49 * C + c], db);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 49 * C; i += nthreads) {
+    const int k = i / C, cc = i - k * C;
+    const int kh = k / 7, kw = k - kh * 7;
+    atomicAdd(&p.dw[kh * p.w_skh + kw * p.w_skw + cc * p.w_sc], red[i]);
+  }
+  if (p.dbias)
+    for (int cc = threadIdx.x; cc < C; cc += nthreads) atomicAdd(&p.dbias[cc], red[49 * C + cc]);
+}
+
+// ------------------------------------------------------------------------------------------------ grid flavour (P = 1, G = 7)
+__global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) {
+  constexpr int G = 7, L = 49;
+  extern __shared__ __align__(16) float smem[];   // ubuf [V][C]
+  __shared__ int slot_s[L];
+  const int C = p.C, V = p.geo.V, n = blockIdx.x;
+  const int nthreads = blockDim.x;
+  if (threadIdx.x < L) slot_s[threadIdx.x] = p.slot_of ? p.slot_of[n * L + threadIdx.x] : (int)threadIdx.x;
+  __syncthreads();
+  const int64_t row0 = (int64_t)n * V;
+  for (int c = threadIdx.x; c < C; c += nthreads) {
+    float x[L], w[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int s = slot_s[i];
+      x[i] = s >= 0 ? __ldg(p.x + (row0 + s) * C + c) : 0.f;
+      const int kh = i / 7, kw = i % 7;
+      const int a = p.flip ? 6 - kh : kh, b = p.flip ? 6 - kw : kw;
+      w[i] = __ldg(p.w + a * p.w_skh + b * p.w_skw + c * p.w_sc);
+    }
+    const float b0 = p.bias ? __ldg(p.bias + c) : 0.f;
+#pragma unroll
+    for (int oy = 0; oy < G; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < G; ++ox) {
+        const int s = slot_s[oy * G + ox];
+        if (s >= 0) {  // warp-uniform: the mask is per sample
+          float acc = b0;
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int iy = oy + kh - 3, ix = ox + kw - 3;
+              if (iy >= 0 && iy < G && ix >= 0 && ix < G) acc = fmaf(x[iy * G + ix], w[kh * 7 + kw], acc);
+            }
+          smem[(size_t)s * C + c] = acc;
+        }
+      }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+  if (p.do_ln) {
+    for (int o = warp; o < V; o += nw) {
+      float *ur = smem + (size_t)o * C;
+      float s = 0.f;
+      for (int cc = lane; cc < C; cc += 32) s += ur[cc];
+      const float mean = warp_sum(s) / (float)C;
+      float v = 0.f;
+      for (int cc = lane; cc < C; cc += 32) { const float d = ur[cc] - mean; v += d * d; }
+      const float rstd = rsqrtf(warp_sum(v) / (float)C + p.eps);
+      for (int cc = lane; cc < C; cc += 32) ur[cc] = (ur[cc] - mean) * rstd;
+      if (lane == 0) p.rstd[row0 + o] = rstd;
+    }
+    __syncthreads();
+  }
+  const int n4 = V * C / 4;
+  float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+  const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+  for (int i = threadIdx.x; i < n4; i += nthreads) {
+    float4 v = reinterpret_cast<const float4 *>(smem)[i];
+    if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    dst[i] = v;
+  }
+}
+
+// weight gradient on the 7x7 maps: thread per channel, x[49] and dW[49] in registers, persistent over samples
+__global__ void __launch_bounds__(128) dwconv_grid7_wgrad_kernel(DwWgradArgs p) {
+  constexpr int G = 7, L = 49;
+  __shared__ int slot_s[L];
+  const int C = p.C, V = p.geo.V;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = c < C;
+  float dw[L];
+  float db = 0.f;
+#pragma unroll
+  for (int i = 0; i < L; ++i) dw[i] = 0.f;
+  for (int n = blockIdx.x; n < p.geo.B; n += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < L) slot_s[threadIdx.x] = p.slot_of ? p.slot_of[n * L + threadIdx.x] : (int)threadIdx.x;
+    __syncthreads();
+    if (!active) continue;
+    const int64_t row0 = (int64_t)n * V;
+    float x[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int s = slot_s[i];
+      x[i] = s >= 0 ? __ldg(p.x + (row0 + s) * C + c) : 0.f;
+    }
+#pragma unroll
+    for (int oy = 0; oy < G; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < G; ++ox) {
+        const int s = slot_s[oy * G + ox];
+        if (s >= 0) {
+          const float d = __ldg(p.du + (row0 + s) * C + c);
+          db += d;
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int iy = oy + kh - 3, ix = ox + kw - 3;
+              if (iy >= 0 && iy < G && ix >= 0 && ix < G) dw[kh * 7 + kw] = fmaf(d, x[iy * G + ix], dw[kh * 7 + kw]);
+            }
+        }
+      }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      const int kh = k / 7, kw = k % 7;
+      atomicAdd(&p.dw[kh * p.w_skh + kw * p.w_skw + c * p.w_sc], dw[k]);
+    }
+    if (p.dbias) atomicAdd(&p.dbias[c], db);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <int P, int TR>
+inline cudaError_t launch_patch(const DwTiledArgs &t, cudaStream_t st) {
+  const int C = t.a.C;
+  const int threads = ((C * (P / TR) + 31) / 32) * 32;
+  const size_t sm = ((size_t)(P + 6) * (P + 6) + P * P) * C * sizeof(float);
+  if (threads > 512 || sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_kernel<P, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dwconv_patch_kernel<P, TR><<<t.a.geo.B * t.a.geo.V, threads, sm, st>>>(t);
+  return cudaGetLastError();
+}
+
+template <int P, int TR>
+inline cudaError_t launch_patch_wgrad(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  const int C = p.C;
+  const int threads = ((C * (P / TR) + 31) / 32) * 32;
+  size_t sm = ((size_t)(P + 6) * (P + 6) + P * P) * C * sizeof(float);
+  if (sm < (size_t)50 * C * sizeof(float)) sm = (size_t)50 * C * sizeof(float);
+  if (threads > 512 || sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_wgrad_kernel<P, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int per_sm = (int)((220 * 1024) / sm);
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  const int units = p.geo.B * p.geo.V;
+  if (grid > units) grid = units;
+  dwconv_patch_wgrad_kernel<P, TR><<<grid, threads, sm, st>>>(p, vis_patch);
+  return cudaGetLastError();
+}
+
+// Dispatch: returns cudaErrorInvalidConfiguration when the tiled kernels do not take the shape (caller falls back).
+inline cudaError_t launch_dwconv_tiled(const DwArgs &a, const int *vis_patch, cudaStream_t st) {
+  if (a.C % 4 != 0) return cudaErrorInvalidConfiguration;
+  if (a.P == 1) {
+    if (a.geo.G != 7) return cudaErrorInvalidConfiguration;
+    const size_t sm = (size_t)a.geo.V * a.C * sizeof(float);
+    if (sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(dwconv_grid7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) return e;
+      configured = true;
+    }
+    int threads = ((a.C + 31) / 32) * 32;
+    if (threads > 512) threads = 512;
+    dwconv_grid7_kernel<<<a.geo.B, threads, sm, st>>>(a);
+    return cudaGetLastError();
+  }
+  if (!vis_patch || !a.slot_of) return cudaErrorInvalidConfiguration;
+  DwTiledArgs t{a, vis_patch};
+  if (a.P == 8) return launch_patch<8, 2>(t, st);
+  if (a.P == 4) return launch_patch<4, 2>(t, st);
+  if (a.P == 2) return launch_patch<2, 2>(t, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+inline cudaError_t launch_dwconv_wgrad_tiled(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  if (p.C % 4 != 0) return cudaErrorInvalidConfiguration;
+  if (p.P == 1) {
+    if (p.geo.G != 7) return cudaErrorInvalidConfiguration;
+    const int threads = p.C >= 128 ? 128 : ((p.C + 31) / 32) * 32;
+    const int cy = (p.C + threads - 1) / threads;
+    int gx = (148 * 4) / cy;
+    if (gx < 1) gx = 1;
+    if (gx > p.geo.B) gx = p.geo.B;
+    dwconv_grid7_wgrad_kernel<<<dim3(gx, cy), threads, 0, st>>>(p);
+    return cudaGetLastError();
+  }
+  if (!vis_patch || !p.slot_of) return cudaErrorInvalidConfiguration;
+  if (p.P == 8) return launch_patch_wgrad<8, 2>(p, vis_patch, st);
+  if (p.P == 4) return launch_patch_wgrad<4, 2>(p, vis_patch, st);
+  if (p.P == 2) return launch_patch_wgrad<2, 2>(p, vis_patch, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace mpmae

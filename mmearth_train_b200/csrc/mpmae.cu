@@ -17,6 +17,7 @@
 #include "../../include/mpmae.h"
 #include "common.cuh"
 #include "dwconv.cuh"
+#include "dwconv_tiled.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "loss.cuh"
@@ -371,6 +372,18 @@ struct Ctx {
   }
 };
 
+// register-tiled depthwise kernels, generic kernels for the shapes they do not take
+cudaError_t dw_launch(const DwArgs &d, const int *vis, cudaStream_t st) {
+  cudaError_t e = launch_dwconv_tiled(d, vis, st);
+  if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_dwconv_fwd(d, st); }
+  return e;
+}
+cudaError_t dw_wgrad_launch(const DwWgradArgs &d, const int *vis, cudaStream_t st) {
+  cudaError_t e = launch_dwconv_wgrad_tiled(d, vis, st);
+  if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_dwconv_wgrad(d, st); }
+  return e;
+}
+
 template <int MODE>
 void gemm(Ctx &c, const GemmArgs &a, const char *what) {
   if (!c.ok() || a.M <= 0) return;
@@ -419,7 +432,7 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   if (dense) d.geo.V = pl->geo.L;
   d.P = P; d.C = C; d.flip = 0; d.do_ln = 1; d.eps = 1e-6f;
   c.acct(4.0 * (2.0 * R * C + R + 50.0 * C), 2.0 * 49 * (double)R * C);
-  if (c.ok()) c.check(launch_dwconv_fwd(d, c.st), "dwconv_fwd");
+  if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_fwd");
 
   FoldArgs f{};
   f.W = c.p(bp.w1); f.s_n = C; f.s_k = 1; f.scale_k = c.p(bp.ln_w); f.shift_k = c.p(bp.ln_b);
@@ -554,12 +567,12 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   if (dense) d.geo.V = pl->geo.L;
   d.P = P; d.C = C; d.flip = 1; d.do_ln = 0; d.eps = 0.f;
   c.acct(4.0 * (3.0 * R * C + 49.0 * C), 2.0 * 49 * (double)R * C);
-  if (c.ok()) c.check(launch_dwconv_fwd(d, c.st), "dwconv_dx");
+  if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_dx");
   DwWgradArgs dwg{};
   dwg.x = x; dwg.du = du; dwg.dw = c.g(bp.dw_k); dwg.w_skh = d.w_skh; dwg.w_skw = d.w_skw; dwg.w_sc = d.w_sc;
   dwg.dbias = c.g(bp.dw_b); dwg.slot_of = d.slot_of; dwg.geo = d.geo; dwg.P = P; dwg.C = C;
   c.acct(4.0 * (2.0 * R * C + 50.0 * C), 2.0 * 50 * (double)R * C);
-  if (c.ok()) c.check(launch_dwconv_wgrad(dwg, c.st), "dwconv_wgrad");
+  if (c.ok()) c.check(dw_wgrad_launch(dwg, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_wgrad");
 }
 
 InitConvArgs init_args(Ctx &c) {
