@@ -133,9 +133,10 @@ int mpmae_backward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
 /* dense encoder features [B, C3, G, G] (zeros at masked cells) from the last forward */
 int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw, void *cuda_stream);
 
-/* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias) */
+/* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias).
+ * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (needs scratch of 2*N*K floats), 2 = tcgen05 single-pass TF32 */
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
-                    int64_t M, int32_t N, int32_t K, void *cuda_stream);
+                    int64_t M, int32_t N, int32_t K, float *scratch, void *cuda_stream);
 
 /* Fused AdamW over flat buffers (torch.optim.AdamW semantics; the reference builds its optimizer at
  * main_pretrain.py:312-320).  decay_mask: one byte per element (null = decay everything);

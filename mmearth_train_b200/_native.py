@@ -70,7 +70,7 @@ def _load():
         "mpmae_forward_encoder": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_backward": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_encoder_features": (C.c_int, [P, C.POINTER(IO), P, P]),
-        "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P]),
+        "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P, P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
     }
     for name, (res, args) in sig.items():

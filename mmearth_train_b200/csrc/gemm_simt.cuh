@@ -21,6 +21,7 @@ constexpr int kMaxGroupsPerTile = 12;
 struct GemmArgs {
   const float *A;      // [M, K] row-major
   const float *Bw;     // [N, K] row-major ("weight [out, in]")
+  const float *Bw_lo;  // optional low part of a TF32 hi/lo split of the weight (Bw then holds the high part); null = none
   const float *bias;   // [N] or null
   const float *resid;  // [M, N] or null (EPI_STORE)
   float *out;          // [M, N]
@@ -77,7 +78,13 @@ __global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) {
     for (int t = tid; t < BN * 2; t += NTHR) {
       const int r = t >> 1, kq = (t & 1) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + r < p.N) v = *reinterpret_cast<const float4 *>(p.Bw + (int64_t)(n0 + r) * p.K + k0 + kq);
+      if (n0 + r < p.N) {
+        v = *reinterpret_cast<const float4 *>(p.Bw + (int64_t)(n0 + r) * p.K + k0 + kq);
+        if (p.Bw_lo) {
+          const float4 l = *reinterpret_cast<const float4 *>(p.Bw_lo + (int64_t)(n0 + r) * p.K + k0 + kq);
+          v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+        }
+      }
       Bs[kq + 0][r] = v.x; Bs[kq + 1][r] = v.y; Bs[kq + 2][r] = v.z; Bs[kq + 3][r] = v.w;
     }
     __syncthreads();

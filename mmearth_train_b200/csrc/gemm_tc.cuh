@@ -1,9 +1,544 @@
-// tcgen05 (5th-generation tensor core) GEMM path -- placeholder until the TMA/TMEM kernel lands.
+// tcgen05 (5th-generation tensor core) GEMM for the pointwise / strided convolutions:
+//     out[M, N] = A[M, K] . Bw[N, K]^T   (+ fused epilogue, same EpiMode contract as gemm_simt.cuh)
+//
+// sm_100a only, written directly against the PTX ISA (no CUTLASS):
+//   * TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) streams [128 x 32] fp32 A tiles and [BN x 32] weight tiles
+//     into a 4-stage shared-memory ring; out-of-range rows / K-tail columns are zero-filled by the TMA unit, so
+//     ragged M, N and K (e.g. K = 40) need no padding in HBM;
+//   * ONE elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN <= 256, K = 8 per instruction),
+//     accumulating in TMEM; two accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of
+//     tile i+1; tcgen05.commit releases shared-memory slots / publishes accumulators through mbarriers;
+//   * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per warp), apply the fused
+//     epilogue (bias, GELU, residual, GRN statistics, GELU backward) and write rows straight to HBM;
+//   * persistent CTAs (one per SM) walk the tile list with N fastest so the A tile is re-used from L2.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+// Precision: kind::tf32 keeps 10 mantissa bits of each operand.  backend 2 = single pass;
+// backend 1 = "3xTF32": weights pre-split into hi/lo parts by the caller, activations split in shared memory by the
+// epilogue-side splitter, D += Ahi.Bhi + Alo.Bhi + Ahi.Blo (fp32-faithful, 3x tensor work).
 #pragma once
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "gemm_simt.cuh"
 
 namespace mpmae {
-inline bool tc_gemm_supported(int /*mode*/, const GemmArgs & /*a*/) { return false; }
+namespace tc {
+
+constexpr int BM = 128, BK = 32, STAGES = 4, ACC_STAGES = 2;
+constexpr uint64_t kSpinLimit = 4000000000ull;  // ~2 s of SM clocks: a lost barrier traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both K-major, fp32 storage consumed as TF32
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).  cute/arch/mma_sm100_desc.hpp field layout.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Transposed warp reduction: every lane holds v[0..32); afterwards lane l returns sum over lanes of v[l].
+// 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float *v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+struct TcParams {
+  GemmArgs g;
+  int bn;        // N tile (multiple of 16, <= 256)
+  int num_m, num_n, num_k;
+  int stages;    // shared-memory ring depth (<= STAGES)
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void tmem_ld16v(uint32_t taddr, float *v) { tmem_ld16(taddr, v); }
+
+// Transposed warp reduction over 16 columns: lane l returns sum over all 32 lanes of v[l & 15].
+__device__ __forceinline__ float warp_colsum16(float *v, int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
+constexpr int kThreadsNoSplit = 64 + kEpiThreads, kThreadsSplit = kThreadsNoSplit + 128;
+
+// SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
+// (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
+// tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
+template <int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsNoSplit, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int bn = p.bn, nstage = p.stages;
+  constexpr uint32_t a_bytes = BM * BK * 4;
+  const uint32_t b_bytes = (uint32_t)bn * BK * 4;
+  const uint32_t a_span = SPLIT ? 2 * a_bytes : a_bytes;             // [A | Alo]
+  const uint32_t stage_bytes = a_span + (SPLIT ? 2 : 1) * b_bytes;   // [A | Alo | B | Blo]
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)nstage * stage_bytes);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *split_bar = empty_bar + STAGES;
+  uint64_t *tfull_bar = split_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
+  float *colacc = reinterpret_cast<float *>(tmem_ptr + 4);           // [kTcGroups][bn]
+  constexpr int kTcGroups = 4;                                       // a 128-row tile spans <= 4 groups of >= 32 rows
+  float *colacc2 = colacc + kTcGroups * bn;                          // [bn]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmArgs &g = p.g;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
+  if (MODE != EPI_STORE && warp >= 2 && warp < 2 + kEpiWarps) {
+    for (int i = threadIdx.x - 64; i < (kTcGroups + 1) * bn; i += kEpiThreads) colacc[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int total_tiles = p.num_m * p.num_n;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n, n_blk = tile - m_blk * p.num_n;
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], a_bytes + (SPLIT ? 2 : 1) * b_bytes);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa + a_span, &map_b, &full_bar[stage], kb * BK, n_blk * bn);
+          if (SPLIT) tma_load_2d(sa + a_span + b_bytes, &map_b_lo, &full_bar[stage], kb * BK, n_blk * bn);
+          if (++stage == nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(bn);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (SPLIT) mbar_wait(&split_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_span);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes per instruction: advance the start address by 2 (x16 B)
+            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          if (SPLIT) {
+            const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sa + a_span + b_bytes);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
+          if (kb == p.num_k - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == nstage) { stage = 0; phase ^= 1; }
+        }
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ================================================================ epilogue: 8 warps, TMEM lane quarter = warp % 4,
+    // the two warps of a quarter take alternate 16-column chunks
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n, n_blk = tile - m_blk * p.num_n;
+      const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < g.M;
+      const int n_base = n_blk * bn;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
+      const int64_t g_first = ((int64_t)m_blk * BM) / g.group_rows;
+      const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
+      const int gw_lo = (int)(mw0 / g.group_rows - g_first);
+      const int64_t mw_last = (mw0 + 31 < g.M ? mw0 + 31 : g.M - 1);
+      const int gw_hi = mw_last >= mw0 ? (int)(mw_last / g.group_rows - g_first) : gw_lo;
+      const int my_g = row_ok ? (int)(m / g.group_rows - g_first) : gw_lo;
+
+      for (int c0 = half * 16; c0 < bn; c0 += 32) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        float s1[16], s2[16];  // statistics contributions (dead code for EPI_STORE)
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const int n = n_base + c0 + j4;
+          const bool col_ok = n < g.N;   // N % 4 == 0: a float4 is entirely in or out
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f), o2 = o;
+          float4 st1 = o, st2 = o;
+          if (col_ok) {
+            const float4 acc = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+            if (MODE == EPI_STORE) {
+              o = acc;
+              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (g.resid && row_ok) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(g.resid + m * g.N + n));
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+            } else if (MODE == EPI_GELU_SQ) {
+              o = acc;
+              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              o2 = make_float4(gelu_f(o.x), gelu_f(o.y), gelu_f(o.z), gelu_f(o.w));
+              if (row_ok) st1 = make_float4(o2.x * o2.x, o2.y * o2.y, o2.z * o2.z, o2.w * o2.w);
+            } else if (MODE == EPI_DG) {
+              o = acc;
+              if (row_ok) {
+                const float4 h = __ldg(reinterpret_cast<const float4 *>(g.aux + m * g.N + n));
+                st1 = make_float4(acc.x * h.x, acc.y * h.y, acc.z * h.z, acc.w * h.w);
+                st2 = acc;
+              }
+            } else {  // EPI_DH_GELU
+              if (row_ok) {
+                const float4 h = __ldg(reinterpret_cast<const float4 *>(g.aux + m * g.N + n));
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(g.aux2 + m * g.N + n));
+                float4 kgv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.kg) kgv = __ldg(reinterpret_cast<const float4 *>(g.kg + (g_first + my_g) * g.N + n));
+                o.x = (acc.x + kgv.x * h.x) * gelu_grad_f(a.x);
+                o.y = (acc.y + kgv.y * h.y) * gelu_grad_f(a.y);
+                o.z = (acc.z + kgv.z * h.z) * gelu_grad_f(a.z);
+                o.w = (acc.w + kgv.w * h.w) * gelu_grad_f(a.w);
+                st2 = o;
+              }
+            }
+            if (row_ok) {
+              *reinterpret_cast<float4 *>(g.out + m * g.N + n) = o;
+              if (MODE == EPI_GELU_SQ) *reinterpret_cast<float4 *>(g.out2 + m * g.N + n) = o2;
+            }
+          }
+          if (MODE != EPI_STORE) {
+            s1[j4] = st1.x; s1[j4 + 1] = st1.y; s1[j4 + 2] = st1.z; s1[j4 + 3] = st1.w;
+            s2[j4] = st2.x; s2[j4 + 1] = st2.y; s2[j4 + 2] = st2.z; s2[j4 + 3] = st2.w;
+          }
+        }
+        if (MODE != EPI_STORE) {
+          // column sums over the warp's 32 rows (per statistics group), then one shared-memory atomic per column
+          const int col = c0 + (lane & 15);
+          if (MODE == EPI_GELU_SQ || MODE == EPI_DG) {
+            if (gw_hi == gw_lo) {
+              const float t = warp_colsum16(s1, lane);
+              if (lane < 16) atomicAdd(&colacc[gw_lo * bn + col], t);
+            } else {
+              float lo[16], hi[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { lo[j] = (my_g == gw_lo) ? s1[j] : 0.f; hi[j] = (my_g == gw_lo) ? 0.f : s1[j]; }
+              const float tl = warp_colsum16(lo, lane), th = warp_colsum16(hi, lane);
+              if (lane < 16) { atomicAdd(&colacc[gw_lo * bn + col], tl); atomicAdd(&colacc[gw_hi * bn + col], th); }
+            }
+          }
+          if (MODE == EPI_DG || MODE == EPI_DH_GELU) {
+            const float t = warp_colsum16(s2, lane);
+            if (lane < 16) atomicAdd(&colacc2[col], t);
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+
+      if (MODE != EPI_STORE) {
+        // flush this tile's column statistics (epilogue warps only: named barrier 1)
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        const int64_t m_last = ((int64_t)(m_blk + 1) * BM < g.M ? (int64_t)(m_blk + 1) * BM : g.M) - 1;
+        const int ng = (int)(m_last / g.group_rows - g_first) + 1;
+        if ((MODE == EPI_GELU_SQ || MODE == EPI_DG) && g.colsum) {
+          for (int i = et; i < ng * bn; i += kEpiThreads) {
+            const int gg = i / bn, cidx = i - gg * bn;
+            if (n_base + cidx < g.N) atomicAdd(&g.colsum[(g_first + gg) * g.N + n_base + cidx], colacc[i]);
+            colacc[i] = 0.f;
+          }
+        }
+        if ((MODE == EPI_DG || MODE == EPI_DH_GELU) && g.colsum2) {
+          for (int i = et; i < bn; i += kEpiThreads) {
+            if (n_base + i < g.N) atomicAdd(&g.colsum2[n_base + i], colacc2[i]);
+            colacc2[i] = 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+    }
+  } else if (SPLIT) {
+    // ================================================================ A splitter (4 warps): hi in place, lo next to it
+    const int stid = threadIdx.x - kThreadsNoSplit;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4 *A = reinterpret_cast<float4 *>(smem + (size_t)stage * stage_bytes);
+        float4 *Alo = A + a_bytes / 16;
+#pragma unroll
+        for (int i = 0; i < (int)(a_bytes / 16) / 128; ++i) {
+          const float4 x = A[i * 128 + stid];
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
+          hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
+          hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
+          hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
+          A[i * 128 + stid] = hi;
+          Alo[i * 128 + stid] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+        if (++stage == nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// [rows, cols] fp32 row-major, box = [box_rows, 32] with 128-byte swizzle, zero fill outside
+inline bool make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct MapCache {
+  std::mutex mu;
+  std::map<std::tuple<const void *, int64_t, int64_t, int>, CUtensorMap> maps;
+  bool get(CUtensorMap *out, const float *ptr, int64_t rows, int64_t cols, int box_rows) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((const void *)ptr, rows, cols, box_rows);
+    auto it = maps.find(key);
+    if (it == maps.end()) {
+      CUtensorMap m;
+      if (!make_map(&m, ptr, rows, cols, box_rows)) return false;
+      it = maps.emplace(key, m).first;
+    }
+    *out = it->second;
+    return true;
+  }
+};
+inline MapCache &map_cache() { static MapCache c; return c; }
+
+inline int pick_bn(int N) {
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 256;
+}
+
+}  // namespace tc
+
+inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
+  if (a.M < 1 || a.N < 8 || a.K < 8) return false;
+  if (a.K % 4 != 0 || a.N % 4 != 0) return false;
+  if (((uintptr_t)a.A | (uintptr_t)a.Bw | (uintptr_t)a.out) & 15) return false;
+  if (mode != EPI_STORE && a.group_rows < 32) return false;
+  if (a.M < 64) return false;  // a 128-row MMA tile would be mostly padding: tiny products stay on the SIMT path
+  return tc::encode_fn() != nullptr;
+}
+
+template <int MODE, bool SPLIT>
+inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) {
+  using namespace tc;
+  TcParams p{};
+  p.g = a;
+  int bn = pick_bn(a.N);
+  if (SPLIT && bn > 160) {   // [A | Alo | Bhi | Blo] x 3 stages must fit in 227 KB
+    bn = 0;
+    for (int c = 160; c >= 64; c -= 16)
+      if (a.N % c == 0) { bn = c; break; }
+    if (!bn) bn = 128;
+  }
+  p.bn = bn;
+  p.num_m = (int)cdiv64(a.M, BM);
+  p.num_n = cdiv(a.N, p.bn);
+  p.num_k = cdiv(a.K, BK);
+  p.stages = SPLIT ? 3 : 4;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(ACC_STAGES * p.bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap ma, mb, mbl;
+  if (!map_cache().get(&ma, a.A, a.M, a.K, BM) || !map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
+  mbl = mb;
+  if (SPLIT && !map_cache().get(&mbl, a.Bw_lo, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
+  const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)5 * p.bn * 4;
+  if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = p.num_m * p.num_n;
+  if (grid > 148) grid = 148;
+  gemm_tc_kernel<MODE, SPLIT><<<grid, SPLIT ? kThreadsSplit : kThreadsNoSplit, smem, st>>>(ma, mb, mbl, p);
+  return cudaGetLastError();
+}
+
 template <int MODE>
-inline cudaError_t launch_gemm_rows_tc(const GemmArgs &, int, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t launch_gemm_rows_tc(const GemmArgs &a, int backend, cudaStream_t st) {
+  if (backend == 1 && a.Bw_lo) return launch_gemm_rows_tc_impl<MODE, true>(a, st);
+  return launch_gemm_rows_tc_impl<MODE, false>(a, st);
+}
+
 }  // namespace mpmae

@@ -196,7 +196,11 @@ struct FoldArgs {
   float *WfT;            // [K, N] or null
   float *bf;             // [N] or null
   int N, K, SL;
+  // 3xTF32: when set, Wf / WfT receive the TF32-representable high part and these the remainder (w - hi)
+  float *Wf_lo;
+  float *WfT_lo;
 };
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __global__ void fold_kernel(FoldArgs p) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= p.N) return;
@@ -207,8 +211,11 @@ __global__ void fold_kernel(FoldArgs p) {
     const float w = p.W[n * p.s_n + k * p.s_k];
     const int j = k % p.SL;
     const float wf = w * (p.scale_k ? p.scale_k[j] : 1.f) * sn;
-    if (p.Wf) p.Wf[(int64_t)n * p.K + k] = wf;
-    if (p.WfT) p.WfT[(int64_t)k * p.N + n] = wf;
+    const float hi = tf32_hi(wf);
+    if (p.Wf) p.Wf[(int64_t)n * p.K + k] = p.Wf_lo ? hi : wf;
+    if (p.Wf_lo) p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
+    if (p.WfT) p.WfT[(int64_t)k * p.N + n] = p.WfT_lo ? hi : wf;
+    if (p.WfT_lo) p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
     if (p.shift_k) acc = fmaf(w, p.shift_k[j], acc);
   }
   if (p.bf) {

@@ -78,7 +78,7 @@ struct mpmae_plan {
   std::vector<BlockW> dw;
   int64_t o_z, o_xd, o_pooled, o_pool_rstd, o_dpix, o_dimg, o_acc, o_cs_pix, o_cs_img, o_dpooled;
   int64_t o_zero_begin, o_zero_end;  // statistics region cleared at the start of forward
-  int64_t o_wf, o_wft, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
+  int64_t o_wf, o_wft, o_wf_lo, o_wft_lo, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
   int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
   int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
   int launches_fwd = 0, launches_bwd = 0;
@@ -312,6 +312,8 @@ void build_workspace(mpmae_plan *pl) {
   // weight-fold scratch + backward temporaries
   pl->o_wf = ws_alloc(pl, nullptr, 1, pl->max_wf);
   pl->o_wft = ws_alloc(pl, nullptr, 1, pl->max_wf);
+  pl->o_wf_lo = ws_alloc(pl, nullptr, 1, pl->max_wf);
+  pl->o_wft_lo = ws_alloc(pl, nullptr, 1, pl->max_wf);
   pl->o_bf = ws_alloc(pl, nullptr, 1, pl->max_n);
   pl->o_dwf = ws_alloc(pl, nullptr, 1, pl->max_wf);
   pl->o_dbf = ws_alloc(pl, nullptr, 1, pl->max_n);
@@ -384,16 +386,33 @@ cudaError_t dw_wgrad_launch(const DwWgradArgs &d, const int *vis, cudaStream_t s
   return e;
 }
 
+void fold(Ctx &c, FoldArgs a, const char *what);
+
 template <int MODE>
-void gemm(Ctx &c, const GemmArgs &a, const char *what) {
-  if (!c.ok() || a.M <= 0) return;
+void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
+  if (!c.ok() || a_in.M <= 0) return;
+  GemmArgs a = a_in;
+  mpmae_plan *pl = c.pl;
+  const bool use_tc = pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a);
+  if (pl->cfg.gemm_backend == 1) {
+    // 3xTF32: the weight operand is consumed as a (hi, lo) pair; folded weights were written that way by fold(),
+    // raw parameter matrices are split here into the scratch buffers
+    if (a.Bw == c.w(pl->o_wf)) a.Bw_lo = c.w(pl->o_wf_lo);
+    else if (a.Bw == c.w(pl->o_wft)) a.Bw_lo = c.w(pl->o_wft_lo);
+    else if (use_tc) {
+      FoldArgs f{};
+      f.W = a.Bw; f.s_n = a.K; f.s_k = 1; f.Wf = c.w(pl->o_wf); f.N = a.N; f.K = a.K; f.SL = a.K;
+      fold(c, f, "split_w");
+      a.Bw = c.w(pl->o_wf); a.Bw_lo = c.w(pl->o_wf_lo);
+    }
+  }
   {
     const double mn = (double)a.M * a.N, io_mn = (MODE == EPI_STORE ? 1 + (a.resid ? 1 : 0) : MODE == EPI_GELU_SQ ? 2
                                                   : MODE == EPI_DG ? 2 : 3);
     c.acct(4.0 * ((double)a.M * a.K + (double)a.N * a.K + mn * io_mn), 2.0 * mn * a.K);
   }
-  if (c.pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a)) {
-    c.check(launch_gemm_rows_tc<MODE>(a, c.pl->cfg.gemm_backend, c.st), what);
+  if (use_tc) {
+    c.check(launch_gemm_rows_tc<MODE>(a, pl->cfg.gemm_backend, c.st), what);
   } else {
     c.check(launch_gemm_rows_simt<MODE>(a, c.st), what);
   }
@@ -405,6 +424,10 @@ void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
 }
 void fold(Ctx &c, FoldArgs a, const char *what) {
   if (!c.ok()) return;
+  if (c.pl->cfg.gemm_backend == 1) {
+    if (a.Wf == c.w(c.pl->o_wf)) a.Wf_lo = c.w(c.pl->o_wf_lo);
+    if (a.WfT == c.w(c.pl->o_wft)) a.WfT_lo = c.w(c.pl->o_wft_lo);
+  }
   fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
   c.post(what);
 }
@@ -1052,16 +1075,24 @@ int mpmae_encoder_features(mpmae_plan *pl, const mpmae_io *io, float *out_nchw, 
 }
 
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out, int64_t M, int32_t N,
-                    int32_t K, void *cuda_stream) {
+                    int32_t K, float *scratch, void *cuda_stream) {
   if (!a || !b || !out || M < 0 || N <= 0 || K <= 0 || K % 8 != 0) return fail(MPMAE_ERR_INVALID, "gemm args");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   GemmArgs g{};
   g.A = a; g.Bw = b; g.bias = bias; g.out = out; g.M = M; g.N = N; g.K = K; g.group_rows = 0x7fffffff;
   cudaError_t e;
   if (backend != 0) {
     if (!tc_gemm_supported(EPI_STORE, g)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
-    e = launch_gemm_rows_tc<EPI_STORE>(g, backend, static_cast<cudaStream_t>(cuda_stream));
+    if (backend == 1) {  // 3xTF32: split the weight into TF32-exact high part + remainder in the caller's scratch
+      if (!scratch) return fail(MPMAE_ERR_INVALID, "backend 1 needs scratch of 2*N*K floats");
+      FoldArgs f{};
+      f.W = b; f.s_n = K; f.s_k = 1; f.Wf = scratch; f.Wf_lo = scratch + (int64_t)N * K; f.N = N; f.K = K; f.SL = K;
+      fold_kernel<<<cdiv(N, 8), 256, 0, st>>>(f);
+      g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
+    }
+    e = launch_gemm_rows_tc<EPI_STORE>(g, backend, st);
   } else {
-    e = launch_gemm_rows_simt<EPI_STORE>(g, static_cast<cudaStream_t>(cuda_stream));
+    e = launch_gemm_rows_simt<EPI_STORE>(g, st);
   }
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "gemm: %s", cudaGetErrorString(e));
   return MPMAE_OK;
