@@ -138,6 +138,11 @@ int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
                     int64_t M, int32_t N, int32_t K, float *scratch, void *cuda_stream);
 
+/* stand-alone weight-gradient product (unit tests): dw[N,K] += x[R,N]^T . y[R,K].
+ * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 */
+int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
+                     void *cuda_stream);
+
 /* Fused AdamW over flat buffers (torch.optim.AdamW semantics; the reference builds its optimizer at
  * main_pretrain.py:312-320).  decay_mask: one byte per element (null = decay everything);
  * grad_scale_inv multiplies the gradient first (GradScaler unscale, helpers.py:485-497); step >= 1. */

@@ -71,6 +71,7 @@ def _load():
         "mpmae_backward": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_encoder_features": (C.c_int, [P, C.POINTER(IO), P, P]),
         "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P, P]),
+        "mpmae_gemm_wgrad": (C.c_int, [I32, P, P, P, I64, I32, I32, P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
     }
     for name, (res, args) in sig.items():
@@ -84,7 +85,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_backward", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_adamw_step"]
+           "mpmae_forward_encoder", "mpmae_backward", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_wgrad", "mpmae_adamw_step"]
 
 
 def check(rc: int, what: str = "") -> None:

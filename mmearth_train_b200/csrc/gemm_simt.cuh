@@ -210,6 +210,7 @@ struct WgradArgs {
   int64_t R;
   int N, K;
   int rows_per_split;
+  int exact;        // tensor-core path: 3xTF32 (the result feeds back into the data path)
 };
 
 __device__ __forceinline__ float4 load4_guard(const float *base, int64_t row, int ld, int col, int ncols, bool vec_ok) {

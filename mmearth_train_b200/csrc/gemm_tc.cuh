@@ -485,6 +485,214 @@ inline int pick_bn(int N) {
   return 256;
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// dW[n, k] += rs[n] * sum_r X[r, n] * Y[r, k]: the contraction runs over ROWS, so both operands are "MN-major" for
+// the tensor core (the feature dimension is contiguous in memory).  TMA boxes of [32 rows x 32 floats] (128-byte
+// swizzle) land as the canonical MN-major atoms ([8 rows][128 B], 1024 B each); one tcgen05.mma (K = 8 rows)
+// consumes one atom per 32-feature block, blocks LBO = 4096 B apart.  Work item = (m tile, n tile, row split);
+// partial tiles are merged with fp32 atomics (the reference merges with atomics too,
+// MinkowskiEngine/src/convolution_kernel.cu:198-290).  Single-pass TF32.
+struct TnParams {
+  const float *rs;   // [Nw] scale of dW rows or null
+  float *dW;         // [Nw, Kw]
+  int64_t R;
+  int Nw, Kw;
+  int swap;          // 0: MMA M side = X features (n), N side = Y features (k);  1: M side = Y (k), N side = X (n)
+  int Msz, Nsz;      // feature counts on the M / N side
+  int bn;            // N tile, multiple of 32, <= 256
+  int num_m, num_n, splits, chunks_per_split;   // chunk = 32 rows
+  int stages;
+  uint32_t tmem_cols;
+};
+
+// MN-major TF32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte atomicity
+// (UMMA LayoutType SWIZZLE_128B_BASE32B = 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of [4 rows][128 B].
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | ((4096u >> 4) << 16);   // LBO: next 32-feature block
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);             // SBO: next 4-row atom ; v1 ; SWIZZLE_128B_BASE32B
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+constexpr int kTnThreads = 192;
+
+// SPLIT = 3xTF32: both operand tiles are split in shared memory (hi in place, remainder in a second buffer) by four
+// splitter warps; D += Mhi.Nhi + Mlo.Nhi + Mhi.Nlo.  Used where the product feeds back into the data path (the GRN
+// statistic gradient is derived from dW2f by the chain rule of the weight fold).
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kTnThreads + 128 : kTnThreads, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int bn = p.bn, nstage = p.stages;
+  constexpr uint32_t m_bytes = BM * 32 * 4;                 // 4 blocks x [32 rows][128 B]
+  const uint32_t n_bytes = (uint32_t)bn * 32 * 4;           // bn/32 blocks
+  const uint32_t m_span = SPLIT ? 2 * m_bytes : m_bytes;
+  const uint32_t stage_bytes = m_span + (SPLIT ? 2 : 1) * n_bytes;   // [M | Mlo | N | Nlo]
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)nstage * stage_bytes);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *split_bar = empty_bar + STAGES;
+  uint64_t *tfull_bar = split_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_m)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_n)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int total = p.num_m * p.num_n * p.splits;
+  const int total_chunks = (int)((p.R + 31) / 32);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int sp = item / (p.num_m * p.num_n), t = item - sp * (p.num_m * p.num_n);
+        const int m_blk = t / p.num_n, n_blk = t - m_blk * p.num_n;
+        const int c_begin = sp * p.chunks_per_split;
+        const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *sm = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], m_bytes + n_bytes);
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sm + j * 4096, &map_m, &full_bar[stage], m_blk * BM + j * 32, ch * 32);
+          for (int j = 0; j < bn / 32; ++j)
+            tma_load_2d(sm + m_span + j * 4096, &map_n, &full_bar[stage], n_blk * bn + j * 32, ch * 32);
+          if (++stage == nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(bn) | (1u << 15) | (1u << 16);   // A and B MN-major
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int sp = item / (p.num_m * p.num_n);
+        const int c_begin = sp * p.chunks_per_split;
+        const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          mbar_wait(&full_bar[stage], phase);
+          if (SPLIT) mbar_wait(&split_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sm = smem_u32(smem + (size_t)stage * stage_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 8 rows per instruction = one 1024-byte atom per feature block
+            umma_tf32(tmem_d, make_smem_desc_mn(sm + k * 1024), make_smem_desc_mn(sm + m_span + k * 1024), idesc,
+                      (ch > c_begin || k > 0) ? 1u : 0u);
+          if (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_d, make_smem_desc_mn(sm + m_bytes + k * 1024), make_smem_desc_mn(sm + m_span + k * 1024), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_d, make_smem_desc_mn(sm + k * 1024), make_smem_desc_mn(sm + m_span + n_bytes + k * 1024), idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ch == c_end - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == nstage) { stage = 0; phase ^= 1; }
+        }
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int t = item % (p.num_m * p.num_n);
+      const int m_blk = t / p.num_n, n_blk = t - m_blk * p.num_n;
+      const int mi = m_blk * BM + q * 32 + lane;          // index on the M side
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (mi < p.Msz) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ni = n_blk * bn + c0 + j;
+            if (ni < p.Nsz) {
+              const int n = p.swap ? ni : mi, k = p.swap ? mi : ni;
+              const float sc = p.rs ? __ldg(p.rs + n) : 1.f;
+              atomicAdd(&p.dW[(int64_t)n * p.Kw + k], sc * v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+    }
+  } else if (SPLIT) {
+    const int stid = threadIdx.x - kTnThreads;   // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    auto split_region = [&](float4 *src, float4 *lo, int n4) {
+      for (int i = stid; i < n4; i += 128) {
+        const float4 x = src[i];
+        float4 hi, l;
+        hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - hi.w;
+        src[i] = hi;
+        lo[i] = l;
+      }
+    };
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      const int sp = item / (p.num_m * p.num_n);
+      const int c_begin = sp * p.chunks_per_split;
+      const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t *sm = smem + (size_t)stage * stage_bytes;
+        split_region(reinterpret_cast<float4 *>(sm), reinterpret_cast<float4 *>(sm + m_bytes), m_bytes / 16);
+        split_region(reinterpret_cast<float4 *>(sm + m_span), reinterpret_cast<float4 *>(sm + m_span + n_bytes), n_bytes / 16);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[stage]);
+        if (++stage == nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// [rows, cols] fp32 row-major, box = [32 rows, 32 floats], 128-byte swizzle with 32-byte atoms
+inline bool make_map_box32(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace tc
 
 inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
@@ -539,6 +747,87 @@ template <int MODE>
 inline cudaError_t launch_gemm_rows_tc(const GemmArgs &a, int backend, cudaStream_t st) {
   if (backend == 1 && a.Bw_lo) return launch_gemm_rows_tc_impl<MODE, true>(a, st);
   return launch_gemm_rows_tc_impl<MODE, false>(a, st);
+}
+
+
+inline bool tc_wgrad_supported(const WgradArgs &a) {
+  if (a.R < 256 || a.N < 8 || a.K < 8 || a.N % 4 != 0 || a.K % 4 != 0) return false;
+  if (((uintptr_t)a.X | (uintptr_t)a.Y) & 15) return false;
+  return tc::encode_fn() != nullptr;
+}
+
+// dW += rs * X^T . Y on the tensor cores (db is NOT produced here)
+template <bool SPLIT>
+inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st) {
+  using namespace tc;
+  TnParams p{};
+  p.rs = a.rs; p.dW = a.dW; p.R = a.R; p.Nw = a.N; p.Kw = a.K;
+  auto cost = [](int msz, int nsz) {  // operand re-reads: M-side operand once per n tile, N-side once per m tile
+    const int nm = cdiv(msz, BM), nn = cdiv(nsz, 256);
+    return (double)msz * nn + (double)nsz * nm;
+  };
+  p.swap = cost(a.K, a.N) < cost(a.N, a.K) ? 1 : 0;
+  p.Msz = p.swap ? a.K : a.N;
+  p.Nsz = p.swap ? a.N : a.K;
+  int bn;
+  if (p.Nsz <= 256) bn = ((p.Nsz + 31) / 32) * 32;
+  else {
+    bn = 256;
+    for (int c = 256; c >= 128; c -= 32)
+      if (p.Nsz % c == 0) { bn = c; break; }
+  }
+  p.bn = bn;
+  p.num_m = cdiv(p.Msz, BM);
+  p.num_n = cdiv(p.Nsz, bn);
+  const int total_chunks = (int)cdiv64(a.R, 32);
+  const int tiles = p.num_m * p.num_n;
+  int splits = cdiv(148 * 2, tiles);
+  const int max_splits = cdiv(total_chunks, 8);   // >= 256 rows per item
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.chunks_per_split = cdiv(total_chunks, splits);
+  p.splits = cdiv(total_chunks, p.chunks_per_split);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(ACC_STAGES * bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  const float *msrc = p.swap ? a.Y : a.X, *nsrc = p.swap ? a.X : a.Y;
+  static std::map<std::tuple<const void *, int64_t, int64_t>, CUtensorMap> cache;
+  static std::mutex mu;
+  auto get = [&](CUtensorMap *out, const float *ptr, int64_t rows, int64_t cols_) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((const void *)ptr, rows, cols_);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      CUtensorMap m;
+      if (!make_map_box32(&m, ptr, rows, cols_)) return false;
+      it = cache.emplace(key, m).first;
+    }
+    *out = it->second;
+    return true;
+  };
+  CUtensorMap mm, mn;
+  if (!get(&mm, msrc, a.R, p.Msz) || !get(&mn, nsrc, a.R, p.Nsz)) return cudaErrorInvalidValue;
+  const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * 32 * 4 + (size_t)bn * 32 * 4);
+  int stages = (int)((224 * 1024 - 2048) / stage_bytes);
+  if (stages > STAGES) stages = STAGES;
+  if (stages < 2) return cudaErrorInvalidConfiguration;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = tiles * p.splits;
+  if (grid > 148) grid = 148;
+  gemm_tn_tc_kernel<SPLIT><<<grid, SPLIT ? kTnThreads + 128 : kTnThreads, smem, st>>>(mm, mn, p);
+  return cudaGetLastError();
+}
+
+// exact = 3xTF32 (fp32-faithful); otherwise single-pass TF32
+inline cudaError_t launch_gemm_wgrad_tc(const WgradArgs &a, bool exact, cudaStream_t st) {
+  return exact ? launch_gemm_wgrad_tc_impl<true>(a, st) : launch_gemm_wgrad_tc_impl<false>(a, st);
 }
 
 }  // namespace mpmae

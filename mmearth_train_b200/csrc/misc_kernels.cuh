@@ -382,7 +382,8 @@ __global__ void densify_kernel(const float *__restrict__ x3, const int *__restri
 }
 
 // column sums of a [R, C] matrix into out[C] (+=): bias gradients that have no GEMM to ride on
-__global__ void colsum_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t R, int C) {
+__global__ void colsum_kernel(const float *__restrict__ x, const float *__restrict__ rs, float *__restrict__ out, int64_t R,
+                              int C) {
   // blockDim = (32, 8): x over channels, y over rows
   const int c = blockIdx.x * 32 + threadIdx.x;
   __shared__ float red[8][33];
@@ -395,7 +396,7 @@ __global__ void colsum_kernel(const float *__restrict__ x, float *__restrict__ o
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(&out[c], t);
+    atomicAdd(&out[c], rs ? rs[c] * t : t);
   }
 }
 

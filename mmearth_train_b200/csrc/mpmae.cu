@@ -420,7 +420,18 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
 void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
   if (!c.ok()) return;
   c.acct(4.0 * ((double)a.R * a.N + (double)a.R * a.K + (double)a.N * a.K), 2.0 * (double)a.R * a.N * a.K);
-  c.check(launch_gemm_wgrad(a, c.st), what);
+  if (c.pl->cfg.gemm_backend != 0 && tc_wgrad_supported(a)) {
+    c.check(launch_gemm_wgrad_tc(a, a.exact != 0 && c.pl->cfg.gemm_backend == 1, c.st), what);
+    if (a.db && c.ok()) {   // bias gradient = column sums of X (the tensor-core kernel produces dW only)
+      c.acct(4.0 * (double)a.R * a.N, 0);
+      int gy = (int)(a.R / 256);
+      gy = gy < 1 ? 1 : (gy > 592 ? 592 : gy);
+      colsum_kernel<<<dim3(cdiv(a.N, 32), gy), dim3(32, 8), 0, c.st>>>(a.X, a.rs, a.db, a.R, a.N);
+      c.post("colsum");
+    }
+  } else {
+    c.check(launch_gemm_wgrad(a, c.st), what);
+  }
 }
 void fold(Ctx &c, FoldArgs a, const char *what) {
   if (!c.ok()) return;
@@ -535,6 +546,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
     c.zero(dsv, D4, "zero_ds");
     WgradArgs wg{};
     wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf; wg.db = dbf; wg.R = R; wg.N = C; wg.K = D4;
+    wg.exact = 1;   // ds (GRN statistic gradient) is derived from dW2f and feeds every row's gradient
     wgrad(c, wg, "dW2f");
     UnfoldArgs u{};
     u.W = c.p(bp.w2); u.s_n = D4; u.s_k = 1; u.scale_k = c.w(bw.scale); u.shift_k = c.p(bp.beta);
@@ -1095,6 +1107,23 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
     e = launch_gemm_rows_simt<EPI_STORE>(g, st);
   }
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "gemm: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
+                     void *cuda_stream) {
+  if (!x || !y || !dw || R <= 0 || N <= 0 || K <= 0) return fail(MPMAE_ERR_INVALID, "wgrad args");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  WgradArgs w{};
+  w.X = x; w.Y = y; w.dW = dw; w.R = R; w.N = N; w.K = K;
+  cudaError_t e;
+  if (backend != 0) {
+    if (!tc_wgrad_supported(w)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
+    e = launch_gemm_wgrad_tc(w, backend == 1, st);
+  } else {
+    e = launch_gemm_wgrad(w, st);
+  }
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "wgrad: %s", cudaGetErrorString(e));
   return MPMAE_OK;
 }
 

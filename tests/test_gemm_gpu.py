@@ -37,3 +37,39 @@ def test_gemm_rows(native_lib, shape, backend, tol):
     assert torch.isfinite(out).all()
     err = float((out.double() - ref).abs().max() / ref.abs().max())
     assert err < tol, (shape, backend, err)
+
+
+WG_SHAPES = [(2432, 40, 160), (2432, 160, 40), (608, 80, 320), (4096, 128, 128), (1000, 512, 320), (12544, 2048, 512),
+             (333, 96, 384), (5000, 2816, 512)]
+
+
+@pytest.mark.parametrize("backend,tol", [(0, 2e-6), (2, 2e-3), (1, 2e-5)])
+@pytest.mark.parametrize("shape", WG_SHAPES)
+def test_gemm_wgrad(native_lib, shape, backend, tol):
+    """dW[N, K] += X[R, N]^T . Y[R, K]: contraction over rows (MN-major tcgen05 operands), accumulating."""
+    nat = native_lib
+    R, N, K = shape
+    g = torch.Generator().manual_seed(R + N + K)
+    x = torch.randn(R, N, generator=g).cuda()
+    y = torch.randn(R, K, generator=g).cuda()
+    init = torch.randn(N, K, generator=g).cuda()
+    dw = init.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    nat.check(nat.lib.mpmae_gemm_wgrad(backend, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                       R, N, K, C.c_void_p(st)), "gemm_wgrad")
+    torch.cuda.synchronize()
+    ref = x.double().t() @ y.double()
+    err = float(((dw - init).double() - ref).norm() / ref.norm())
+    assert err < tol, (shape, backend, err)
+    if backend != 0:   # localisation: a single non-zero row must land exactly
+        x2 = torch.zeros_like(x)
+        x2[R // 3] = 1.0
+        dw2 = torch.zeros(N, K, device="cuda")
+        nat.check(nat.lib.mpmae_gemm_wgrad(backend, C.c_void_p(x2.data_ptr()), C.c_void_p(y.data_ptr()),
+                                           C.c_void_p(dw2.data_ptr()), R, N, K, C.c_void_p(st)), "gemm_wgrad")
+        torch.cuda.synchronize()
+        assert gu_rel(dw2, y[R // 3].repeat(N, 1)) < tol
+
+
+def gu_rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
