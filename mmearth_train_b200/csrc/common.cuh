@@ -44,6 +44,14 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// h = gelu(x) and d gelu / dx from one erf evaluation
+__device__ __forceinline__ void gelu_both_f(float x, float &h, float &dgelu) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  h = x * cdf;
+  dgelu = cdf + x * pdf;
+}
+
 // Geometry of the visible-patch row layout shared by all sparse kernels.
 //   rows of stage with patch side P:  row = (n*V + slot)*P*P + morton(py, px)
 //   slot_of[n*L + l] = slot of patch l (ascending patch index among visible ones) or -1

@@ -171,7 +171,7 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;
+constexpr int kEpiWarps = 12, kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsNoSplit = 64 + kEpiThreads, kThreadsSplit = kThreadsNoSplit + 128;
 
 // SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
@@ -197,6 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float *colacc = reinterpret_cast<float *>(tmem_ptr + 4);           // [kTcGroups][bn]
   constexpr int kTcGroups = 4;                                       // a 128-row tile spans <= 4 groups of >= 32 rows
   float *colacc2 = colacc + kTcGroups * bn;                          // [bn]
+  float *vec_bias_all = colacc2 + bn;                                // [num_n * bn] bias (zero padded)
+  float *vec_kg_all = vec_bias_all + p.num_n * bn;                   // [num_n * bn] kg of group 0 (EPI_DH_GELU)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs &g = p.g;
@@ -209,8 +211,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
-  if (MODE != EPI_STORE && warp >= 2 && warp < 2 + kEpiWarps) {
-    for (int i = threadIdx.x - 64; i < (kTcGroups + 1) * bn; i += kEpiThreads) colacc[i] = 0.f;
+  if (warp >= 2 && warp < 2 + kEpiWarps) {
+    if (MODE != EPI_STORE)
+      for (int i = threadIdx.x - 64; i < (kTcGroups + 1) * bn; i += kEpiThreads) colacc[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < p.num_n * bn; i += kEpiThreads) {
+      vec_bias_all[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
+      if (MODE == EPI_DH_GELU) vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -270,10 +277,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp < 2 + kEpiWarps) {
-    // ================================================================ epilogue: 8 warps, TMEM lane quarter = warp % 4,
-    // the two warps of a quarter take alternate 16-column chunks
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ================================================================ epilogue: kEpiWarps warps, TMEM lane quarter =
+    // warp % 4, the warps of a quarter take alternate 16-column chunks.  Per-column vectors (bias, kg) sit in shared
+    // memory; the per-element operand of the next chunk (residual / h / a) is prefetched into registers before the
+    // accumulator chunk is read, so its HBM latency overlaps the math of the current chunk.
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    constexpr int kParts = kEpiWarps / 4;
     const int et = threadIdx.x - 64;
+    const float *pre_src = (MODE == EPI_STORE) ? g.resid : (MODE == EPI_DG) ? g.aux : (MODE == EPI_DH_GELU) ? g.aux2 : nullptr;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -281,17 +292,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
       const bool row_ok = m < g.M;
       const int n_base = n_blk * bn;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
+      const float *vec_bias = vec_bias_all + n_base, *vec_kg = vec_kg_all + n_base;
       const int64_t g_first = ((int64_t)m_blk * BM) / g.group_rows;
       const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
       const int gw_lo = (int)(mw0 / g.group_rows - g_first);
       const int64_t mw_last = (mw0 + 31 < g.M ? mw0 + 31 : g.M - 1);
       const int gw_hi = mw_last >= mw0 ? (int)(mw_last / g.group_rows - g_first) : gw_lo;
       const int my_g = row_ok ? (int)(m / g.group_rows - g_first) : gw_lo;
+      auto prefetch = [&](int c0, float4 *dst) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n_base + c0 + 4 * j;
+          dst[j] = (pre_src && row_ok && c0 < bn && n < g.N) ? __ldg(reinterpret_cast<const float4 *>(pre_src + m * g.N + n))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 pre[4];
+      prefetch(part * 16, pre);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
 
-      for (int c0 = half * 16; c0 < bn; c0 += 32) {
+      for (int c0 = part * 16; c0 < bn; c0 += 16 * kParts) {
+        float4 nxt[4];
+        prefetch(c0 + 16 * kParts, nxt);
         float v[16];
         tmem_ld16(taddr + c0, v);
         float s1[16], s2[16];  // statistics contributions (dead code for EPI_STORE)
@@ -303,35 +327,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float4 st1 = o, st2 = o;
           if (col_ok) {
             const float4 acc = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+            const float4 pv = pre[j4 >> 2];
+            const float4 bv = *reinterpret_cast<const float4 *>(vec_bias + c0 + j4);
             if (MODE == EPI_STORE) {
-              o = acc;
-              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-              if (g.resid && row_ok) {
-                const float4 r = __ldg(reinterpret_cast<const float4 *>(g.resid + m * g.N + n));
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-              }
+              o = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
             } else if (MODE == EPI_GELU_SQ) {
-              o = acc;
-              if (g.bias) { const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              o = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
               o2 = make_float4(gelu_f(o.x), gelu_f(o.y), gelu_f(o.z), gelu_f(o.w));
               if (row_ok) st1 = make_float4(o2.x * o2.x, o2.y * o2.y, o2.z * o2.z, o2.w * o2.w);
             } else if (MODE == EPI_DG) {
               o = acc;
               if (row_ok) {
-                const float4 h = __ldg(reinterpret_cast<const float4 *>(g.aux + m * g.N + n));
-                st1 = make_float4(acc.x * h.x, acc.y * h.y, acc.z * h.z, acc.w * h.w);
+                st1 = make_float4(acc.x * pv.x, acc.y * pv.y, acc.z * pv.z, acc.w * pv.w);
                 st2 = acc;
               }
-            } else {  // EPI_DH_GELU
+            } else {  // EPI_DH_GELU: h = a * Phi(a) is recomputed from a (it shares the erf with gelu')
               if (row_ok) {
-                const float4 h = __ldg(reinterpret_cast<const float4 *>(g.aux + m * g.N + n));
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(g.aux2 + m * g.N + n));
-                float4 kgv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.kg) kgv = __ldg(reinterpret_cast<const float4 *>(g.kg + (g_first + my_g) * g.N + n));
-                o.x = (acc.x + kgv.x * h.x) * gelu_grad_f(a.x);
-                o.y = (acc.y + kgv.y * h.y) * gelu_grad_f(a.y);
-                o.z = (acc.z + kgv.z * h.z) * gelu_grad_f(a.z);
-                o.w = (acc.w + kgv.w * h.w) * gelu_grad_f(a.w);
+                const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j4);
+                float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
+                gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
+                o.x = (acc.x + kgv.x * hx) * dx_;
+                o.y = (acc.y + kgv.y * hy) * dy_;
+                o.z = (acc.z + kgv.z * hz) * dz_;
+                o.w = (acc.w + kgv.w * hw) * dw_;
                 st2 = o;
               }
             }
@@ -365,6 +383,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane < 16) atomicAdd(&colacc2[col], t);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[j] = nxt[j];
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
@@ -709,18 +729,24 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   using namespace tc;
   TcParams p{};
   p.g = a;
-  int bn = pick_bn(a.N);
-  if (SPLIT && bn > 160) {   // [A | Alo | Bhi | Blo] x 3 stages must fit in 227 KB
-    bn = 0;
-    for (int c = 160; c >= 64; c -= 16)
-      if (a.N % c == 0) { bn = c; break; }
-    if (!bn) bn = 128;
-  }
+  p.stages = SPLIT ? 3 : 4;
+  auto smem_for = [&](int bn) {
+    const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)bn * BK * 4);
+    const int num_n = cdiv(a.N, bn);
+    return 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)(5 * bn + 2 * num_n * bn) * 4;
+  };
+  // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget, else a ragged tail
+  int bn = 0;
+  const int cap = a.N <= 256 ? ((a.N + 15) / 16) * 16 : 256;
+  for (int c = cap; c >= 64 && !bn; c -= 16)
+    if ((a.N % c == 0 || c >= a.N) && smem_for(c) <= 226 * 1024) bn = c;
+  for (int c = cap; c >= 16 && !bn; c -= 16)
+    if (smem_for(c) <= 226 * 1024) bn = c;
+  if (!bn) return cudaErrorInvalidConfiguration;
   p.bn = bn;
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
   p.num_k = cdiv(a.K, BK);
-  p.stages = SPLIT ? 3 : 4;
   uint32_t cols = 32;
   while (cols < (uint32_t)(ACC_STAGES * p.bn)) cols <<= 1;
   p.tmem_cols = cols;
@@ -728,9 +754,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   if (!map_cache().get(&ma, a.A, a.M, a.K, BM) || !map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
   mbl = mb;
   if (SPLIT && !map_cache().get(&mbl, a.Bw_lo, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
-  const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)5 * p.bn * 4;
-  if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;
+  const size_t smem = smem_for(bn);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
