@@ -138,6 +138,20 @@ int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
                     int64_t M, int32_t N, int32_t K, float *scratch, void *cuda_stream);
 
+/* stand-alone fused-epilogue GEMM (unit tests / microbench of the epilogue modes the step uses):
+ *   mode 0  out = a.b^T + bias (+ resid)
+ *   mode 1  out = a.b^T + bias ; out2 = gelu(out) ; colsum[g, n] += out2^2           (pw1 + GELU + GRN statistic)
+ *   mode 2  out = a.b^T ; colsum[g, n] += out * aux ; colsum2[n] += out              (decoder dg)
+ *   mode 3  out = (a.b^T + kg[n] * gelu(aux2)) * gelu'(aux2) ; colsum2[n] += out    (GELU/GRN backward)
+ * group_rows = rows per statistics group (>= M: one group).  scratch: 2*N*K floats (backend 1). */
+typedef struct mpmae_gemm_desc {
+  const float *a, *b, *bias, *resid, *aux, *aux2, *kg;
+  float *out, *out2, *colsum, *colsum2, *scratch;
+  int64_t M;
+  int32_t N, K, group_rows;
+} mpmae_gemm_desc;
+int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void *cuda_stream);
+
 /* stand-alone weight-gradient product (unit tests): dw[N,K] += x[R,N]^T . y[R,K].
  * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 */
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,

@@ -130,6 +130,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 256-bit global store (sm_100+): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void st_global_v8(float *ptr, const float4 &a, const float4 &b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+               "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void ld_global_v8(const float *ptr, float4 &a, float4 &b) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(ptr));
+}
+
 // Transposed warp reduction: every lane holds v[0..32); afterwards lane l returns sum over lanes of v[l].
 // 31 shuffles instead of 32 x 5.
 __device__ __forceinline__ float warp_colsum32(float *v, int lane) {
@@ -151,6 +164,8 @@ struct TcParams {
   int bn;        // N tile (multiple of 16, <= 256)
   int num_m, num_n, num_k;
   int stages;    // shared-memory ring depth (<= STAGES)
+  int vec8;      // N % 8 == 0 and 32-byte aligned outputs: 256-bit stores
+  int vec8_in;   // same for the prefetched per-element operand
   uint32_t tmem_cols;
 };
 
@@ -300,11 +315,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int gw_hi = mw_last >= mw0 ? (int)(mw_last / g.group_rows - g_first) : gw_lo;
       const int my_g = row_ok ? (int)(m / g.group_rows - g_first) : gw_lo;
       auto prefetch = [&](int c0, float4 *dst) {
+        if (p.vec8_in) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n_base + c0 + 4 * j;
-          dst[j] = (pre_src && row_ok && c0 < bn && n < g.N) ? __ldg(reinterpret_cast<const float4 *>(pre_src + m * g.N + n))
-                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 4; j += 2) {
+            const int n = n_base + c0 + 4 * j;
+            if (pre_src && row_ok && c0 < bn && n < g.N) ld_global_v8(pre_src + m * g.N + n, dst[j], dst[j + 1]);
+            else dst[j] = dst[j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n_base + c0 + 4 * j;
+            dst[j] = (pre_src && row_ok && c0 < bn && n < g.N) ? __ldg(reinterpret_cast<const float4 *>(pre_src + m * g.N + n))
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       };
       float4 pre[4];
@@ -319,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[16];
         tmem_ld16(taddr + c0, v);
         float s1[16], s2[16];  // statistics contributions (dead code for EPI_STORE)
+        float4 ov[4], ov2[4];
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
           const int n = n_base + c0 + j4;
@@ -353,14 +378,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 st2 = o;
               }
             }
-            if (row_ok) {
-              *reinterpret_cast<float4 *>(g.out + m * g.N + n) = o;
-              if (MODE == EPI_GELU_SQ) *reinterpret_cast<float4 *>(g.out2 + m * g.N + n) = o2;
-            }
           }
+          ov[j4 >> 2] = o; ov2[j4 >> 2] = o2;
           if (MODE != EPI_STORE) {
             s1[j4] = st1.x; s1[j4 + 1] = st1.y; s1[j4 + 2] = st1.z; s1[j4 + 3] = st1.w;
             s2[j4] = st2.x; s2[j4 + 1] = st2.y; s2[j4 + 2] = st2.z; s2[j4 + 3] = st2.w;
+          }
+        }
+        if (row_ok) {
+          // rows are written in 32-byte (8-float) pieces when N allows: full sectors, half as many requests
+          const int n0 = n_base + c0;
+          if (p.vec8) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              if (n0 + 8 * h8 < g.N) {
+                st_global_v8(g.out + m * g.N + n0 + 8 * h8, ov[2 * h8], ov[2 * h8 + 1]);
+                if (MODE == EPI_GELU_SQ) st_global_v8(g.out2 + m * g.N + n0 + 8 * h8, ov2[2 * h8], ov2[2 * h8 + 1]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n0 + 4 * j < g.N) {
+                *reinterpret_cast<float4 *>(g.out + m * g.N + n0 + 4 * j) = ov[j];
+                if (MODE == EPI_GELU_SQ) *reinterpret_cast<float4 *>(g.out2 + m * g.N + n0 + 4 * j) = ov2[j];
+              }
+            }
           }
         }
         if (MODE != EPI_STORE) {
@@ -747,6 +790,8 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
   p.num_k = cdiv(a.K, BK);
+  p.vec8 = (a.N % 8 == 0) && (((uintptr_t)a.out | (uintptr_t)a.out2) & 31) == 0;
+  p.vec8_in = (a.N % 8 == 0) && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2) & 31) == 0;
   uint32_t cols = 32;
   while (cols < (uint32_t)(ACC_STAGES * p.bn)) cols <<= 1;
   p.tmem_cols = cols;

@@ -1110,6 +1110,35 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
   return MPMAE_OK;
 }
 
+int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void *cuda_stream) {
+  if (!d || !d->a || !d->b || !d->out || d->M <= 0 || d->N <= 0 || d->K <= 0 || d->K % 8 != 0 || mode < 0 || mode > 3)
+    return fail(MPMAE_ERR_INVALID, "gemm_epi args");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  GemmArgs g{};
+  g.A = d->a; g.Bw = d->b; g.bias = d->bias; g.resid = d->resid; g.out = d->out; g.out2 = d->out2; g.aux = d->aux;
+  g.aux2 = d->aux2; g.kg = d->kg; g.colsum = d->colsum; g.colsum2 = d->colsum2; g.M = d->M; g.N = d->N; g.K = d->K;
+  g.group_rows = d->group_rows > 0 ? d->group_rows : 0x7fffffff;
+  const bool tc_ok = backend != 0 && tc_gemm_supported(mode, g);
+  if (backend != 0 && !tc_ok) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
+  if (backend == 1) {
+    if (!d->scratch) return fail(MPMAE_ERR_INVALID, "backend 1 needs scratch of 2*N*K floats");
+    FoldArgs f{};
+    f.W = d->b; f.s_n = d->K; f.s_k = 1; f.Wf = d->scratch; f.Wf_lo = d->scratch + (int64_t)d->N * d->K; f.N = d->N;
+    f.K = d->K; f.SL = d->K;
+    fold_kernel<<<cdiv(d->N, 8), 256, 0, st>>>(f);
+    g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
+  }
+  cudaError_t e = cudaSuccess;
+  switch (mode) {
+    case 0: e = tc_ok ? launch_gemm_rows_tc<EPI_STORE>(g, backend, st) : launch_gemm_rows_simt<EPI_STORE>(g, st); break;
+    case 1: e = tc_ok ? launch_gemm_rows_tc<EPI_GELU_SQ>(g, backend, st) : launch_gemm_rows_simt<EPI_GELU_SQ>(g, st); break;
+    case 2: e = tc_ok ? launch_gemm_rows_tc<EPI_DG>(g, backend, st) : launch_gemm_rows_simt<EPI_DG>(g, st); break;
+    default: e = tc_ok ? launch_gemm_rows_tc<EPI_DH_GELU>(g, backend, st) : launch_gemm_rows_simt<EPI_DH_GELU>(g, st); break;
+  }
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "gemm_epi: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
                      void *cuda_stream) {
   if (!x || !y || !dw || R <= 0 || N <= 0 || K <= 0) return fail(MPMAE_ERR_INVALID, "wgrad args");
