@@ -49,8 +49,12 @@ struct BlockP { int64_t dw_k, dw_b, ln_w, ln_b, w1, b1, gamma, beta, w2, b2; };
 struct DsP { int64_t ln_w, ln_b, k, b; };
 struct Tap { int64_t off_bytes, rows, cols; };
 
+// A weight matrix as the GEMMs consume it, produced once per step by fold_slot(): Wf [N, K] and WfT [K, N] (LayerNorm /
+// GRN affines folded in), each as a TF32-exact high part + remainder when the backend is 3xTF32, the folded bias, and
+// (zeroed at the start of backward) the gradient of the folded weight / bias.
+struct WSlot { int64_t wf, wf_lo, wft, wft_lo, bf, dwf, dbf; int N, K; };
 // per-block saved activations / statistics (float offsets into the workspace)
-struct BlockW { int64_t vhat, rstd, a, h, g, y, gsq, nx, scale, denom; };
+struct BlockW { int64_t vhat, rstd, a, h, g, y, gsq, nx, scale, denom, dsv; WSlot s1, s2; };
 
 }  // namespace
 
@@ -78,6 +82,8 @@ struct mpmae_plan {
   std::vector<BlockW> dw;
   int64_t o_z, o_xd, o_pooled, o_pool_rstd, o_dpix, o_dimg, o_acc, o_cs_pix, o_cs_img, o_dpooled;
   int64_t o_zero_begin, o_zero_end;  // statistics region cleared at the start of forward
+  int64_t o_bzero_begin, o_bzero_end;  // folded-weight gradients + GRN statistic gradients, cleared at the start of backward
+  WSlot ds_slot[3], proj_slot, pix_slot;
   int64_t o_wf, o_wft, o_wf_lo, o_wft_lo, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
   int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
   int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
@@ -225,6 +231,21 @@ void note_wf(mpmae_plan *pl, int64_t n, int64_t k) {
   if (k > pl->max_n) pl->max_n = k;
 }
 
+WSlot alloc_slot(mpmae_plan *pl, int N, int K) {
+  WSlot s{};
+  s.N = N; s.K = K;
+  s.wf = ws_alloc(pl, nullptr, N, K);
+  s.wf_lo = ws_alloc(pl, nullptr, N, K);
+  s.wft = ws_alloc(pl, nullptr, K, N);
+  s.wft_lo = ws_alloc(pl, nullptr, K, N);
+  s.bf = ws_alloc(pl, nullptr, 1, N);
+  return s;
+}
+void alloc_slot_grads(mpmae_plan *pl, WSlot &s) {
+  s.dwf = ws_alloc(pl, nullptr, s.N, s.K);
+  s.dbf = ws_alloc(pl, nullptr, 1, s.N);
+}
+
 void build_workspace(mpmae_plan *pl) {
   const mpmae_cfg &c = pl->cfg;
   const int *dm = c.dims;
@@ -249,6 +270,7 @@ void build_workspace(mpmae_plan *pl) {
       pl->o_ds_rstd[i - 1] = ws_alloc(pl, nm, pl->R[i - 1], 1);
       snprintf(nm, sizeof nm, "down%d.out", i);
       pl->o_ds_out[i - 1] = ws_alloc(pl, nm, R, C);
+      pl->ds_slot[i - 1] = alloc_slot(pl, C, 4 * dm[i - 1]);
       note_wf(pl, C, 4 * dm[i - 1]);
     }
     note_wf(pl, 4 * C, C);
@@ -264,11 +286,15 @@ void build_workspace(mpmae_plan *pl) {
       w.nx = ws_alloc(pl, N("nx"), 1, 4 * C);
       w.scale = ws_alloc(pl, N("scale"), 1, 4 * C);
       w.denom = ws_alloc(pl, N("denom"), 1, 1);
+      w.s1 = alloc_slot(pl, 4 * C, C);
+      w.s2 = alloc_slot(pl, C, 4 * C);
       pl->bw[i].push_back(w);
     }
   }
   pl->o_z = ws_alloc(pl, "proj.z", B * V, D);
   pl->o_xd = ws_alloc(pl, "decoder.in", pl->cells, D);
+  pl->proj_slot = alloc_slot(pl, D, dm[3]);
+  pl->pix_slot = alloc_slot(pl, pl->npix > 0 ? pl->npix : 8, D);
   note_wf(pl, D, dm[3]);
   note_wf(pl, 4 * D, D);
   if (pl->cells * D > pl->max_rc) pl->max_rc = pl->cells * D;
@@ -285,6 +311,8 @@ void build_workspace(mpmae_plan *pl) {
     w.nx = ws_alloc(pl, N("nx"), B, 4 * D);
     w.scale = ws_alloc(pl, N("scale"), B, 4 * D);
     w.denom = ws_alloc(pl, N("denom"), B, 1);
+    w.s1 = alloc_slot(pl, 4 * D, D);
+    w.s2 = alloc_slot(pl, D, 4 * D);
     pl->dw.push_back(w);
   }
   pl->o_pooled = ws_alloc(pl, "pooled", B, D);
@@ -309,6 +337,20 @@ void build_workspace(mpmae_plan *pl) {
     pl->dw[k].gsq = ws_alloc(pl, nm, B, 4 * D);
   }
   pl->o_zero_end = pl->ws_floats;
+  // cleared by one memset at the start of backward
+  pl->o_bzero_begin = pl->ws_floats;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < c.depths[i]; ++j) {
+      alloc_slot_grads(pl, pl->bw[i][j].s1);
+      alloc_slot_grads(pl, pl->bw[i][j].s2);
+      pl->bw[i][j].dsv = ws_alloc(pl, nullptr, 1, 4 * dm[i]);
+    }
+  for (int k = 0; k < c.dec_depth; ++k) {
+    alloc_slot_grads(pl, pl->dw[k].s1);
+    pl->dw[k].dsv = ws_alloc(pl, nullptr, B, 4 * D);
+  }
+  for (int i = 0; i < 3; ++i) alloc_slot_grads(pl, pl->ds_slot[i]);
+  pl->o_bzero_end = pl->ws_floats;
   // weight-fold scratch + backward temporaries
   pl->o_wf = ws_alloc(pl, nullptr, 1, pl->max_wf);
   pl->o_wft = ws_alloc(pl, nullptr, 1, pl->max_wf);
@@ -397,9 +439,7 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
   if (pl->cfg.gemm_backend == 1) {
     // 3xTF32: the weight operand is consumed as a (hi, lo) pair; folded weights were written that way by fold(),
     // raw parameter matrices are split here into the scratch buffers
-    if (a.Bw == c.w(pl->o_wf)) a.Bw_lo = c.w(pl->o_wf_lo);
-    else if (a.Bw == c.w(pl->o_wft)) a.Bw_lo = c.w(pl->o_wft_lo);
-    else if (use_tc) {
+    if (!a.Bw_lo && use_tc) {
       FoldArgs f{};
       f.W = a.Bw; f.s_n = a.K; f.s_k = 1; f.Wf = c.w(pl->o_wf); f.N = a.N; f.K = a.K; f.SL = a.K;
       fold(c, f, "split_w");
@@ -442,6 +482,24 @@ void fold(Ctx &c, FoldArgs a, const char *what) {
   fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
   c.post(what);
 }
+// fold a weight into its slot: both orientations (+ hi/lo split for 3xTF32) and the folded bias in one launch
+void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what) {
+  if (!c.ok()) return;
+  const bool split = c.pl->cfg.gemm_backend == 1;
+  a.Wf = c.w(s.wf); a.WfT = c.w(s.wft);
+  a.Wf_lo = split ? c.w(s.wf_lo) : nullptr;
+  a.WfT_lo = split ? c.w(s.wft_lo) : nullptr;
+  if (a.bias || a.shift_k) a.bf = c.w(s.bf);
+  a.N = s.N; a.K = s.K;
+  fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
+  c.post(what);
+}
+// point a GEMM at a slot: out = A . Wf^T (transposed = false) or A . Wf (transposed = true)
+void use_slot(Ctx &c, GemmArgs &g, const WSlot &s, bool transposed) {
+  const bool split = c.pl->cfg.gemm_backend == 1;
+  g.Bw = c.w(transposed ? s.wft : s.wf);
+  g.Bw_lo = split ? c.w(transposed ? s.wft_lo : s.wf_lo) : nullptr;
+}
 void unfold(Ctx &c, UnfoldArgs a, const char *what) {
   if (!c.ok()) return;
   unfold_kernel<<<a.K, 256, 0, c.st>>>(a);
@@ -470,13 +528,13 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
 
   FoldArgs f{};
   f.W = c.p(bp.w1); f.s_n = C; f.s_k = 1; f.scale_k = c.p(bp.ln_w); f.shift_k = c.p(bp.ln_b);
-  f.bias = c.p(bp.b1); f.Wf = c.w(pl->o_wf); f.bf = c.w(pl->o_bf); f.N = D4; f.K = C; f.SL = C;
-  fold(c, f, "fold_pw1");
+  f.bias = c.p(bp.b1); f.SL = C;
+  fold_slot(c, f, bw.s1, "fold_pw1");
 
   const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
   const int groups = dense ? pl->geo.B : 1;
   GemmArgs g1{};
-  g1.A = c.w(bw.vhat); g1.Bw = c.w(pl->o_wf); g1.bias = c.w(pl->o_bf);
+  g1.A = c.w(bw.vhat); use_slot(c, g1, bw.s1, false); g1.bias = c.w(bw.s1.bf);
   g1.out = c.w(bw.a); g1.out2 = c.w(bw.h); g1.colsum = c.w(bw.gsq);
   g1.M = R; g1.N = D4; g1.K = C; g1.group_rows = group_rows;
   gemm<EPI_GELU_SQ>(c, g1, "pw1");
@@ -488,6 +546,8 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   }
   GemmArgs g2{};
   g2.out = c.w(bw.y); g2.resid = x; g2.M = R; g2.N = C; g2.K = D4; g2.group_rows = group_rows;
+  FoldArgs f2{};
+  f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.SL = D4;
   if (dense) {
     if (c.ok()) {
       c.acct(4.0 * 2.0 * R * D4, 0);
@@ -495,15 +555,15 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
                                                                group_rows);
       c.post("grn_apply");
     }
-    g2.A = c.w(bw.g); g2.Bw = c.p(bp.w2); g2.bias = c.p(bp.b2);
+    fold_slot(c, f2, bw.s2, "split_pw2");   // per-sample GRN cannot be folded: plain (split) copy of W2
+    g2.A = c.w(bw.g); g2.bias = c.p(bp.b2);
   } else {
     // GRN is affine in h per channel: fold s = 1 + gamma*Nx into W2's columns and beta into the bias
-    FoldArgs f2{};
-    f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.scale_k = c.w(bw.scale); f2.shift_k = c.p(bp.beta);
-    f2.bias = c.p(bp.b2); f2.Wf = c.w(pl->o_wf); f2.bf = c.w(pl->o_bf); f2.N = C; f2.K = D4; f2.SL = D4;
-    fold(c, f2, "fold_pw2");
-    g2.A = c.w(bw.h); g2.Bw = c.w(pl->o_wf); g2.bias = c.w(pl->o_bf);
+    f2.scale_k = c.w(bw.scale); f2.shift_k = c.p(bp.beta); f2.bias = c.p(bp.b2);
+    fold_slot(c, f2, bw.s2, "fold_pw2");
+    g2.A = c.w(bw.h); g2.bias = c.w(bw.s2.bf);
   }
+  use_slot(c, g2, bw.s2, false);
   gemm<EPI_STORE>(c, g2, "pw2");
 }
 
@@ -515,16 +575,13 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
   const int groups = dense ? pl->geo.B : 1;
   float *da = c.w(pl->o_gda);
-  float *dsv = c.w(pl->o_dsv), *kg = c.w(pl->o_kg), *dwf = c.w(pl->o_dwf), *dbf = c.w(pl->o_dbf);
+  float *dsv = c.w(bw.dsv), *kg = c.w(pl->o_kg);
+  float *dwf1 = c.w(bw.s1.dwf), *dbf1 = c.w(bw.s1.dbf);
 
   if (dense) {
     // dg = dy . W2 ; A[g,d] = sum dg*h ; dbeta = sum dg
-    FoldArgs ft{};
-    ft.W = c.p(bp.w2); ft.s_n = D4; ft.s_k = 1; ft.WfT = c.w(pl->o_wft); ft.N = C; ft.K = D4; ft.SL = D4;
-    fold(c, ft, "w2T");
-    c.zero(dsv, (int64_t)groups * D4, "zero_ds");
     GemmArgs gd{};
-    gd.A = dy; gd.Bw = c.w(pl->o_wft); gd.out = da; gd.aux = c.w(bw.h); gd.colsum = dsv; gd.colsum2 = c.g(bp.beta);
+    gd.A = dy; use_slot(c, gd, bw.s2, true); gd.out = da; gd.aux = c.w(bw.h); gd.colsum = dsv; gd.colsum2 = c.g(bp.beta);
     gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
     gemm<EPI_DG>(c, gd, "dg");
     // dW2 += dy^T . g ; db2 += sum dy
@@ -538,54 +595,47 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
       grn_gelu_bwd_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(da, c.w(bw.h), c.w(bw.a), c.w(bw.scale), kg, da, R, D4,
                                                                   group_rows);
       c.post("grn_gelu_bwd");
+      int gy = (int)(R / 256);
+      gy = gy < 1 ? 1 : (gy > 592 ? 592 : gy);
+      colsum_kernel<<<dim3(cdiv(D4, 32), gy), dim3(32, 8), 0, c.st>>>(da, nullptr, dbf1, R, D4);   // db1f = sum da
+      c.post("colsum");
     }
   } else {
     // folded pw2:  dW2f = dy^T . h, db2f = sum dy  ->  dW2, ds (= A), dbeta, db2 by the chain rule of the fold
-    c.zero(dwf, (int64_t)C * D4, "zero_dwf");
-    c.zero(dbf, C, "zero_dbf");
-    c.zero(dsv, D4, "zero_ds");
+    float *dwf2 = c.w(bw.s2.dwf), *dbf2 = c.w(bw.s2.dbf);
     WgradArgs wg{};
-    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf; wg.db = dbf; wg.R = R; wg.N = C; wg.K = D4;
+    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf2; wg.db = dbf2; wg.R = R; wg.N = C; wg.K = D4;
     wg.exact = 1;   // ds (GRN statistic gradient) is derived from dW2f and feeds every row's gradient
     wgrad(c, wg, "dW2f");
     UnfoldArgs u{};
     u.W = c.p(bp.w2); u.s_n = D4; u.s_k = 1; u.scale_k = c.w(bw.scale); u.shift_k = c.p(bp.beta);
-    u.dWf = dwf; u.dbf = dbf; u.dW = c.g(bp.w2); u.dscale = dsv; u.dshift = c.g(bp.beta); u.dbias = c.g(bp.b2);
+    u.dWf = dwf2; u.dbf = dbf2; u.dW = c.g(bp.w2); u.dscale = dsv; u.dshift = c.g(bp.beta); u.dbias = c.g(bp.b2);
     u.N = C; u.K = D4; u.SL = D4;
     unfold(c, u, "unfold_pw2");
     if (c.ok()) {
       grn_bwd_scale_kernel<<<1, 256, 0, c.st>>>(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
       c.post("grn_bwd_scale");
     }
-    // da = (dy . W2f + kg*h) * gelu'(a)
-    FoldArgs f2{};
-    f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.scale_k = c.w(bw.scale); f2.WfT = c.w(pl->o_wft);
-    f2.N = C; f2.K = D4; f2.SL = D4;
-    fold(c, f2, "fold_pw2T");
+    // da = (dy . W2f + kg*h) * gelu'(a) ; db1f = sum da rides on the epilogue
     GemmArgs gd{};
-    gd.A = dy; gd.Bw = c.w(pl->o_wft); gd.out = da; gd.aux = c.w(bw.h); gd.aux2 = c.w(bw.a); gd.kg = kg;
+    gd.A = dy; use_slot(c, gd, bw.s2, true); gd.out = da; gd.aux = c.w(bw.h); gd.aux2 = c.w(bw.a); gd.kg = kg;
+    gd.colsum2 = dbf1;
     gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
     gemm<EPI_DH_GELU>(c, gd, "da");
   }
-  // pw1 (LN affine folded): dW1f = da^T . vhat, db1f = sum da
-  c.zero(dwf, (int64_t)D4 * C, "zero_dwf");
-  c.zero(dbf, D4, "zero_dbf");
+  // pw1 (LN affine folded): dW1f = da^T . vhat
   WgradArgs w1{};
-  w1.X = da; w1.Y = c.w(bw.vhat); w1.dW = dwf; w1.db = dbf; w1.R = R; w1.N = D4; w1.K = C;
+  w1.X = da; w1.Y = c.w(bw.vhat); w1.dW = dwf1; w1.db = nullptr; w1.R = R; w1.N = D4; w1.K = C;
   wgrad(c, w1, "dW1f");
   UnfoldArgs u1{};
   u1.W = c.p(bp.w1); u1.s_n = C; u1.s_k = 1; u1.scale_k = c.p(bp.ln_w); u1.shift_k = c.p(bp.ln_b);
-  u1.dWf = dwf; u1.dbf = dbf; u1.dW = c.g(bp.w1); u1.dscale = c.g(bp.ln_w); u1.dshift = c.g(bp.ln_b);
+  u1.dWf = dwf1; u1.dbf = dbf1; u1.dW = c.g(bp.w1); u1.dscale = c.g(bp.ln_w); u1.dshift = c.g(bp.ln_b);
   u1.dbias = c.g(bp.b1); u1.N = D4; u1.K = C; u1.SL = C;
   unfold(c, u1, "unfold_pw1");
   // dvhat = da . W1f
-  FoldArgs f1{};
-  f1.W = c.p(bp.w1); f1.s_n = C; f1.s_k = 1; f1.scale_k = c.p(bp.ln_w); f1.WfT = c.w(pl->o_wft);
-  f1.N = D4; f1.K = C; f1.SL = C;
-  fold(c, f1, "fold_pw1T");
   float *dv = c.w(pl->o_gdv), *du = c.w(pl->o_gdu);
   GemmArgs gv{};
-  gv.A = da; gv.Bw = c.w(pl->o_wft); gv.out = dv; gv.M = R; gv.N = C; gv.K = D4; gv.group_rows = group_rows;
+  gv.A = da; use_slot(c, gv, bw.s1, true); gv.out = dv; gv.M = R; gv.N = C; gv.K = D4; gv.group_rows = group_rows;
   gemm<EPI_STORE>(c, gv, "dvhat");
   if (c.ok()) {
     c.acct(4.0 * (3.0 * R * C + R), 0);
@@ -828,11 +878,11 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       c.post("ds_ln");
       FoldArgs f{};
       f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w);
-      f.shift_k = c.p(pl->ds[i - 1].ln_b); f.bias = c.p(pl->ds[i - 1].b);
-      f.Wf = c.w(pl->o_wf); f.bf = c.w(pl->o_bf); f.N = Co; f.K = 4 * Ci; f.SL = Ci;
-      fold(c, f, "fold_ds");
+      f.shift_k = c.p(pl->ds[i - 1].ln_b); f.bias = c.p(pl->ds[i - 1].b); f.SL = Ci;
+      fold_slot(c, f, pl->ds_slot[i - 1], "fold_ds");
       GemmArgs g{};
-      g.A = c.w(pl->o_ds_xhat[i - 1]); g.Bw = c.w(pl->o_wf); g.bias = c.w(pl->o_bf); g.out = c.w(pl->o_ds_out[i - 1]);
+      g.A = c.w(pl->o_ds_xhat[i - 1]); use_slot(c, g, pl->ds_slot[i - 1], false); g.bias = c.w(pl->ds_slot[i - 1].bf);
+      g.out = c.w(pl->o_ds_out[i - 1]);
       g.M = pl->R[i]; g.N = Co; g.K = 4 * Ci; g.group_rows = 0x7fffffff;
       gemm<EPI_STORE>(c, g, "ds_conv");
       x = c.w(pl->o_ds_out[i - 1]);
@@ -849,8 +899,11 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   // decoder entry: proj on visible rows, mask token elsewhere (fcmae.py:251-255)
   const int D = cf.dec_dim;
   {
+    FoldArgs fp{};
+    fp.W = c.p(pl->proj_w); fp.s_n = dm[3]; fp.s_k = 1; fp.SL = dm[3];
+    fold_slot(c, fp, pl->proj_slot, "split_proj");
     GemmArgs g{};
-    g.A = x; g.Bw = c.p(pl->proj_w); g.bias = c.p(pl->proj_b); g.out = c.w(pl->o_z);
+    g.A = x; use_slot(c, g, pl->proj_slot, false); g.bias = c.p(pl->proj_b); g.out = c.w(pl->o_z);
     g.M = (int64_t)geo.B * geo.V; g.N = D; g.K = dm[3]; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "proj");
     scatter_token_kernel<<<ew_grid(pl->cells * (D / 4)), 256, 0, c.st>>>(c.w(pl->o_z), c.p(pl->tok), slot_of, c.w(pl->o_xd),
@@ -863,8 +916,11 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
     d = c.w(pl->dw[k].y);
   }
   if (pl->npix > 0) {
+    FoldArgs fp{};
+    fp.W = c.p(pl->pixw); fp.s_n = D; fp.s_k = 1; fp.SL = D;
+    fold_slot(c, fp, pl->pix_slot, "split_heads");
     GemmArgs g{};
-    g.A = d; g.Bw = c.p(pl->pixw); g.bias = c.p(pl->pixb); g.out = io->pred_pixel;
+    g.A = d; use_slot(c, g, pl->pix_slot, false); g.bias = c.p(pl->pixb); g.out = io->pred_pixel;
     g.M = pl->cells; g.N = pl->npix; g.K = D; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "pixel_heads");
   }
@@ -906,6 +962,7 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
   const int *slot_of = reinterpret_cast<const int *>(c.w(pl->o_slot));
   float *g0 = c.w(pl->o_g0), *g1 = c.w(pl->o_g1);
 
+  c.zero(c.w(pl->o_bzero_begin), pl->o_bzero_end - pl->o_bzero_begin, "zero_bwd");
   {  // seeds: d total / d L_i / denominator_i per prediction column ; d total / d log_vars
     SeedArgs s{};
     s.acc = c.w(pl->o_acc); s.log_vars = pl->logv >= 0 ? c.p(pl->logv) : nullptr; s.losses = io->losses;
@@ -920,11 +977,10 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
   float *dd = g0;  // gradient at the decoder output [cells, D]
   if (pl->npix > 0) {
     FoldArgs f{};
-    f.W = c.p(pl->pixw); f.s_n = D; f.s_k = 1; f.scale_n = c.w(pl->o_cs_pix); f.WfT = c.w(pl->o_wft);
-    f.N = pl->npix; f.K = D; f.SL = D;
-    fold(c, f, "fold_pixT");
+    f.W = c.p(pl->pixw); f.s_n = D; f.s_k = 1; f.scale_n = c.w(pl->o_cs_pix); f.SL = D;
+    fold_slot(c, f, pl->pix_slot, "fold_pixT");   // loss seeds (known only now) scale the rows of the head matrix
     GemmArgs g{};
-    g.A = c.w(pl->o_dpix); g.Bw = c.w(pl->o_wft); g.out = dd; g.M = pl->cells; g.N = D; g.K = pl->npix; g.group_rows = 0x7fffffff;
+    g.A = c.w(pl->o_dpix); use_slot(c, g, pl->pix_slot, true); g.out = dd; g.M = pl->cells; g.N = D; g.K = pl->npix; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "d_dec_pix");
     WgradArgs w{};
     w.X = c.w(pl->o_dpix); w.Y = dec_out; w.rs = c.w(pl->o_cs_pix); w.dW = c.g(pl->pixw); w.db = c.g(pl->pixb);
@@ -967,11 +1023,8 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
     WgradArgs w{};
     w.X = dz; w.Y = x3; w.dW = c.g(pl->proj_w); w.db = c.g(pl->proj_b); w.R = BV; w.N = D; w.K = dm[3];
     wgrad(c, w, "dW_proj");
-    FoldArgs f{};
-    f.W = c.p(pl->proj_w); f.s_n = dm[3]; f.s_k = 1; f.WfT = c.w(pl->o_wft); f.N = D; f.K = dm[3]; f.SL = dm[3];
-    fold(c, f, "projT");
     GemmArgs g{};
-    g.A = dz; g.Bw = c.w(pl->o_wft); g.out = nxt; g.M = BV; g.N = dm[3]; g.K = D; g.group_rows = 0x7fffffff;
+    g.A = dz; use_slot(c, g, pl->proj_slot, true); g.out = nxt; g.M = BV; g.N = dm[3]; g.K = D; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "d_x3");
     std::swap(cur, nxt);
   }
@@ -983,9 +1036,7 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
     }
     if (i > 0) {
       const int Ci = dm[i - 1], Co = dm[i];
-      float *dwf = c.w(pl->o_dwf), *dbf = c.w(pl->o_dbf);
-      c.zero(dwf, (int64_t)Co * 4 * Ci, "zero_dwf");
-      c.zero(dbf, Co, "zero_dbf");
+      float *dwf = c.w(pl->ds_slot[i - 1].dwf), *dbf = c.w(pl->ds_slot[i - 1].dbf);
       WgradArgs w{};
       w.X = cur; w.Y = c.w(pl->o_ds_xhat[i - 1]); w.dW = dwf; w.db = dbf; w.R = pl->R[i]; w.N = Co; w.K = 4 * Ci;
       wgrad(c, w, "dW_ds");
@@ -994,13 +1045,9 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
       u.dWf = dwf; u.dbf = dbf; u.dW = c.g(pl->ds[i - 1].k); u.dscale = c.g(pl->ds[i - 1].ln_w);
       u.dshift = c.g(pl->ds[i - 1].ln_b); u.dbias = c.g(pl->ds[i - 1].b); u.N = Co; u.K = 4 * Ci; u.SL = Ci;
       unfold(c, u, "unfold_ds");
-      FoldArgs f{};
-      f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w); f.WfT = c.w(pl->o_wft);
-      f.N = Co; f.K = 4 * Ci; f.SL = Ci;
-      fold(c, f, "fold_dsT");
       float *dxh = c.w(pl->o_gdv);
       GemmArgs g{};
-      g.A = cur; g.Bw = c.w(pl->o_wft); g.out = dxh; g.M = pl->R[i]; g.N = 4 * Ci; g.K = Co; g.group_rows = 0x7fffffff;
+      g.A = cur; use_slot(c, g, pl->ds_slot[i - 1], true); g.out = dxh; g.M = pl->R[i]; g.N = 4 * Ci; g.K = Co; g.group_rows = 0x7fffffff;
       gemm<EPI_STORE>(c, g, "d_ds_in");
       if (c.ok()) {
         ln_rows_bwd_kernel<<<(unsigned)cdiv64(pl->R[i - 1], 8), 256, 0, c.st>>>(dxh, c.w(pl->o_ds_xhat[i - 1]),
