@@ -130,6 +130,14 @@ int mpmae_forward_encoder(mpmae_plan *plan, const mpmae_io *io, void *cuda_strea
  * on the same workspace. */
 int mpmae_backward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
 
+/* The same backward in three parts, in reverse layer order, so the caller can all-reduce the part of the flat gradient
+ * buffer that is final while the rest is still being computed (replaces DDP's bucket hooks, main_pretrain.py:306-310):
+ *   part 0 = loss seeds + heads + decoder + proj, part 1 = stages 3 and 2, part 2 = stages 1, 0 + patch embedding.
+ * Must be called in order 0, 1, 2 after mpmae_forward.  mpmae_backward_part_range gives the [lo, hi) float range of
+ * the gradient buffer completed by each part. */
+int mpmae_backward_part(mpmae_plan *plan, const mpmae_io *io, int32_t part, void *cuda_stream);
+int mpmae_backward_part_range(const mpmae_plan *plan, int32_t part, int64_t *lo, int64_t *hi);
+
 /* dense encoder features [B, C3, G, G] (zeros at masked cells) from the last forward */
 int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw, void *cuda_stream);
 

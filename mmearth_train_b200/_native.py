@@ -75,6 +75,8 @@ def _load():
         "mpmae_forward": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_forward_encoder": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_backward": (C.c_int, [P, C.POINTER(IO), P]),
+        "mpmae_backward_part": (C.c_int, [P, C.POINTER(IO), I32, P]),
+        "mpmae_backward_part_range": (C.c_int, [P, I32, C.POINTER(I64), C.POINTER(I64)]),
         "mpmae_encoder_features": (C.c_int, [P, C.POINTER(IO), P, P]),
         "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P, P]),
         "mpmae_gemm_epi": (C.c_int, [I32, I32, C.POINTER(GemmDesc), P]),
@@ -92,7 +94,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_backward", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_adamw_step"]
+           "mpmae_forward_encoder", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_adamw_step"]
 
 
 def check(rc: int, what: str = "") -> None:
@@ -174,6 +176,15 @@ class Plan:
             n, c, ms, b, f = line.split(",")
             rows.append((n, int(c), float(ms), float(b), float(f)))
         return rows
+
+    def backward_ranges(self):
+        """[(lo, hi)] float ranges of the flat gradient buffer completed by backward parts 0, 1, 2."""
+        out = []
+        for part in range(3):
+            lo, hi = C.c_int64(), C.c_int64()
+            check(lib.mpmae_backward_part_range(self.handle, part, C.byref(lo), C.byref(hi)), "backward_part_range")
+            out.append((lo.value, hi.value))
+        return out
 
     def launches(self, backward: bool) -> int:
         return lib.mpmae_launch_count(self.handle, 1 if backward else 0)

@@ -88,6 +88,7 @@ struct mpmae_plan {
   int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
   int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
   int launches_fwd = 0, launches_bwd = 0;
+  int bwd_flip = 0;   // which ping-pong buffer holds the running activation gradient between backward parts
   // optional per-launch CUDA-event profile (bench.py roofline leg)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -950,7 +951,8 @@ int mpmae_forward_encoder(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream)
 }
 
 // -------------------------------------------------------------------------------------------------
-int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
+// parts: bit 0 = seeds + heads + decoder + proj ; bit 1 = stages 3, 2 ; bit 2 = stages 1, 0 + patch embedding
+static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, int parts) {
   int rc = check_io(pl, io, true);
   if (rc) return rc;
   Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
@@ -962,6 +964,10 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
   const int *slot_of = reinterpret_cast<const int *>(c.w(pl->o_slot));
   float *g0 = c.w(pl->o_g0), *g1 = c.w(pl->o_g1);
 
+  float *cur = pl->bwd_flip ? g1 : g0, *nxt = pl->bwd_flip ? g0 : g1;
+  const int64_t BV = (int64_t)geo.B * geo.V;
+  if (parts & 1) {
+  cur = g0; nxt = g1;
   c.zero(c.w(pl->o_bzero_begin), pl->o_bzero_end - pl->o_bzero_begin, "zero_bwd");
   {  // seeds: d total / d L_i / denominator_i per prediction column ; d total / d log_vars
     SeedArgs s{};
@@ -1005,14 +1011,12 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
       c.post("pool_ln_bwd");
     }
   }
-  float *cur = g0, *nxt = g1;
   for (int k = cf.dec_depth - 1; k >= 0; --k) {
     const float *xin = k > 0 ? c.w(pl->dw[k - 1].y) : c.w(pl->o_xd);
     block_backward(c, pl->dec[k], pl->dw[k], xin, cur, nxt, pl->cells, D, 1, true);
     std::swap(cur, nxt);
   }
   // decoder entry backward: visible cells -> proj rows, masked cells -> mask token
-  const int64_t BV = (int64_t)geo.B * geo.V;
   const float *x3 = c.w(pl->bw[3][cf.depths[3] - 1].y);
   {
     float *dz = c.w(pl->o_gdv);
@@ -1028,7 +1032,9 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
     gemm<EPI_STORE>(c, g, "d_x3");
     std::swap(cur, nxt);
   }
+  }  // part 0
   for (int i = 3; i >= 0; --i) {
+    if (!(parts & (i >= 2 ? 2 : 4))) continue;
     for (int j = cf.depths[i] - 1; j >= 0; --j) {
       const float *xin = j > 0 ? c.w(pl->bw[i][j - 1].y) : (i > 0 ? c.w(pl->o_ds_out[i - 1]) : c.w(pl->o_x0));
       block_backward(c, pl->blk[i][j], pl->bw[i][j], xin, cur, nxt, pl->R[i], dm[i], pl->P[i], false);
@@ -1058,7 +1064,7 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
       std::swap(cur, nxt);
     }
   }
-  {  // stem + initial conv
+  if (parts & 4) {  // stem + initial conv
     StemBwdArgs sb{};
     sb.f = stem_args(c);
     sb.dx0 = cur; sb.dc = nxt;
@@ -1082,7 +1088,28 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
       c.post("initial_conv_wgrad");
     }
   }
-  return finish(c, &pl->launches_bwd);
+  pl->bwd_flip = (cur == g1) ? 1 : 0;
+  int n = 0;
+  rc = finish(c, &n);
+  pl->launches_bwd = (parts & 1) ? n : pl->launches_bwd + n;
+  return rc;
+}
+
+int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) { return backward_impl(pl, io, cuda_stream, 7); }
+
+int mpmae_backward_part(mpmae_plan *pl, const mpmae_io *io, int32_t part, void *cuda_stream) {
+  if (part < 0 || part > 2) return fail(MPMAE_ERR_INVALID, "backward part %d", part);
+  return backward_impl(pl, io, cuda_stream, 1 << part);
+}
+
+// [lo, hi) of the flat gradient buffer that is final once backward part `part` has run (reverse layer order)
+int mpmae_backward_part_range(const mpmae_plan *pl, int32_t part, int64_t *lo, int64_t *hi) {
+  if (!pl || !lo || !hi || part < 0 || part > 2) return fail(MPMAE_ERR_INVALID, "backward part %d", part);
+  const int64_t mid_begin = pl->blk[2][0].dw_k, tail_begin = pl->proj_w;
+  if (part == 0) { *lo = tail_begin; *hi = pl->n_params; }
+  else if (part == 1) { *lo = mid_begin; *hi = tail_begin; }
+  else { *lo = 0; *hi = mid_begin; }
+  return MPMAE_OK;
 }
 
 int mpmae_profile_begin(mpmae_plan *pl) {

@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nat
+from .dist import FlatGradReducer
 
 PIXEL_CONTINUOUS = ("sentinel2", "sentinel1", "aster", "canopy_height_eth")
 PIXEL_CATEGORICAL = ("dynamic_world", "esa_worldcover")
@@ -141,6 +142,7 @@ class FCMAE(nn.Module):
         self._param_slices: List[Tuple[int, int, Tuple[int, ...]]] = []
         self.allreduce_chunks = 4
         self.noise_override: Optional[torch.Tensor] = None
+        self.backward_in_parts = False      # world_size > 1 always runs the backward in parts (overlapped all-reduce)
         self.last_run: Optional[dict] = None
 
         # ---- module tree with the reference's names
@@ -381,10 +383,19 @@ class FCMAE(nn.Module):
         target.zero_()
         io = self._io(run, grads=target, grad_out=go)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        plan = run["plan"]
         with torch.cuda.device(dev):
-            nat.check(nat.lib.mpmae_backward(run["plan"].handle, C.byref(io), C.c_void_p(stream)), "mpmae_backward")
-        if world > 1:
-            dist.all_reduce(target, op=dist.ReduceOp.SUM)     # flat fp32 buffer over NCCL/NVLink
+            if world == 1 and not self.backward_in_parts:
+                nat.check(nat.lib.mpmae_backward(plan.handle, C.byref(io), C.c_void_p(stream)), "mpmae_backward")
+            else:
+                # three parts in reverse layer order; the finished slice of the flat buffer is all-reduced (NCCL over
+                # NVLink / NVSwitch, on the backend's stream) while the next part computes
+                reducer = FlatGradReducer(plan.backward_ranges(), self._n_flat)
+                for part in range(3):
+                    nat.check(nat.lib.mpmae_backward_part(plan.handle, C.byref(io), part, C.c_void_p(stream)),
+                              "mpmae_backward_part")
+                    reducer.reduce_part(target, part)
+                reducer.wait()
         if not fresh:
             self._gacc.add_(self._gstep)
         self._bind_grads()

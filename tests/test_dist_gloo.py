@@ -1,0 +1,84 @@
+"""World-size-2 gloo tests (CPU) of the N > 1 host logic: the flat-buffer gradient reducer over the ranges the native
+backward completes part by part, and DistributedDataParallel construction around the drop-in module."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fcmae_oracle as fo
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build_model():
+    import mmearth_train_b200 as m
+    args = fo.make_args(None, "uncertainty")
+    return m.convnextv2_atto(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True, patch_size=8,
+                             img_size=56, args=args, loss_fn=m.UncertaintyWeightingStrategy(12))
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmearth_train_b200.dist import FlatGradReducer, seed_scale
+        model = _build_model()
+        plan = model._plan(4)
+        ranges = plan.backward_ranges()
+        n = model._n_flat
+        # ranges tile the flat buffer in reverse layer order: tail (heads/decoder/proj) first, patch embedding last
+        assert ranges[0][1] == n and ranges[2][0] == 0 and ranges[0][0] == ranges[1][1] and ranges[1][0] == ranges[2][1]
+        names = {nm: off for nm, _s, off, _d in plan.params()}
+        assert ranges[0][0] == names["proj.weight"] and ranges[1][0] == names["encoder.stages.2.0.dwconv.kernel"]
+        g = torch.Generator().manual_seed(100 + rank)
+        flat = torch.randn(n, generator=g) * seed_scale()          # each rank's local gradient, pre-scaled by 1/world
+        local = flat.clone()
+        red = FlatGradReducer(ranges, n)
+        for part in range(3):                                       # reverse layer order, asynchronous
+            red.reduce_part(flat, part)
+        red.wait()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(flat, sum(gathered), atol=1e-6)       # == mean of the unscaled gradients (DDP semantics)
+        assert red.bytes_reduced == n * 4
+        with pytest.raises(ValueError):
+            FlatGradReducer([(0, 10), (12, n)], n)
+        # DDP (main_pretrain.py:306-310) must accept the module and manage only the token parameter
+        ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=False)
+        managed = [nm for nm, p in ddp.module.named_parameters() if nm not in ddp.parameters_to_ignore]
+        assert managed == ["_ddp_token"], managed
+        assert ddp.module is model
+        out[rank] = "ok"
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out[rank] = "".join(traceback.format_exception(type(e), e, e.__traceback__))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_reducer_and_ddp_wrap_world2(native_lib):
+    world = 2
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail("gloo worker hung")
+    assert dict(out) == {0: "ok", 1: "ok"}, dict(out)

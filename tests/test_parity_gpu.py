@@ -131,6 +131,22 @@ def test_backward_is_linear_in_upstream_gradient_and_accumulates():
     assert gu.rel_err(model.flat_grads, 2 * g2) < 1e-5
 
 
+def test_backward_in_parts_equals_single_call():
+    """mpmae_backward_part 0, 1, 2 (the multi-GPU path: a slice of the flat gradient is all-reduced after each part)."""
+    z, meta, orc, batch, noise = gu.inputs("atto_p8_all_unc")
+    model = build_native(meta["cfg"], orc, 1)
+    model.noise_override = noise
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    model(dev_batch)[0].backward()
+    g1 = model.flat_grads.clone()
+    model.zero_grad(set_to_none=True)
+    model.backward_in_parts = True
+    model(dev_batch)[0].backward()
+    assert gu.rel_err(model.flat_grads, g1) < 1e-5
+    ranges = model.last_run["plan"].backward_ranges()
+    assert ranges[2][0] == 0 and ranges[0][1] == model._n_flat
+
+
 def test_full_size_properties_cfg2():
     """BASELINE.json configs[1] at full size (bs 256): size-independent properties."""
     B = 256
