@@ -261,7 +261,7 @@ def main():
                      "kernels": [{"name": r[0], "launches": r[1] // prof_steps, "ms_per_step": r[2] / prof_steps,
                                   "GBps": (r[3] / (r[2] / 1e3) / 1e9) if r[2] > 0 else None,
                                   "TFLOPs": (r[4] / (r[2] / 1e3) / 1e12) if r[2] > 0 else None}
-                                 for r in sorted(rows, key=lambda r: -r[2])[:12]]})
+                                 for r in sorted(rows, key=lambda r: -r[2])[:40]]})
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = oracle_cpu_throughput(cfg, 12, 1, max_seconds=20.0)
         else:

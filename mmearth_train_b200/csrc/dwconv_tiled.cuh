@@ -58,13 +58,14 @@ __device__ __forceinline__ void load_neighbour_slots(const int *slot_of, const G
 }
 
 // ------------------------------------------------------------------------------------------------ patch flavour
-template <int P, int TR>
+// CT = channel count known at compile time (0 = run time): shared-memory addresses become immediates
+template <int P, int TR, int CT>
 __global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
   constexpr int W = P + 6, TILES = P / TR;
   const DwArgs &p = t.a;
   extern __shared__ __align__(16) float smem[];
   __shared__ int nb[25];
-  const int C = p.C, V = p.geo.V;
+  const int C = CT ? CT : p.C, V = p.geo.V;
   float *win = smem;                         // [W*W][C]
   float *ubuf = win + (size_t)W * W * C;     // [P*P][C]
   const int pu = blockIdx.x, n = pu / V;
@@ -145,12 +146,12 @@ __global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
 
 // dW[tap, c] += sum du[o, c] * x[o + off(tap), c] ; db[c] += sum du[o, c].  Persistent CTAs: every thread keeps its
 // channel's 49 partial sums in registers across all the patches it visits.
-template <int P, int TR>
+template <int P, int TR, int CT>
 __global__ void __launch_bounds__(512) dwconv_patch_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
   constexpr int W = P + 6, TILES = P / TR;
   extern __shared__ __align__(16) float smem[];
   __shared__ int nb[25];
-  const int C = p.C, V = p.geo.V;
+  const int C = CT ? CT : p.C, V = p.geo.V;
   float *win = smem;                         // [W*W][C]   x halo window
   float *dus = win + (size_t)W * W * C;      // [P*P][C]   du of the patch (Z-order) ; reused for the final reduction
   const int nthreads = blockDim.x;
@@ -333,8 +334,219 @@ __global__ void __launch_bounds__(128) dwconv_grid7_wgrad_kernel(DwWgradArgs p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ sample flavour (P = 2, G = 7)
+// With 2x2-pixel patches a per-patch halo window is 16x larger than the patch, so stage 2 stages the WHOLE sample
+// instead: a zero-padded 20x20 pixel grid per channel chunk of CC channels lives in shared memory, every visible pixel
+// is loaded exactly once, and one thread computes a 2x2 patch of one channel from an 8x8 register window
+// (64 shared loads for 196 FMAs).  The [76, C] result tile collects all chunks, then LayerNorm + coalesced copy-out.
+template <int CC>
+__global__ void __launch_bounds__(512) dwconv_s2_kernel(DwArgs p, const int *__restrict__ vis_patch) {
+  constexpr int GW = 20, NCELL = GW * GW, CC4 = CC / 4;
+  constexpr int NT = (512 / CC) * CC, NPG = NT / CC;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int vis[64];
+  const int C = p.C, V = p.geo.V, n = blockIdx.x, tid = threadIdx.x;
+  float *grid = smem;                       // [NCELL][CC]
+  float *ubuf = smem + NCELL * CC;          // [V*4][C]
+  const int64_t row0 = (int64_t)n * V * 4;
+  if (tid < V) vis[tid] = vis_patch[n * V + tid];
+  const int c = tid % CC, pg = tid / CC;
+  for (int c0 = 0; c0 < C; c0 += CC) {
+    __syncthreads();
+    for (int i = tid; i < NCELL * CC4; i += NT) reinterpret_cast<float4 *>(grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int i = tid; i < V * 4 * CC4; i += NT) {
+      const int r = i / CC4, c4 = i - r * CC4;
+      const int l = vis[r >> 2], m = r & 3;
+      const int gy = (l / 7) * 2 + (m & 1) + 3, gx = (l % 7) * 2 + (m >> 1) + 3;
+      reinterpret_cast<float4 *>(grid)[(gy * GW + gx) * CC4 + c4] =
+          __ldg(reinterpret_cast<const float4 *>(p.x + (row0 + r) * C + c0) + c4);
+    }
+    float w[49];
+#pragma unroll
+    for (int k = 0; k < 49; ++k) {
+      const int kh = k / 7, kw = k % 7;
+      const int a = p.flip ? 6 - kh : kh, b = p.flip ? 6 - kw : kw;
+      w[k] = __ldg(p.w + a * p.w_skh + b * p.w_skw + (c0 + c) * p.w_sc);
+    }
+    const float b0 = p.bias ? __ldg(p.bias + c0 + c) : 0.f;
+    __syncthreads();
+    if (tid < NT) {
+      for (int slot = pg; slot < V; slot += NPG) {
+        const int l = vis[slot];
+        const int y0 = (l / 7) * 2, x0 = (l % 7) * 2;   // window origin in the padded grid
+        float acc[2][2] = {{b0, b0}, {b0, b0}};
+#pragma unroll
+        for (int iy = 0; iy < 8; ++iy) {
+          float in[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) in[j] = grid[((y0 + iy) * GW + x0 + j) * CC + c];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int kh = iy - r;
+            if (kh >= 0 && kh < 7) {
+#pragma unroll
+              for (int kw = 0; kw < 7; ++kw) {
+                acc[r][0] = fmaf(in[kw], w[kh * 7 + kw], acc[r][0]);
+                acc[r][1] = fmaf(in[kw + 1], w[kh * 7 + kw], acc[r][1]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) ubuf[(size_t)(slot * 4 + (r | (ox << 1))) * C + c0 + c] = acc[r][ox];
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int rows = V * 4;
+  if (p.do_ln) {
+    for (int o = warp; o < rows; o += nw) {
+      float *ur = ubuf + (size_t)o * C;
+      float s = 0.f;
+      for (int cc = lane; cc < C; cc += 32) s += ur[cc];
+      const float mean = warp_sum(s) / (float)C;
+      float v = 0.f;
+      for (int cc = lane; cc < C; cc += 32) { const float d = ur[cc] - mean; v += d * d; }
+      const float rstd = rsqrtf(warp_sum(v) / (float)C + p.eps);
+      for (int cc = lane; cc < C; cc += 32) ur[cc] = (ur[cc] - mean) * rstd;
+      if (lane == 0) p.rstd[row0 + o] = rstd;
+    }
+    __syncthreads();
+  }
+  const int n4 = rows * C / 4;
+  float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+  const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+  for (int i = tid; i < n4; i += blockDim.x) {
+    float4 v = reinterpret_cast<const float4 *>(ubuf)[i];
+    if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+    dst[i] = v;
+  }
+}
+
+// weight gradient, same staging; blockIdx.y = channel chunk, blockIdx.x strides samples; every thread keeps its channel's
+// 49 partial sums in registers across all the patches and samples it visits
+template <int CC>
+__global__ void __launch_bounds__(512) dwconv_s2_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+  constexpr int GW = 20, NCELL = GW * GW, CC4 = CC / 4;
+  constexpr int NT = (512 / CC) * CC, NPG = NT / CC;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int vis[64];
+  const int C = p.C, V = p.geo.V, tid = threadIdx.x;
+  const int c0 = blockIdx.y * CC;
+  float *grid = smem;
+  const int c = tid % CC, pg = tid / CC;
+  float dw[49];
+  float db = 0.f;
+#pragma unroll
+  for (int k = 0; k < 49; ++k) dw[k] = 0.f;
+  for (int n = blockIdx.x; n < p.geo.B; n += gridDim.x) {
+    const int64_t row0 = (int64_t)n * V * 4;
+    __syncthreads();
+    if (tid < V) vis[tid] = vis_patch[n * V + tid];
+    for (int i = tid; i < NCELL * CC4; i += NT) reinterpret_cast<float4 *>(grid)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int i = tid; i < V * 4 * CC4; i += NT) {
+      const int r = i / CC4, c4 = i - r * CC4;
+      const int l = vis[r >> 2], m = r & 3;
+      const int gy = (l / 7) * 2 + (m & 1) + 3, gx = (l % 7) * 2 + (m >> 1) + 3;
+      reinterpret_cast<float4 *>(grid)[(gy * GW + gx) * CC4 + c4] =
+          __ldg(reinterpret_cast<const float4 *>(p.x + (row0 + r) * C + c0) + c4);
+    }
+    __syncthreads();
+    if (tid < NT) {
+      for (int slot = pg; slot < V; slot += NPG) {
+        const int l = vis[slot];
+        const int y0 = (l / 7) * 2, x0 = (l % 7) * 2;
+        float d[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) {
+            d[r][ox] = __ldg(p.du + (row0 + slot * 4 + (r | (ox << 1))) * C + c0 + c);
+            db += d[r][ox];
+          }
+#pragma unroll
+        for (int iy = 0; iy < 8; ++iy) {
+          float in[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) in[j] = grid[((y0 + iy) * GW + x0 + j) * CC + c];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int kh = iy - r;
+            if (kh >= 0 && kh < 7) {
+#pragma unroll
+              for (int kw = 0; kw < 7; ++kw)
+                dw[kh * 7 + kw] = fmaf(d[r][0], in[kw], fmaf(d[r][1], in[kw + 1], dw[kh * 7 + kw]));
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float *red = smem;  // [50][CC]
+  for (int i = tid; i < 50 * CC; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if (tid < NT) {
+#pragma unroll
+    for (int k = 0; k < 49; ++k) atomicAdd(&red[k * CC + c], dw[k]);
+    atomicAdd(&red[49 * CC + c], db);
+  }
+  __syncthreads();
+  for (int i = tid; i < 49 * CC; i += blockDim.x) {
+    const int k = i / CC, cc = i - k * CC;
+    const int kh = k / 7, kw = k - kh * 7;
+    atomicAdd(&p.dw[kh * p.w_skh + kw * p.w_skw + (c0 + cc) * p.w_sc], red[i]);
+  }
+  if (p.dbias)
+    for (int cc = tid; cc < CC; cc += blockDim.x) atomicAdd(&p.dbias[c0 + cc], red[49 * CC + cc]);
+}
+
+template <int CC>
+inline cudaError_t launch_s2(const DwArgs &a, const int *vis_patch, cudaStream_t st) {
+  const size_t sm = ((size_t)400 * CC + (size_t)a.geo.V * 4 * a.C) * sizeof(float);
+  if (sm > 226 * 1024 || a.geo.V > 49) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_s2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dwconv_s2_kernel<CC><<<a.geo.B, (512 / CC) * CC, sm, st>>>(a, vis_patch);
+  return cudaGetLastError();
+}
+template <int CC>
+inline cudaError_t launch_s2_wgrad(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  const size_t sm = (size_t)400 * CC * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_s2_wgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int chunks = p.C / CC;
+  int per_sm = (int)((220 * 1024) / sm);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int gx = (148 * per_sm) / chunks;
+  if (gx < 1) gx = 1;
+  if (gx > p.geo.B) gx = p.geo.B;
+  dwconv_s2_wgrad_kernel<CC><<<dim3(gx, chunks), (512 / CC) * CC, sm, st>>>(p, vis_patch);
+  return cudaGetLastError();
+}
+inline int s2_chunk(int C) {
+  if (C % 80 == 0) return 80;
+  if (C % 64 == 0) return 64;
+  if (C % 48 == 0) return 48;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
-template <int P, int TR>
+template <int P, int TR, int CT>
 inline cudaError_t launch_patch(const DwTiledArgs &t, cudaStream_t st) {
   const int C = t.a.C;
   const int threads = ((C * (P / TR) + 31) / 32) * 32;
@@ -342,15 +554,16 @@ inline cudaError_t launch_patch(const DwTiledArgs &t, cudaStream_t st) {
   if (threads > 512 || sm > 226 * 1024) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_kernel<P, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_kernel<P, TR, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(dwconv_patch_kernel<P, TR, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
-  dwconv_patch_kernel<P, TR><<<t.a.geo.B * t.a.geo.V, threads, sm, st>>>(t);
+  dwconv_patch_kernel<P, TR, CT><<<t.a.geo.B * t.a.geo.V, threads, sm, st>>>(t);
   return cudaGetLastError();
 }
 
-template <int P, int TR>
+template <int P, int TR, int CT>
 inline cudaError_t launch_patch_wgrad(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
   const int C = p.C;
   const int threads = ((C * (P / TR) + 31) / 32) * 32;
@@ -359,8 +572,9 @@ inline cudaError_t launch_patch_wgrad(const DwWgradArgs &p, const int *vis_patch
   if (threads > 512 || sm > 226 * 1024) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_wgrad_kernel<P, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_wgrad_kernel<P, TR, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(dwconv_patch_wgrad_kernel<P, TR, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
   int per_sm = (int)((220 * 1024) / sm);
@@ -369,7 +583,7 @@ inline cudaError_t launch_patch_wgrad(const DwWgradArgs &p, const int *vis_patch
   int grid = 148 * per_sm;
   const int units = p.geo.B * p.geo.V;
   if (grid > units) grid = units;
-  dwconv_patch_wgrad_kernel<P, TR><<<grid, threads, sm, st>>>(p, vis_patch);
+  dwconv_patch_wgrad_kernel<P, TR, CT><<<grid, threads, sm, st>>>(p, vis_patch);
   return cudaGetLastError();
 }
 
@@ -393,9 +607,28 @@ inline cudaError_t launch_dwconv_tiled(const DwArgs &a, const int *vis_patch, cu
   }
   if (!vis_patch || !a.slot_of) return cudaErrorInvalidConfiguration;
   DwTiledArgs t{a, vis_patch};
-  if (a.P == 8) return launch_patch<8, 2>(t, st);
-  if (a.P == 4) return launch_patch<4, 2>(t, st);
-  if (a.P == 2) return launch_patch<2, 2>(t, st);
+  if (a.P == 8) {
+    if (a.C == 40) return launch_patch<8, 2, 40>(t, st);
+    if (a.C == 96) return launch_patch<8, 2, 96>(t, st);
+    return launch_patch<8, 2, 0>(t, st);
+  }
+  if (a.P == 4) {
+    if (a.C == 80) return launch_patch<4, 2, 80>(t, st);
+    if (a.C == 192) return launch_patch<4, 2, 192>(t, st);
+    return launch_patch<4, 2, 0>(t, st);
+  }
+  if (a.P == 2) {
+    if (a.geo.G == 7) {
+      cudaError_t e = cudaErrorInvalidConfiguration;
+      const int cc = s2_chunk(a.C);
+      if (cc == 80) e = launch_s2<80>(a, vis_patch, st);
+      else if (cc == 64) e = launch_s2<64>(a, vis_patch, st);
+      else if (cc == 48) e = launch_s2<48>(a, vis_patch, st);
+      if (e != cudaErrorInvalidConfiguration) return e;
+      (void)cudaGetLastError();
+    }
+    return launch_patch<2, 2, 0>(t, st);
+  }
   return cudaErrorInvalidConfiguration;
 }
 
@@ -412,9 +645,25 @@ inline cudaError_t launch_dwconv_wgrad_tiled(const DwWgradArgs &p, const int *vi
     return cudaGetLastError();
   }
   if (!vis_patch || !p.slot_of) return cudaErrorInvalidConfiguration;
-  if (p.P == 8) return launch_patch_wgrad<8, 2>(p, vis_patch, st);
-  if (p.P == 4) return launch_patch_wgrad<4, 2>(p, vis_patch, st);
-  if (p.P == 2) return launch_patch_wgrad<2, 2>(p, vis_patch, st);
+  if (p.P == 8) {
+    if (p.C == 40) return launch_patch_wgrad<8, 2, 40>(p, vis_patch, st);
+    if (p.C == 96) return launch_patch_wgrad<8, 2, 96>(p, vis_patch, st);
+    return launch_patch_wgrad<8, 2, 0>(p, vis_patch, st);
+  }
+  if (p.P == 4) {
+    if (p.C == 80) return launch_patch_wgrad<4, 2, 80>(p, vis_patch, st);
+    if (p.C == 192) return launch_patch_wgrad<4, 2, 192>(p, vis_patch, st);
+    return launch_patch_wgrad<4, 2, 0>(p, vis_patch, st);
+  }
+  if (p.P == 2) {
+    if (p.geo.G == 7 && p.geo.V <= 49) {
+      const int cc = s2_chunk(p.C);
+      if (cc == 80) return launch_s2_wgrad<80>(p, vis_patch, st);
+      if (cc == 64) return launch_s2_wgrad<64>(p, vis_patch, st);
+      if (cc == 48) return launch_s2_wgrad<48>(p, vis_patch, st);
+    }
+    return launch_patch_wgrad<2, 2, 0>(p, vis_patch, st);
+  }
   return cudaErrorInvalidConfiguration;
 }
 
