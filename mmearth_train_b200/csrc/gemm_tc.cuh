@@ -46,10 +46,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps until the phase flips
       : "memory");
   return ok != 0;
 }
@@ -115,6 +115,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// issue only: the registers are defined after tmem_ld_wait16() (which names them, so no use can be hoisted above it)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   uint32_t r[16];
@@ -197,7 +214,7 @@ __global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsNoSplit, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
   constexpr uint32_t a_bytes = BM * BK * 4;
   const uint32_t b_bytes = (uint32_t)bn * BK * 4;
@@ -214,6 +231,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float *colacc2 = colacc + kTcGroups * bn;                          // [bn]
   float *vec_bias_all = colacc2 + bn;                                // [num_n * bn] bias (zero padded)
   float *vec_kg_all = vec_bias_all + p.num_n * bn;                   // [num_n * bn] kg of group 0 (EPI_DH_GELU)
+  float *statacc1 = vec_kg_all + p.num_n * bn;                       // [num_n * bn] kernel-long column sums (one group)
+  float *statacc2 = statacc1 + p.num_n * bn;                         // [num_n * bn]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs &g = p.g;
@@ -232,6 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = threadIdx.x - 64; i < p.num_n * bn; i += kEpiThreads) {
       vec_bias_all[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
       if (MODE == EPI_DH_GELU) vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+      if (MODE != EPI_STORE) { statacc1[i] = 0.f; statacc2[i] = 0.f; }
     }
   }
   tc_fence_before();
@@ -300,6 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int kParts = kEpiWarps / 4;
     const int et = threadIdx.x - 64;
     const float *pre_src = (MODE == EPI_STORE) ? g.resid : (MODE == EPI_DG) ? g.aux : (MODE == EPI_DH_GELU) ? g.aux2 : nullptr;
+    const bool single_group = (int64_t)g.group_rows >= g.M;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -331,11 +352,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       };
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
+      const int ncols = (g.N - n_base < bn) ? g.N - n_base : bn;
+      // ---- fast path: full 128-row tile, one statistics group, whole 8-column pieces, 32-byte aligned rows.  No
+      // per-element predicates; column statistics accumulate in shared memory for the whole kernel (flushed once at the
+      // end); the next chunk's accumulator (tcgen05.ld) and per-element operand are in flight while this one is computed.
+      if (single_group && (int64_t)(m_blk + 1) * BM <= g.M && (ncols & 7) == 0 && p.vec8 && (!pre_src || p.vec8_in)) {
+        const int64_t row_off = m * (int64_t)g.N + n_base;
+        float *outp = g.out + row_off;
+        float *out2p = (MODE == EPI_GELU_SQ) ? g.out2 + row_off : nullptr;
+        const float *prep = pre_src ? pre_src + row_off : nullptr;
+        auto load_pre = [&](int c0, float4 *dst) {
+          if (prep) {
+            ld_global_v8(prep + c0, dst[0], dst[1]);
+            if (c0 + 8 < ncols) ld_global_v8(prep + c0 + 8, dst[2], dst[3]);
+          }
+        };
+        int c0 = part * 16;
+        float4 pre[4];
+        uint32_t vr[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 < ncols) load_pre(c0, pre);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        if (c0 < ncols) tmem_ld16_issue(taddr + c0, vr);
+        for (; c0 < ncols; c0 += 16 * kParts) {
+          const int cn = c0 + 16 * kParts;
+          float v[16];
+          float4 cur[4];
+          tmem_ld_wait16(vr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cur[j] = pre[j];
+          if (cn < ncols) { tmem_ld16_issue(taddr + cn, vr); load_pre(cn, pre); }
+          float s1[16], s2[16];
+          const bool two = c0 + 8 < ncols;   // warp uniform
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (h8 == 1 && !two) {
+#pragma unroll
+              for (int j = 8; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+              break;
+            }
+            float4 o[2], o2[2];
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              const int j = h8 * 8 + q4 * 4;
+              const float4 acc = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              const float4 pv = cur[h8 * 2 + q4];
+              const float4 bv = *reinterpret_cast<const float4 *>(vec_bias + c0 + j);
+              float4 r, r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (MODE == EPI_STORE) {
+                r = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
+              } else if (MODE == EPI_GELU_SQ) {
+                r = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
+                r2 = make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
+                s1[j] = r2.x * r2.x; s1[j + 1] = r2.y * r2.y; s1[j + 2] = r2.z * r2.z; s1[j + 3] = r2.w * r2.w;
+              } else if (MODE == EPI_DG) {
+                r = acc;
+                s1[j] = acc.x * pv.x; s1[j + 1] = acc.y * pv.y; s1[j + 2] = acc.z * pv.z; s1[j + 3] = acc.w * pv.w;
+                s2[j] = acc.x; s2[j + 1] = acc.y; s2[j + 2] = acc.z; s2[j + 3] = acc.w;
+              } else {  // EPI_DH_GELU
+                const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j);
+                float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
+                gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
+                r.x = fmaf(kgv.x, hx, acc.x) * dx_;
+                r.y = fmaf(kgv.y, hy, acc.y) * dy_;
+                r.z = fmaf(kgv.z, hz, acc.z) * dz_;
+                r.w = fmaf(kgv.w, hw, acc.w) * dw_;
+                s2[j] = r.x; s2[j + 1] = r.y; s2[j + 2] = r.z; s2[j + 3] = r.w;
+              }
+              o[q4] = r; o2[q4] = r2;
+            }
+            st_global_v8(outp + c0 + h8 * 8, o[0], o[1]);
+            if (MODE == EPI_GELU_SQ) st_global_v8(out2p + c0 + h8 * 8, o2[0], o2[1]);
+          }
+          if (MODE == EPI_GELU_SQ || MODE == EPI_DG) {
+            const float t = warp_colsum16(s1, lane);
+            if (lane < 16) atomicAdd(&statacc1[n_base + c0 + lane], t);
+          }
+          if (MODE == EPI_DG || MODE == EPI_DH_GELU) {
+            const float t = warp_colsum16(s2, lane);
+            if (lane < 16) atomicAdd(&statacc2[n_base + c0 + lane], t);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+        continue;
+      }
       float4 pre[4];
       prefetch(part * 16, pre);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
 
       for (int c0 = part * 16; c0 < bn; c0 += 16 * kParts) {
         float4 nxt[4];
@@ -454,6 +566,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+    }
+    if (MODE != EPI_STORE) {   // fast-path statistics: one global atomic per column per CTA
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      for (int i = et; i < g.N; i += kEpiThreads) {
+        if ((MODE == EPI_GELU_SQ || MODE == EPI_DG) && g.colsum) { const float t = statacc1[i]; if (t != 0.f) atomicAdd(&g.colsum[i], t); }
+        if ((MODE == EPI_DG || MODE == EPI_DH_GELU) && g.colsum2) { const float t = statacc2[i]; if (t != 0.f) atomicAdd(&g.colsum2[i], t); }
       }
     }
   } else if (SPLIT) {
@@ -586,7 +705,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kTnThreads + 128 : kTnThreads, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
   constexpr uint32_t m_bytes = BM * 32 * 4;                 // 4 blocks x [32 rows][128 B]
   const uint32_t n_bytes = (uint32_t)bn * 32 * 4;           // bn/32 blocks
@@ -776,7 +895,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   auto smem_for = [&](int bn) {
     const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)bn * BK * 4);
     const int num_n = cdiv(a.N, bn);
-    return 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)(5 * bn + 2 * num_n * bn) * 4;
+    return 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)(5 * bn + 4 * num_n * bn) * 4;
   };
   // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget, else a ragged tail
   int bn = 0;
