@@ -53,14 +53,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 // cdf = Phi(x), e = exp(-x^2 / 2)
 __device__ __forceinline__ void normal_cdf_f(float x, float &cdf, float &e) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float u = fabsf(x) * 0.849321800f;                  // |x| sqrt(log2(e) / 2):  u^2 = x^2 log2(e) / 2
+  const float t = rcp_approx(fmaf(0.272737481f, u, 1.0f));  // 1 / (1 + 0.3275911 |x| / sqrt 2)
   float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
   p = fmaf(p, t, 0.5f * 1.421413741f);
   p = fmaf(p, t, 0.5f * -0.284496736f);
   p = fmaf(p, t, 0.5f * 0.254829592f);
   p *= t;
-  e = ex2_approx((x * x) * -0.72134752044448170f);   // 2^(-x^2 log2(e) / 2)
+  e = ex2_approx(-(u * u));                           // exp(-x^2 / 2)
   const float q = p * e;                             // 0.5 erfc(|x| / sqrt 2)
   cdf = x < 0.f ? q : 1.0f - q;
 }

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -183,7 +184,10 @@ struct TcParams {
   int stages;    // shared-memory ring depth (<= STAGES)
   int vec8;      // N % 8 == 0 and 32-byte aligned outputs: 256-bit stores
   int vec8_in;   // same for the prefetched per-element operand
+  int tma_out;   // output tensor maps are valid: the fast path stores through TMA
   uint32_t tmem_cols;
+  int dbg;       // MPMAE_TC_DBG timing experiments (results invalid): 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld,
+                 // 32 no MMAs, 64 no operand split
 };
 
 __device__ __forceinline__ void tmem_ld16v(uint32_t taddr, float *v) { tmem_ld16(taddr, v); }
@@ -203,16 +207,40 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-constexpr int kEpiWarps = 12, kEpiThreads = kEpiWarps * 32;
-constexpr int kThreadsNoSplit = 64 + kEpiThreads, kThreadsSplit = kThreadsNoSplit + 128;
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then the epilogue warps, then (3xTF32 only) the
+// operand-splitter warps.  GELU / statistics epilogues are latency bound and get 16 warps (4 per scheduler) with 2 splitter
+// warps (their K is the narrow side); the plain store epilogue is light and its K is the wide side, so it runs 8 + 8.
+// 18-20 warps = 5 per scheduler keeps 96 registers per thread.
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == EPI_STORE ? 8 : 16; }
+__host__ __device__ constexpr int split_warps(int mode, bool split) { return !split ? 0 : (mode == EPI_STORE ? 8 : 2); }
+__host__ __device__ constexpr int tc_threads(int mode, bool split) { return 64 + 32 * epi_warps(mode) + 32 * split_warps(mode, split); }
+__host__ __device__ constexpr int out_arrays(int mode) { return mode == EPI_GELU_SQ ? 2 : 1; }
+constexpr uint32_t kStageOutBytes = 32 * 16 * 4;   // one warp's [32 rows x 16 columns] output chunk
+
+// 2D TMA store of a [32 x 16] fp32 chunk (64-byte swizzle) from shared memory; out-of-range rows / columns are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
 // (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
 // tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
 template <int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kThreadsSplit : kThreadsNoSplit, 1)
+__global__ void __launch_bounds__(tc_threads(MODE, SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_b_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
+               const __grid_constant__ CUtensorMap map_out2, const TcParams p) {
+  constexpr int kEpiWarps = epi_warps(MODE), kEpiThreads = 32 * kEpiWarps;
+  constexpr int kSplitWarps = split_warps(MODE, SPLIT), kSplitThreads = 32 * kSplitWarps;
+  constexpr int kThreadsNoSplit = 64 + kEpiThreads;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
@@ -220,7 +248,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t b_bytes = (uint32_t)bn * BK * 4;
   const uint32_t a_span = SPLIT ? 2 * a_bytes : a_bytes;             // [A | Alo]
   const uint32_t stage_bytes = a_span + (SPLIT ? 2 : 1) * b_bytes;   // [A | Alo | B | Blo]
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)nstage * stage_bytes);
+  uint8_t *stage_out = smem + (size_t)nstage * stage_bytes;          // [kEpiWarps][out_arrays][32 x 16] TMA-store staging
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_out + (size_t)kEpiWarps * out_arrays(MODE) * kStageOutBytes);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *split_bar = empty_bar + STAGES;
   uint64_t *tfull_bar = split_bar + STAGES;
@@ -240,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], kSplitWarps > 0 ? kSplitWarps : 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -294,10 +324,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_span);
+          if (!(p.dbg & 32)) {
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes per instruction: advance the start address by 2 (x16 B)
             umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          if (SPLIT) {
+          }
+          if (SPLIT && !(p.dbg & 32)) {
             const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sa + a_span + b_bytes);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
@@ -354,14 +386,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
       const int ncols = (g.N - n_base < bn) ? g.N - n_base : bn;
-      // ---- fast path: full 128-row tile, one statistics group, whole 8-column pieces, 32-byte aligned rows.  No
-      // per-element predicates; column statistics accumulate in shared memory for the whole kernel (flushed once at the
-      // end); the next chunk's accumulator (tcgen05.ld) and per-element operand are in flight while this one is computed.
-      if (single_group && (int64_t)(m_blk + 1) * BM <= g.M && (ncols & 7) == 0 && p.vec8 && (!pre_src || p.vec8_in)) {
+      // ---- fast path: full 128-row tile, one statistics group.  No per-element predicates; every warp stages its
+      // [32 rows x 16 columns] result chunk in shared memory (64-byte swizzle: conflict-free 16-byte stores) and one lane
+      // hands it to the TMA unit (cp.async.bulk.tensor store: full-sector writes, no LSU work, columns beyond N clipped);
+      // column statistics accumulate in shared memory for the whole kernel (flushed once at the end); the next chunk's
+      // accumulator (tcgen05.ld) and per-element operand are in flight while this one is computed.
+      if (p.tma_out && single_group && (int64_t)(m_blk + 1) * BM <= g.M && (!pre_src || ((ncols & 7) == 0 && p.vec8_in))) {
         const int64_t row_off = m * (int64_t)g.N + n_base;
-        float *outp = g.out + row_off;
-        float *out2p = (MODE == EPI_GELU_SQ) ? g.out2 + row_off : nullptr;
         const float *prep = pre_src ? pre_src + row_off : nullptr;
+        const uint32_t sbuf = smem_u32(stage_out) + (uint32_t)(warp - 2) * out_arrays(MODE) * kStageOutBytes;
+        const uint32_t srow = sbuf + (uint32_t)lane * 64u, sx = (uint32_t)(lane >> 1) & 3u;
+        const int row0 = m_blk * BM + q * 32;
         auto load_pre = [&](int c0, float4 *dst) {
           if (prep) {
             ld_global_v8(prep + c0, dst[0], dst[1]);
@@ -376,58 +411,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (c0 < ncols) load_pre(c0, pre);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-        if (c0 < ncols) tmem_ld16_issue(taddr + c0, vr);
+        if (c0 < ncols && !(p.dbg & 8)) tmem_ld16_issue(taddr + c0, vr);
         for (; c0 < ncols; c0 += 16 * kParts) {
           const int cn = c0 + 16 * kParts;
           float v[16];
           float4 cur[4];
-          tmem_ld_wait16(vr);
+          if (!(p.dbg & 8)) tmem_ld_wait16(vr);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) cur[j] = pre[j];
-          if (cn < ncols) { tmem_ld16_issue(taddr + cn, vr); load_pre(cn, pre); }
+          if (cn < ncols) {
+            if (!(p.dbg & 8)) tmem_ld16_issue(taddr + cn, vr);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            load_pre(cn, pre);
+          }
           float s1[16], s2[16];
-          const bool two = c0 + 8 < ncols;   // warp uniform
+          float4 o[4], o2[4];
 #pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            if (h8 == 1 && !two) {
-#pragma unroll
-              for (int j = 8; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-              break;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int j = q4 * 4;
+            const float4 acc = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            const float4 pv = cur[q4];
+            const float4 bv = *reinterpret_cast<const float4 *>(vec_bias + c0 + j);
+            float4 r, r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == EPI_STORE) {
+              r = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
+            } else if (MODE == EPI_GELU_SQ) {
+              r = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
+              r2 = (p.dbg & 2) ? r : make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
+              s1[j] = r2.x * r2.x; s1[j + 1] = r2.y * r2.y; s1[j + 2] = r2.z * r2.z; s1[j + 3] = r2.w * r2.w;
+            } else if (MODE == EPI_DG) {
+              r = acc;
+              s1[j] = acc.x * pv.x; s1[j + 1] = acc.y * pv.y; s1[j + 2] = acc.z * pv.z; s1[j + 3] = acc.w * pv.w;
+              s2[j] = acc.x; s2[j + 1] = acc.y; s2[j + 2] = acc.z; s2[j + 3] = acc.w;
+            } else {  // EPI_DH_GELU
+              const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j);
+              float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
+              gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
+              r.x = fmaf(kgv.x, hx, acc.x) * dx_;
+              r.y = fmaf(kgv.y, hy, acc.y) * dy_;
+              r.z = fmaf(kgv.z, hz, acc.z) * dz_;
+              r.w = fmaf(kgv.w, hw, acc.w) * dw_;
+              s2[j] = r.x; s2[j + 1] = r.y; s2[j + 2] = r.z; s2[j + 3] = r.w;
             }
-            float4 o[2], o2[2];
+            o[q4] = r; o2[q4] = r2;
+          }
+          if (!(p.dbg & 4)) {
+            if (lane == 0) bulk_wait_read0();   // the previous chunk's TMA store has finished reading the staging buffer
+            __syncwarp();
 #pragma unroll
-            for (int q4 = 0; q4 < 2; ++q4) {
-              const int j = h8 * 8 + q4 * 4;
-              const float4 acc = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              const float4 pv = cur[h8 * 2 + q4];
-              const float4 bv = *reinterpret_cast<const float4 *>(vec_bias + c0 + j);
-              float4 r, r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (MODE == EPI_STORE) {
-                r = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
-              } else if (MODE == EPI_GELU_SQ) {
-                r = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
-                r2 = make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
-                s1[j] = r2.x * r2.x; s1[j + 1] = r2.y * r2.y; s1[j + 2] = r2.z * r2.z; s1[j + 3] = r2.w * r2.w;
-              } else if (MODE == EPI_DG) {
-                r = acc;
-                s1[j] = acc.x * pv.x; s1[j + 1] = acc.y * pv.y; s1[j + 2] = acc.z * pv.z; s1[j + 3] = acc.w * pv.w;
-                s2[j] = acc.x; s2[j + 1] = acc.y; s2[j + 2] = acc.z; s2[j + 3] = acc.w;
-              } else {  // EPI_DH_GELU
-                const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j);
-                float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
-                gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
-                r.x = fmaf(kgv.x, hx, acc.x) * dx_;
-                r.y = fmaf(kgv.y, hy, acc.y) * dy_;
-                r.z = fmaf(kgv.z, hz, acc.z) * dz_;
-                r.w = fmaf(kgv.w, hw, acc.w) * dw_;
-                s2[j] = r.x; s2[j + 1] = r.y; s2[j + 2] = r.z; s2[j + 3] = r.w;
-              }
-              o[q4] = r; o2[q4] = r2;
+            for (int q4 = 0; q4 < 4; ++q4) {
+              sts_v4(srow + (((uint32_t)q4 ^ sx) << 4), o[q4]);
+              if (MODE == EPI_GELU_SQ) sts_v4(srow + kStageOutBytes + (((uint32_t)q4 ^ sx) << 4), o2[q4]);
             }
-            st_global_v8(outp + c0 + h8 * 8, o[0], o[1]);
-            if (MODE == EPI_GELU_SQ) st_global_v8(out2p + c0 + h8 * 8, o2[0], o2[1]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_out, sbuf, n_base + c0, row0);
+              if (MODE == EPI_GELU_SQ) tma_store_2d(&map_out2, sbuf + kStageOutBytes, n_base + c0, row0);
+              bulk_commit();
+            }
+          }
+          if (p.dbg & 1) {
+            if (s1[0] + s1[5] + s1[10] + s1[15] + s2[3] == 123.456f) atomicAdd(&statacc1[n_base + c0 + lane], s1[7]);
+            continue;
           }
           if (MODE == EPI_GELU_SQ || MODE == EPI_DG) {
             const float t = warp_colsum16(s1, lane);
@@ -568,6 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
     }
+    if (lane == 0) bulk_wait0();   // this warp's TMA stores have landed
     if (MODE != EPI_STORE) {   // fast-path statistics: one global atomic per column per CTA
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       for (int i = et; i < g.N; i += kEpiThreads) {
@@ -577,7 +627,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (SPLIT) {
     // ================================================================ A splitter (4 warps): hi in place, lo next to it
-    const int stid = threadIdx.x - kThreadsNoSplit;   // 0..127
+    const int stid = threadIdx.x - kThreadsNoSplit;   // 0..kSplitThreads-1
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -585,16 +635,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&full_bar[stage], phase);
         float4 *A = reinterpret_cast<float4 *>(smem + (size_t)stage * stage_bytes);
         float4 *Alo = A + a_bytes / 16;
+        if (!(p.dbg & 64))
 #pragma unroll
-        for (int i = 0; i < (int)(a_bytes / 16) / 128; ++i) {
-          const float4 x = A[i * 128 + stid];
+        for (int i = 0; i < (int)(a_bytes / 16) / (kSplitThreads > 0 ? kSplitThreads : 1); ++i) {
+          const float4 x = A[i * kSplitThreads + stid];
           float4 hi, lo;
           hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
           hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
           hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); lo.z = x.z - hi.z;
           hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); lo.w = x.w - hi.w;
-          A[i * 128 + stid] = hi;
-          Alo[i * 128 + stid] = lo;
+          A[i * kSplitThreads + stid] = hi;
+          Alo[i * kSplitThreads + stid] = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
         __syncwarp();
@@ -642,16 +693,30 @@ inline bool make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t c
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows, cols] fp32 row-major, box = [32 rows, 16 floats] with 64-byte swizzle: the epilogue's TMA-store chunk
+inline bool make_map_out(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {16, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct MapCache {
   std::mutex mu;
   std::map<std::tuple<const void *, int64_t, int64_t, int>, CUtensorMap> maps;
+  // box_rows > 0: operand map (K-major, 128-byte swizzle, box [box_rows x 32]); box_rows == -1: output map
   bool get(CUtensorMap *out, const float *ptr, int64_t rows, int64_t cols, int box_rows) {
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_tuple((const void *)ptr, rows, cols, box_rows);
     auto it = maps.find(key);
     if (it == maps.end()) {
       CUtensorMap m;
-      if (!make_map(&m, ptr, rows, cols, box_rows)) return false;
+      if (box_rows == -1 ? !make_map_out(&m, ptr, rows, cols) : !make_map(&m, ptr, rows, cols, box_rows)) return false;
       it = maps.emplace(key, m).first;
     }
     *out = it->second;
@@ -891,21 +956,25 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   using namespace tc;
   TcParams p{};
   p.g = a;
-  p.stages = SPLIT ? 3 : 4;
-  auto smem_for = [&](int bn) {
+  auto smem_for = [&](int bn, int stages) {
     const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)bn * BK * 4);
     const int num_n = cdiv(a.N, bn);
-    return 1024 + (size_t)p.stages * stage_bytes + 256 + (size_t)(5 * bn + 4 * num_n * bn) * 4;
+    return 1024 + (size_t)stages * stage_bytes + (size_t)epi_warps(MODE) * out_arrays(MODE) * kStageOutBytes + 256 +
+           (size_t)(5 * bn + (MODE == EPI_STORE ? 2 : 4) * num_n * bn) * 4;
   };
-  // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget, else a ragged tail
+  // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget with a 2-stage ring,
+  // else a ragged tail; then as many ring stages as still fit
   int bn = 0;
   const int cap = a.N <= 256 ? ((a.N + 15) / 16) * 16 : 256;
   for (int c = cap; c >= 64 && !bn; c -= 16)
-    if ((a.N % c == 0 || c >= a.N) && smem_for(c) <= 226 * 1024) bn = c;
+    if ((a.N % c == 0 || c >= a.N) && smem_for(c, 2) <= 226 * 1024) bn = c;
   for (int c = cap; c >= 16 && !bn; c -= 16)
-    if (smem_for(c) <= 226 * 1024) bn = c;
+    if (smem_for(c, 2) <= 226 * 1024) bn = c;
+  { const char *e = getenv("MPMAE_TC_BN"); if (e && atoi(e) > 0 && atoi(e) % 16 == 0 && smem_for(atoi(e), 2) <= 226 * 1024) bn = atoi(e); }
   if (!bn) return cudaErrorInvalidConfiguration;
   p.bn = bn;
+  p.stages = 2;
+  while (p.stages < STAGES && smem_for(bn, p.stages + 1) <= 226 * 1024) ++p.stages;
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
   p.num_k = cdiv(a.K, BK);
@@ -914,11 +983,16 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   uint32_t cols = 32;
   while (cols < (uint32_t)(ACC_STAGES * p.bn)) cols <<= 1;
   p.tmem_cols = cols;
-  CUtensorMap ma, mb, mbl;
+  { const char *e = getenv("MPMAE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  CUtensorMap ma, mb, mbl, mo, mo2;
   if (!map_cache().get(&ma, a.A, a.M, a.K, BM) || !map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
   mbl = mb;
   if (SPLIT && !map_cache().get(&mbl, a.Bw_lo, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
-  const size_t smem = smem_for(bn);
+  p.tma_out = map_cache().get(&mo, a.out, a.M, a.N, -1) ? 1 : 0;
+  mo2 = mo;
+  if (MODE == EPI_GELU_SQ && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
+  if (!p.tma_out) mo = mo2 = ma;
+  const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -927,7 +1001,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   }
   int grid = p.num_m * p.num_n;
   if (grid > 148) grid = 148;
-  gemm_tc_kernel<MODE, SPLIT><<<grid, SPLIT ? kThreadsSplit : kThreadsNoSplit, smem, st>>>(ma, mb, mbl, p);
+  gemm_tc_kernel<MODE, SPLIT><<<grid, tc_threads(MODE, SPLIT), smem, st>>>(ma, mb, mbl, mo, mo2, p);
   return cudaGetLastError();
 }
 
