@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) {
 }
 
 // weight gradient on the 7x7 maps: thread per channel, x[49] and dW[49] in registers, persistent over samples
-__global__ void __launch_bounds__(128) dwconv_grid7_wgrad_kernel(DwWgradArgs p) {
+__global__ void __launch_bounds__(128, 2) dwconv_grid7_wgrad_kernel(DwWgradArgs p) {
   constexpr int G = 7, L = 49;
   __shared__ int slot_s[L];
   const int C = p.C, V = p.geo.V;
@@ -300,11 +300,12 @@ __global__ void __launch_bounds__(128) dwconv_grid7_wgrad_kernel(DwWgradArgs p) 
     __syncthreads();
     if (!active) continue;
     const int64_t row0 = (int64_t)n * V;
-    float x[L];
+    float x[L], dreg[L];   // all 98 loads are issued before the first FMA needs one
 #pragma unroll
     for (int i = 0; i < L; ++i) {
       const int s = slot_s[i];
       x[i] = s >= 0 ? __ldg(p.x + (row0 + s) * C + c) : 0.f;
+      dreg[i] = s >= 0 ? __ldg(p.du + (row0 + s) * C + c) : 0.f;
     }
 #pragma unroll
     for (int oy = 0; oy < G; ++oy)
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(128) dwconv_grid7_wgrad_kernel(DwWgradArgs p) 
       for (int ox = 0; ox < G; ++ox) {
         const int s = slot_s[oy * G + ox];
         if (s >= 0) {
-          const float d = __ldg(p.du + (row0 + s) * C + c);
+          const float d = dreg[oy * G + ox];
           db += d;
 #pragma unroll
           for (int kh = 0; kh < 7; ++kh)

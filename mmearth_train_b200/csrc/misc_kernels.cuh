@@ -199,29 +199,102 @@ struct FoldArgs {
   // 3xTF32: when set, Wf / WfT receive the TF32-representable high part and these the remainder (w - hi)
   float *Wf_lo;
   float *WfT_lo;
+  // fused batch-global GRN statistic (sparse blocks): when gsq is set the K-axis scale is computed here,
+  //   s[k] = 1 + gamma[k] * sqrt(gsq[k]) / (mean_k sqrt(gsq) + eps),  and nx / scale / denom are written for the backward
+  const float *gsq, *gamma;
+  float *nx_out, *scale_out, *denom_out;
+  float grn_eps;
 };
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__global__ void fold_kernel(FoldArgs p) {
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= p.N) return;
-  const int lane = threadIdx.x & 31;
-  const float sn = p.scale_n ? p.scale_n[n] : 1.f;
-  float acc = 0.f;
-  for (int k = lane; k < p.K; k += 32) {
-    const float w = p.W[n * p.s_n + k * p.s_k];
-    const int j = k % p.SL;
-    const float wf = w * (p.scale_k ? p.scale_k[j] : 1.f) * sn;
-    const float hi = tf32_hi(wf);
-    if (p.Wf) p.Wf[(int64_t)n * p.K + k] = p.Wf_lo ? hi : wf;
-    if (p.Wf_lo) p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
-    if (p.WfT) p.WfT[(int64_t)k * p.N + n] = p.WfT_lo ? hi : wf;
-    if (p.WfT_lo) p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
-    if (p.shift_k) acc = fmaf(w, p.shift_k[j], acc);
+// 32 x 32 tiles through shared memory: the source is read along its contiguous axis and both orientations (Wf [N, K],
+// WfT [K, N]) leave with coalesced stores.  grid = (K tiles, N tiles), block = (32, 8).  The folded bias of a row block is
+// produced by the CTAs of the first K tile.
+__global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8];
+  __shared__ float sks[32];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  if (p.gsq) {   // every CTA recomputes the (tiny) GRN denominator; K = SL here
+    float s = 0.f;
+    for (int d = tid; d < p.K; d += 256) s += sqrtf(p.gsq[d]);
+    s = warp_sum(s);
+    if (tx == 0) red[ty] = s;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float den = t / (float)p.K + p.grn_eps;
+    if (tid < 32) {
+      const int k = k0 + tid;
+      float sk = 1.f;
+      if (k < p.K) {
+        const float nx = sqrtf(p.gsq[k]) / den;
+        sk = 1.f + p.gamma[k] * nx;
+        if (blockIdx.y == 0) { p.nx_out[k] = nx; p.scale_out[k] = sk; }
+      }
+      sks[tid] = sk;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) p.denom_out[0] = den;
+  } else if (tid < 32) {
+    const int k = k0 + tid;
+    sks[tid] = (p.scale_k && k < p.K) ? p.scale_k[k % p.SL] : 1.f;
   }
-  if (p.bf) {
-    acc = warp_sum(acc);
-    if (lane == 0) p.bf[n] = (p.bias ? p.bias[n] : 0.f) + acc;
+  // source tile -> tile[n][k]
+  if (p.s_k == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i, k = k0 + tx;
+      tile[ty + 8 * i][tx] = (n < p.N && k < p.K) ? p.W[n * p.s_n + k] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + tx, k = k0 + ty + 8 * i;
+      tile[tx][ty + 8 * i] = (n < p.N && k < p.K) ? p.W[n * p.s_n + k * p.s_k] : 0.f;
+    }
   }
+  __syncthreads();
+  const bool split = p.Wf_lo != nullptr || p.WfT_lo != nullptr;
+  if (p.Wf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int nl = ty + 8 * i, n = n0 + nl, k = k0 + tx;
+      if (n < p.N && k < p.K) {
+        const float wf = tile[nl][tx] * sks[tx] * (p.scale_n ? p.scale_n[n] : 1.f);
+        const float hi = tf32_hi(wf);
+        p.Wf[(int64_t)n * p.K + k] = split ? hi : wf;
+        if (p.Wf_lo) p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
+      }
+    }
+  }
+  if (p.WfT) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = ty + 8 * i, k = k0 + kl, n = n0 + tx;
+      if (n < p.N && k < p.K) {
+        const float wf = tile[tx][kl] * sks[kl] * (p.scale_n ? p.scale_n[n] : 1.f);
+        const float hi = tf32_hi(wf);
+        p.WfT[(int64_t)k * p.N + n] = split ? hi : wf;
+        if (p.WfT_lo) p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
+      }
+    }
+  }
+  if (p.bf && blockIdx.x == 0) {   // bf[n] = bias[n] + sum_k W[n, k] * shift[k % SL]: warp ty owns rows ty, ty+8, ...
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i;
+      if (n >= p.N) continue;
+      float acc = 0.f;
+      if (p.shift_k)
+        for (int k = tx; k < p.K; k += 32) acc = fmaf(p.W[n * p.s_n + k * p.s_k], p.shift_k[k % p.SL], acc);
+      acc = warp_sum(acc);
+      if (tx == 0) p.bf[n] = (p.bias ? p.bias[n] : 0.f) + acc;
+    }
+  }
+}
+inline void launch_fold(const FoldArgs &a, cudaStream_t st) {
+  fold_kernel<<<dim3(cdiv(a.K, 32), cdiv(a.N, 32)), dim3(32, 8), 0, st>>>(a);
 }
 
 // Chain rule back through the fold:  given dWf [N,K] and dbf [N]
@@ -381,35 +454,92 @@ __global__ void densify_kernel(const float *__restrict__ x3, const int *__restri
   }
 }
 
-// column sums of a [R, C] matrix into out[C] (+=): bias gradients that have no GEMM to ride on
-__global__ void colsum_kernel(const float *__restrict__ x, const float *__restrict__ rs, float *__restrict__ out, int64_t R,
-                              int C) {
-  // blockDim = (32, 8): x over channels, y over rows
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  __shared__ float red[8][33];
-  float s = 0.f;
-  if (c < C)
-    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < R; r += (int64_t)gridDim.y * 8) s += x[r * C + c];
-  red[threadIdx.y][threadIdx.x] = s;
+// column sums of a [R, C] matrix into out[C] (+=): bias gradients that have no GEMM to ride on.  The matrix is read as
+// a flat float4 stream: blockDim.x = (C/4 float4 column groups of this chunk) x (rows per pass), so consecutive threads
+// read consecutive addresses whatever C is (C = 40 is 10 float4 per row), and a thread always owns the same 4 columns.
+// gridDim.y walks column chunks of 2048; gridDim.x strides row passes.
+__global__ void __launch_bounds__(512) colsum_kernel(const float *__restrict__ x, const float *__restrict__ rs,
+                                                     float *__restrict__ out, int64_t R, int C) {
+  __shared__ float4 red[512];
+  const int c4_total = C >> 2;
+  const int c4_0 = blockIdx.y * 512;
+  const int c4n = min(512, c4_total - c4_0);          // float4 groups in this chunk
+  const int rpp = blockDim.x / c4n;                   // rows per pass
+  const int tr = threadIdx.x / c4n, tc = threadIdx.x - tr * c4n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tr < rpp) {
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4_0 + tc;
+    for (int64_t r = (int64_t)blockIdx.x * rpp + tr; r < R; r += (int64_t)gridDim.x * rpp) {
+      const float4 v = __ldg(xp + r * c4_total);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    atomicAdd(&out[c], rs ? rs[c] * t : t);
+  if (threadIdx.x < c4n) {
+    float4 t = red[threadIdx.x];
+    for (int i = 1; i < rpp; ++i) {
+      const float4 u = red[i * c4n + threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    const int c = (c4_0 + threadIdx.x) * 4;
+    if (rs) { t.x *= rs[c]; t.y *= rs[c + 1]; t.z *= rs[c + 2]; t.w *= rs[c + 3]; }
+    atomicAdd(&out[c], t.x); atomicAdd(&out[c + 1], t.y); atomicAdd(&out[c + 2], t.z); atomicAdd(&out[c + 3], t.w);
   }
 }
+// launch helper: C % 4 == 0, x 16-byte aligned
+inline void launch_colsum(const float *x, const float *rs, float *out, int64_t R, int C, cudaStream_t st) {
+  const int c4 = C >> 2;
+  const int chunks = cdiv(c4, 512);
+  const int c4n = c4 < 512 ? c4 : 512;
+  int threads = (512 / c4n) * c4n;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  const int rpp = threads / c4n > 0 ? threads / c4n : 1;
+  int64_t gx = cdiv64(R, (int64_t)rpp * 8);            // >= 8 passes per CTA
+  if (gx > 148 * 4) gx = 148 * 4;
+  if (gx < 1) gx = 1;
+  colsum_kernel<<<dim3((unsigned)gx, chunks), threads, 0, st>>>(x, rs, out, R, C);
+}
 
-// out[b, k] = sum_n A[b, n] * cs[n] * W[n, k]   (image-head dX: nimg is ragged, e.g. 878, so this tiny
-// product does not go through the tiled GEMMs).  One thread per output, coalesced over k.
-__global__ void small_gemm_nt_kernel(const float *__restrict__ A, const float *__restrict__ W, const float *__restrict__ cs,
-                                     float *__restrict__ out, int Brows, int Kout, int Nred) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)Brows * Kout) return;
-  const int b = (int)(t / Kout), k = (int)(t - (int64_t)b * Kout);
-  float acc = 0.f;
-  for (int n = 0; n < Nred; ++n) acc = fmaf(A[(int64_t)b * Nred + n] * cs[n], W[(int64_t)n * Kout + k], acc);
-  out[t] = acc;
+// out[b, k] = sum_n A[b, n] * cs[n] * W[n, k]   (image-head dX: nimg is ragged, e.g. 878, so this product does not go
+// through the tensor-core path).  32 x 64 output tile per CTA, shared-memory staged operands, 2 x 4 outputs per thread.
+__global__ void __launch_bounds__(256) small_gemm_nt_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                            const float *__restrict__ cs, float *__restrict__ out, int Brows,
+                                                            int Kout, int Nred) {
+  __shared__ float As[32][33];   // [n][b]
+  __shared__ float Ws[32][64];   // [n][k]
+  const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: 4 columns, ty: 2 rows
+  float acc[2][4] = {};
+  for (int n0 = 0; n0 < Nred; n0 += 32) {
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+      const int b = i >> 5, n = i & 31;
+      As[n][b] = (b0 + b < Brows && n0 + n < Nred) ? A[(int64_t)(b0 + b) * Nred + n0 + n] * cs[n0 + n] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int n = i >> 6, k = i & 63;
+      Ws[n][k] = (n0 + n < Nred && k0 + k < Kout) ? W[(int64_t)(n0 + n) * Kout + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < 32; ++n) {
+      const float a0 = As[n][ty * 2], a1 = As[n][ty * 2 + 1];
+      const float4 w = *reinterpret_cast<const float4 *>(&Ws[n][tx * 4]);
+      acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + ty * 2 + i, k = k0 + tx * 4 + j;
+      if (b < Brows && k < Kout) out[(int64_t)b * Kout + k] = acc[i][j];
+    }
 }
 
 }  // namespace mpmae

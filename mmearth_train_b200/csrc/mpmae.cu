@@ -465,9 +465,7 @@ void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
     c.check(launch_gemm_wgrad_tc(a, a.exact != 0 && c.pl->cfg.gemm_backend == 1, c.st), what);
     if (a.db && c.ok()) {   // bias gradient = column sums of X (the tensor-core kernel produces dW only)
       c.acct(4.0 * (double)a.R * a.N, 0);
-      int gy = (int)(a.R / 256);
-      gy = gy < 1 ? 1 : (gy > 592 ? 592 : gy);
-      colsum_kernel<<<dim3(cdiv(a.N, 32), gy), dim3(32, 8), 0, c.st>>>(a.X, a.rs, a.db, a.R, a.N);
+      launch_colsum(a.X, a.rs, a.db, a.R, a.N, c.st);
       c.post("colsum");
     }
   } else {
@@ -480,7 +478,7 @@ void fold(Ctx &c, FoldArgs a, const char *what) {
     if (a.Wf == c.w(c.pl->o_wf)) a.Wf_lo = c.w(c.pl->o_wf_lo);
     if (a.WfT == c.w(c.pl->o_wft)) a.WfT_lo = c.w(c.pl->o_wft_lo);
   }
-  fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
+  launch_fold(a, c.st);
   c.post(what);
 }
 // fold a weight into its slot: both orientations (+ hi/lo split for 3xTF32) and the folded bias in one launch
@@ -492,7 +490,7 @@ void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what) {
   a.WfT_lo = split ? c.w(s.wft_lo) : nullptr;
   if (a.bias || a.shift_k) a.bf = c.w(s.bf);
   a.N = s.N; a.K = s.K;
-  fold_kernel<<<cdiv(a.N, 8), 256, 0, c.st>>>(a);
+  launch_fold(a, c.st);
   c.post(what);
 }
 // point a GEMM at a slot: out = A . Wf^T (transposed = false) or A . Wf (transposed = true)
@@ -540,9 +538,9 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   g1.M = R; g1.N = D4; g1.K = C; g1.group_rows = group_rows;
   gemm<EPI_GELU_SQ>(c, g1, "pw1");
 
-  if (c.ok()) {
+  if (dense && c.ok()) {   // per-sample statistic; the batch-global one of the sparse blocks is fused into fold_pw2
     grn_scale_kernel<<<groups, 256, 0, c.st>>>(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom),
-                                               D4, dense ? 1e-4f : 1e-6f);
+                                               D4, 1e-4f);
     c.post("grn_scale");
   }
   GemmArgs g2{};
@@ -560,7 +558,9 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
     g2.A = c.w(bw.g); g2.bias = c.p(bp.b2);
   } else {
     // GRN is affine in h per channel: fold s = 1 + gamma*Nx into W2's columns and beta into the bias
-    f2.scale_k = c.w(bw.scale); f2.shift_k = c.p(bp.beta); f2.bias = c.p(bp.b2);
+    f2.shift_k = c.p(bp.beta); f2.bias = c.p(bp.b2);
+    f2.gsq = c.w(bw.gsq); f2.gamma = c.p(bp.gamma); f2.nx_out = c.w(bw.nx); f2.scale_out = c.w(bw.scale);
+    f2.denom_out = c.w(bw.denom); f2.grn_eps = 1e-6f;
     fold_slot(c, f2, bw.s2, "fold_pw2");
     g2.A = c.w(bw.h); g2.bias = c.w(bw.s2.bf);
   }
@@ -596,9 +596,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
       grn_gelu_bwd_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(da, c.w(bw.h), c.w(bw.a), c.w(bw.scale), kg, da, R, D4,
                                                                   group_rows);
       c.post("grn_gelu_bwd");
-      int gy = (int)(R / 256);
-      gy = gy < 1 ? 1 : (gy > 592 ? 592 : gy);
-      colsum_kernel<<<dim3(cdiv(D4, 32), gy), dim3(32, 8), 0, c.st>>>(da, nullptr, dbf1, R, D4);   // db1f = sum da
+      launch_colsum(da, nullptr, dbf1, R, D4, c.st);   // db1f = sum da
       c.post("colsum");
     }
   } else {
@@ -997,7 +995,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   }
   if (pl->nimg > 0) {
     if (c.ok()) {
-      small_gemm_nt_kernel<<<(unsigned)cdiv64((int64_t)geo.B * D, 256), 256, 0, c.st>>>(
+      small_gemm_nt_kernel<<<dim3(cdiv(D, 64), cdiv(geo.B, 32)), 256, 0, c.st>>>(
           c.w(pl->o_dimg), c.p(pl->imgw), c.w(pl->o_cs_img), c.w(pl->o_dpooled), geo.B, D, pl->nimg);
       c.post("d_pooled");
     }
@@ -1173,7 +1171,7 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
       if (!scratch) return fail(MPMAE_ERR_INVALID, "backend 1 needs scratch of 2*N*K floats");
       FoldArgs f{};
       f.W = b; f.s_n = K; f.s_k = 1; f.Wf = scratch; f.Wf_lo = scratch + (int64_t)N * K; f.N = N; f.K = K; f.SL = K;
-      fold_kernel<<<cdiv(N, 8), 256, 0, st>>>(f);
+      launch_fold(f, st);
       g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
     }
     e = launch_gemm_rows_tc<EPI_STORE>(g, backend, st);
@@ -1199,7 +1197,7 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
     FoldArgs f{};
     f.W = d->b; f.s_n = d->K; f.s_k = 1; f.Wf = d->scratch; f.Wf_lo = d->scratch + (int64_t)d->N * d->K; f.N = d->N;
     f.K = d->K; f.SL = d->K;
-    fold_kernel<<<cdiv(d->N, 8), 256, 0, st>>>(f);
+    launch_fold(f, st);
     g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
   }
   cudaError_t e = cudaSuccess;
