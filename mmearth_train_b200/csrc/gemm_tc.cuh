@@ -211,9 +211,12 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
 // operand-splitter warps.  GELU / statistics epilogues are latency bound and get 16 warps (4 per scheduler) with 2 splitter
 // warps (their K is the narrow side); the plain store epilogue is light and its K is the wide side, so it runs 8 + 8.
 // 18-20 warps = 5 per scheduler keeps 96 registers per thread.
-__host__ __device__ constexpr int epi_warps(int mode) { return mode == EPI_STORE ? 8 : 16; }
-__host__ __device__ constexpr int split_warps(int mode, bool split) { return !split ? 0 : (mode == EPI_STORE ? 8 : 2); }
-__host__ __device__ constexpr int tc_threads(int mode, bool split) { return 64 + 32 * epi_warps(mode) + 32 * split_warps(mode, split); }
+// WIDE (K >= 256: the operand stream dominates, e.g. the decoder block) also runs 8 + 8.
+__host__ __device__ constexpr int epi_warps(int mode, bool wide) { return (mode == EPI_STORE || wide) ? 8 : 16; }
+__host__ __device__ constexpr int split_warps(int mode, bool split, bool wide) { return !split ? 0 : ((mode == EPI_STORE || wide) ? 8 : 2); }
+__host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide) {
+  return 64 + 32 * epi_warps(mode, wide) + 32 * split_warps(mode, split, wide);
+}
 __host__ __device__ constexpr int out_arrays(int mode) { return mode == EPI_GELU_SQ ? 2 : 1; }
 constexpr uint32_t kStageOutBytes = 32 * 16 * 4;   // one warp's [32 rows x 16 columns] output chunk
 
@@ -233,13 +236,13 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const float4 &v) {
 // SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
 // (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
 // tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
-template <int MODE, bool SPLIT>
-__global__ void __launch_bounds__(tc_threads(MODE, SPLIT), 1)
+template <int MODE, bool SPLIT, bool WIDE>
+__global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
                const __grid_constant__ CUtensorMap map_out2, const TcParams p) {
-  constexpr int kEpiWarps = epi_warps(MODE), kEpiThreads = 32 * kEpiWarps;
-  constexpr int kSplitWarps = split_warps(MODE, SPLIT), kSplitThreads = 32 * kSplitWarps;
+  constexpr int kEpiWarps = epi_warps(MODE, WIDE), kEpiThreads = 32 * kEpiWarps;
+  constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE), kSplitThreads = 32 * kSplitWarps;
   constexpr int kThreadsNoSplit = 64 + kEpiThreads;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
@@ -951,7 +954,7 @@ inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
   return tc::encode_fn() != nullptr;
 }
 
-template <int MODE, bool SPLIT>
+template <int MODE, bool SPLIT, bool WIDE>
 inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) {
   using namespace tc;
   TcParams p{};
@@ -959,7 +962,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   auto smem_for = [&](int bn, int stages) {
     const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * BK * 4 + (size_t)bn * BK * 4);
     const int num_n = cdiv(a.N, bn);
-    return 1024 + (size_t)stages * stage_bytes + (size_t)epi_warps(MODE) * out_arrays(MODE) * kStageOutBytes + 256 +
+    return 1024 + (size_t)stages * stage_bytes + (size_t)epi_warps(MODE, WIDE) * out_arrays(MODE) * kStageOutBytes + 256 +
            (size_t)(5 * bn + (MODE == EPI_STORE ? 2 : 4) * num_n * bn) * 4;
   };
   // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget with a 2-stage ring,
@@ -995,20 +998,25 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   int grid = p.num_m * p.num_n;
   if (grid > 148) grid = 148;
-  gemm_tc_kernel<MODE, SPLIT><<<grid, tc_threads(MODE, SPLIT), smem, st>>>(ma, mb, mbl, mo, mo2, p);
+  gemm_tc_kernel<MODE, SPLIT, WIDE><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, p);
   return cudaGetLastError();
 }
 
 template <int MODE>
 inline cudaError_t launch_gemm_rows_tc(const GemmArgs &a, int backend, cudaStream_t st) {
-  if (backend == 1 && a.Bw_lo) return launch_gemm_rows_tc_impl<MODE, true>(a, st);
-  return launch_gemm_rows_tc_impl<MODE, false>(a, st);
+  const bool split = backend == 1 && a.Bw_lo;
+  if (MODE == EPI_STORE) {   // WIDE only changes the roles of the statistics / GELU epilogues
+    return split ? launch_gemm_rows_tc_impl<MODE, true, true>(a, st) : launch_gemm_rows_tc_impl<MODE, false, true>(a, st);
+  }
+  const bool wide = a.K >= 256;
+  if (split) return wide ? launch_gemm_rows_tc_impl<MODE, true, true>(a, st) : launch_gemm_rows_tc_impl<MODE, true, false>(a, st);
+  return wide ? launch_gemm_rows_tc_impl<MODE, false, true>(a, st) : launch_gemm_rows_tc_impl<MODE, false, false>(a, st);
 }
 
 
