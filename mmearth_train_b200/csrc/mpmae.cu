@@ -747,6 +747,8 @@ int mpmae_plan_create(const mpmae_cfg *cfg, mpmae_plan **out) {
     if (i > 0 && c.dims[i] < c.dims[i - 1]) return fail(MPMAE_ERR_UNSUPPORTED, "dims must be non-decreasing");
   }
   if (c.dims[0] > 128) return fail(MPMAE_ERR_UNSUPPORTED, "dims[0] > 128: stem kernels hold <= 4 channels per lane");
+  if (c.in_chans < 1 || c.in_chans * (c.dims[0] / 4) > 512)
+    return fail(MPMAE_ERR_UNSUPPORTED, "in_chans * dims[0] / 4 > 512: the patch-embedding weight-gradient kernel maps one thread per (ci, 4 co)");
   auto *pl = new mpmae_plan();
   pl->cfg = c;
   pl->S = c.img_size;
@@ -862,10 +864,16 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       configured = sm;
     }
     const int tiles = (pl->Ppre / 8) * (pl->Ppre / 8);
-    initial_conv_fwd_kernel<<<geo.B * geo.V * tiles, 256, sm, c.st>>>(a);
+    initial_conv_fwd_kernel<<<geo.B * geo.V * tiles, 32 * (a.C0 / 8), sm, c.st>>>(a);
     c.post("initial_conv");
     StemArgs s = stem_args(c);
-    stem_fwd_kernel<<<(unsigned)cdiv64(s.R0, 8), 256, 0, c.st>>>(s);
+    const unsigned sg = (unsigned)cdiv64(s.R0, 8);
+    switch (cdiv(s.C0, 32)) {
+      case 1: stem_fwd_kernel<1><<<sg, 256, 0, c.st>>>(s); break;
+      case 2: stem_fwd_kernel<2><<<sg, 256, 0, c.st>>>(s); break;
+      case 3: stem_fwd_kernel<3><<<sg, 256, 0, c.st>>>(s); break;
+      default: stem_fwd_kernel<4><<<sg, 256, 0, c.st>>>(s); break;
+    }
     c.post("stem");
   }
   const float *x = c.w(pl->o_x0);
@@ -1069,7 +1077,13 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     sb.d_ln0_w = c.g(pl->ic_lnw); sb.d_ln0_b = c.g(pl->ic_lnb); sb.d_kernel = c.g(pl->st_k); sb.d_bias = c.g(pl->st_b);
     sb.d_ln1_w = c.g(pl->st_lnw); sb.d_ln1_b = c.g(pl->st_lnb);
     if (c.ok()) {
-      stem_bwd_kernel<<<148 * 4, 256, (size_t)(5 + sb.f.s2) * sb.f.C0 * 4, c.st>>>(sb);
+      const size_t ssm = (size_t)(5 + sb.f.s2) * sb.f.C0 * 4;
+      switch (cdiv(sb.f.C0, 32)) {
+        case 1: stem_bwd_kernel<1><<<148 * 8, 256, ssm, c.st>>>(sb); break;
+        case 2: stem_bwd_kernel<2><<<148 * 6, 256, ssm, c.st>>>(sb); break;
+        case 3: stem_bwd_kernel<3><<<148 * 4, 256, ssm, c.st>>>(sb); break;
+        default: stem_bwd_kernel<4><<<148 * 4, 256, ssm, c.st>>>(sb); break;
+      }
       c.post("stem_bwd");
     }
     InitConvWgradArgs iw{};
@@ -1082,7 +1096,10 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
       configured = sm;
     }
     if (c.ok()) {
-      initial_conv_wgrad_kernel<<<148 * 2, 256, sm, c.st>>>(iw);
+      const int owners = iw.f.Cin * (iw.f.C0 / 4);
+      const int parts = owners * 4 <= 512 ? 4 : (owners * 2 <= 512 ? 2 : 1);
+      const int per_sm = (owners * parts <= 256) ? 4 : 2;
+      initial_conv_wgrad_kernel<<<148 * per_sm, owners * parts, sm, c.st>>>(iw);
       c.post("initial_conv_wgrad");
     }
   }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void load_input_window(const InitConvArgs &p, int n, 
   }
 }
 
-__global__ void __launch_bounds__(256) initial_conv_fwd_kernel(InitConvArgs p) {
+__global__ void __launch_bounds__(512) initial_conv_fwd_kernel(InitConvArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int C0 = p.C0, Cin = p.Cin;
   float *xin = smem;                       // [Cin][10][10]
@@ -55,38 +55,52 @@ __global__ void __launch_bounds__(256) initial_conv_fwd_kernel(InitConvArgs p) {
   for (int i = threadIdx.x; i < 9 * Cin * C0; i += blockDim.x) wsm[i] = p.kernel[i];
   __syncthreads();
 
-  const int pix = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  // thread = (vertical pixel pair, 8 output channels); blockDim.x = 32 * (C0 / 8).  Per (ci, kw) four window loads
+  // serve 3 taps x 2 pixels and six 16-byte weight loads (warp-broadcast) feed 48 FMAs.
+  const int pp = threadIdx.x & 31, q = threadIdx.x >> 5;
   int iy, ix;
-  morton_decode(pix, iy, ix);
-  if (grp == 0) {
-    float s = 0.f;
-    for (int ci = 0; ci < Cin; ++ci) s += fabsf(xin[ci * 100 + (iy + 1) * 10 + ix + 1]);
-    if (s == 0.f) atomicAdd(&p.flags[0], 1);
+  morton_decode(2 * pp, iy, ix);          // pixels 2pp and 2pp+1 are (iy, ix) and (iy+1, ix)
+  if (q == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      s0 += fabsf(xin[ci * 100 + (iy + 1) * 10 + ix + 1]);
+      s1 += fabsf(xin[ci * 100 + (iy + 2) * 10 + ix + 1]);
+    }
+    if (s0 == 0.f) atomicAdd(&p.flags[0], 1);
+    if (s1 == 0.f) atomicAdd(&p.flags[0], 1);
   }
-  for (int q = grp; q * 8 < C0; q += 4) {
-    float acc[8];
+  {
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = p.bias[q * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = p.bias[q * 8 + j];
     for (int kw = 0; kw < 3; ++kw)
-      for (int kh = 0; kh < 3; ++kh) {
-        const float *wk = wsm + (size_t)((kh + 3 * kw) * Cin) * C0 + q * 8;
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float xv = xin[ci * 100 + (iy + kh) * 10 + ix + kw];
-          const float4 w0 = *reinterpret_cast<const float4 *>(wk + (size_t)ci * C0);
-          const float4 w1 = *reinterpret_cast<const float4 *>(wk + (size_t)ci * C0 + 4);
-          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float *xc = xin + ci * 100 + iy * 10 + ix + kw;
+        const float x0 = xc[0], x1 = xc[10], x2 = xc[20], x3 = xc[30];
+        const float xr[4] = {x0, x1, x2, x3};
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float *wk = wsm + (size_t)((kh + 3 * kw) * Cin + ci) * C0 + q * 8;
+          const float4 w0 = *reinterpret_cast<const float4 *>(wk);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wk + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] = fmaf(xr[kh], wv[j], acc[0][j]);
+            acc[1][j] = fmaf(xr[kh + 1], wv[j], acc[1][j]);
+          }
         }
       }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cbuf[pix * (C0 + 1) + q * 8 + j] = acc[j];
+    for (int j = 0; j < 8; ++j) {
+      cbuf[(2 * pp) * (C0 + 1) + q * 8 + j] = acc[0][j];
+      cbuf[(2 * pp + 1) * (C0 + 1) + q * 8 + j] = acc[1][j];
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
-  for (int px = warp; px < 64; px += 8) {
+  for (int px = warp; px < 64; px += (int)(blockDim.x >> 5)) {
     const float *cr = cbuf + px * (C0 + 1);
     float s = 0.f;
     for (int c = lane; c < C0; c += 32) s += cr[c];
@@ -106,15 +120,30 @@ struct InitConvWgradArgs {
   float *dkernel;      // [9, Cin, C0]
   float *dbias;        // [C0]
 };
-__global__ void __launch_bounds__(256) initial_conv_wgrad_kernel(InitConvWgradArgs a) {
+// Persistent CTAs; a thread owns dW[all 9 taps][one ci][4 consecutive co] (36 accumulators that live in registers for
+// the whole kernel) for one half of each tile's pixels: per pixel 9 window loads + one 16-byte dc load feed 36 FMAs.
+// Threads: Cin * (C0 / 4) owners x `parts` pixel groups (blockDim.x = owners * parts, parts in {1, 2, 4}).  One flush
+// (shared-memory atomics, then global) at the end.
+__global__ void __launch_bounds__(512) initial_conv_wgrad_kernel(InitConvWgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   const InitConvArgs &p = a.f;
   const int C0 = p.C0, Cin = p.Cin;
   float *xin = smem;                     // [Cin][100]
-  float *dcs = xin + Cin * 100;          // [64][C0]
+  float *dcs = xin + Cin * 100;          // [64][C0]   (pixel index = Z-order)
   float *dws = dcs + 64 * C0;            // [9*Cin + 1][C0]  (last row = bias)
   const int nacc = (9 * Cin + 1) * C0;
   for (int i = threadIdx.x; i < nacc; i += blockDim.x) dws[i] = 0.f;
+  const int cog = C0 >> 2, owners = Cin * cog;
+  const int parts = blockDim.x / owners, ppp = 64 / parts;   // pixels per part
+  const int half = threadIdx.x / owners, own = threadIdx.x - half * owners;
+  const bool active = half < parts;
+  const int ci = own / cog, co = (own - ci * cog) * 4;
+  float acc[9][4];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
   const int tiles = (p.Ppre / 8) * (p.Ppre / 8);
   const int64_t units = (int64_t)p.geo.B * p.geo.V * tiles;
   for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
@@ -127,24 +156,39 @@ __global__ void __launch_bounds__(256) initial_conv_wgrad_kernel(InitConvWgradAr
     __syncthreads();
     load_input_window(p, n, gy0, gx0, xin);
     const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
-    for (int i = threadIdx.x; i < 64 * C0; i += blockDim.x) dcs[i] = a.dc[row0 * C0 + i];
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nacc; idx += blockDim.x) {
-      const int kc = idx / C0, co = idx - kc * C0;
-      float acc = 0.f;
-      if (kc == 9 * Cin) {
-        for (int px = 0; px < 64; ++px) acc += dcs[px * C0 + co];
-      } else {
-        const int k = kc / Cin, ci = kc - k * Cin;
-        const int kh = k % 3, kw = k / 3;
-        for (int px = 0; px < 64; ++px) {
-          int iy, ix;
-          morton_decode(px, iy, ix);
-          acc = fmaf(xin[ci * 100 + (iy + kh) * 10 + ix + kw], dcs[px * C0 + co], acc);
-        }
-      }
-      dws[idx] += acc;
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(a.dc + row0 * C0);
+      for (int i = threadIdx.x; i < 16 * C0; i += blockDim.x) reinterpret_cast<float4 *>(dcs)[i] = __ldg(src + i);
     }
+    __syncthreads();
+    if (active) {
+      const float *xc = xin + ci * 100;
+#pragma unroll 4
+      for (int pp = 0; pp < ppp; ++pp) {
+        const int px = half * ppp + pp;
+        // Z-order decode of the pixel (row bit is the LSB of every pair)
+        const int iy = (px & 1) | ((px >> 1) & 2) | ((px >> 2) & 4), ix = ((px >> 1) & 1) | ((px >> 2) & 2) | ((px >> 3) & 4);
+        const float4 d = *reinterpret_cast<const float4 *>(dcs + px * C0 + co);
+        const float *xw = xc + iy * 10 + ix;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float xv = xw[(k % 3) * 10 + k / 3];   // k = kh + 3*kw
+          acc[k][0] = fmaf(xv, d.x, acc[k][0]); acc[k][1] = fmaf(xv, d.y, acc[k][1]);
+          acc[k][2] = fmaf(xv, d.z, acc[k][2]); acc[k][3] = fmaf(xv, d.w, acc[k][3]);
+        }
+        if (ci == 0) { accb[0] += d.x; accb[1] += d.y; accb[2] += d.z; accb[3] += d.w; }
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&dws[(k * Cin + ci) * C0 + co + j], acc[k][j]);
+    if (ci == 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&dws[9 * Cin * C0 + co + j], accb[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 9 * Cin * C0; i += blockDim.x) atomicAdd(&a.dkernel[i], dws[i]);
@@ -168,14 +212,16 @@ struct StemArgs {
 };
 constexpr int kStemMaxPerLane = 4;  // C0 <= 128
 
+// NQ = ceil(C0 / 32) channel rounds per lane (compile time: no dead rounds)
+template <int NQ>
 __global__ void stem_fwd_kernel(StemArgs p) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= p.R0) return;
   const int lane = threadIdx.x & 31, C0 = p.C0;
-  float sv[kStemMaxPerLane];
+  float sv[NQ];
   float sum = 0.f;
 #pragma unroll
-  for (int q = 0; q < kStemMaxPerLane; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = lane + 32 * q;
     sv[q] = 0.f;
     if (c < C0) {
@@ -190,11 +236,11 @@ __global__ void stem_fwd_kernel(StemArgs p) {
   const float mean = warp_sum(sum) / (float)C0;
   float var = 0.f;
 #pragma unroll
-  for (int q = 0; q < kStemMaxPerLane; ++q)
+  for (int q = 0; q < NQ; ++q)
     if (lane + 32 * q < C0) { const float d = sv[q] - mean; var += d * d; }
   const float rstd = rsqrtf(warp_sum(var) / (float)C0 + p.eps);
 #pragma unroll
-  for (int q = 0; q < kStemMaxPerLane; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int c = lane + 32 * q;
     if (c < C0) {
       const float nh = (sv[q] - mean) * rstd;
@@ -212,6 +258,7 @@ struct StemBwdArgs {
   float *d_ln0_w, *d_ln0_b, *d_kernel, *d_bias, *d_ln1_w, *d_ln1_b;
 };
 // per-lane partial column sums: [0]=d_ln1_w [1]=d_ln1_b [2]=d_bias [3]=d_ln0_w [4]=d_ln0_b [5..5+s2)=d_kernel[j]
+template <int NQ>
 __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
   extern __shared__ float red[];  // [(5 + s2)][C0]
   const StemArgs &p = a.f;
@@ -219,18 +266,18 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
   for (int i = threadIdx.x; i < nvec * C0; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float part[9][kStemMaxPerLane];
+  float part[9][NQ];
 #pragma unroll
   for (int v = 0; v < 9; ++v)
 #pragma unroll
-    for (int q = 0; q < kStemMaxPerLane; ++q) part[v][q] = 0.f;
+    for (int q = 0; q < NQ; ++q) part[v][q] = 0.f;
 
   for (int64_t r = (int64_t)blockIdx.x * nw + warp; r < p.R0; r += (int64_t)gridDim.x * nw) {
     // LN1 backward
-    float dsh[kStemMaxPerLane], nh[kStemMaxPerLane];
+    float dsh[NQ], nh[NQ];
     float s1 = 0.f, s2s = 0.f;
 #pragma unroll
-    for (int q = 0; q < kStemMaxPerLane; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int c = lane + 32 * q;
       dsh[q] = 0.f; nh[q] = 0.f;
       if (c < C0) {
@@ -244,9 +291,9 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
     }
     s1 = warp_sum(s1) / (float)C0; s2s = warp_sum(s2s) / (float)C0;
     const float rs = p.rstd_s[r];
-    float ds[kStemMaxPerLane];
+    float ds[NQ];
 #pragma unroll
-    for (int q = 0; q < kStemMaxPerLane; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       ds[q] = (lane + 32 * q < C0) ? rs * (dsh[q] - s1 - nh[q] * s2s) : 0.f;
       part[2][q] += ds[q];
     }
@@ -255,10 +302,10 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
     for (int j = 0; j < 4; ++j) {
       if (j >= s2) break;
       const int64_t rc = r * s2 + j;
-      float dch[kStemMaxPerLane], ch[kStemMaxPerLane];
+      float dch[NQ], ch[NQ];
       float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-      for (int q = 0; q < kStemMaxPerLane; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         const int c = lane + 32 * q;
         dch[q] = 0.f; ch[q] = 0.f;
         if (c < C0) {
@@ -276,7 +323,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
       t1 = warp_sum(t1) / (float)C0; t2 = warp_sum(t2) / (float)C0;
       const float rc_std = p.rstd_c[rc];
 #pragma unroll
-      for (int q = 0; q < kStemMaxPerLane; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         const int c = lane + 32 * q;
         if (c < C0) a.dc[rc * C0 + c] = rc_std * (dch[q] - t1 - ch[q] * t2);
       }
@@ -285,7 +332,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
 #pragma unroll
   for (int v = 0; v < 9; ++v)
 #pragma unroll
-    for (int q = 0; q < kStemMaxPerLane; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int c = lane + 32 * q;
       if (v < nvec && c < C0) atomicAdd(&red[v * C0 + c], part[v][q]);
     }
