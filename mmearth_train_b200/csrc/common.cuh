@@ -30,6 +30,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// (row, part) LayerNorm mapping: NP adjacent lanes (a power of two <= 32) share one row of C channels; lane `part` owns the
+// float4 columns part + NP*j, j < F4 = C / (4 NP).  Consecutive lanes touch consecutive 16-byte pieces, so global
+// accesses coalesce and shared-memory accesses are conflict free, and the row reductions are log2(NP) shuffles instead of
+// a full warp per row (C = 40 would leave most of a warp idle).
+__device__ __forceinline__ float group_sum(float v, int np) {
+  for (int o = np >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// NP for a channel count (C % 4 == 0): the largest power of two dividing C/4, at most 32
+__host__ __device__ __forceinline__ int ln_parts(int C) {
+  int c4 = C >> 2, np = 1;
+  while (np < 32 && (c4 & 1) == 0) { c4 >>= 1; np <<= 1; }
+  return np;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

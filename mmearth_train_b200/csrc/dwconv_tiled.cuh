@@ -22,6 +22,54 @@ __device__ __forceinline__ int zorder3(int py, int px) {
   return spread(py) | (spread(px) << 1);
 }
 
+// LayerNorm (no affine) of `rows` rows staged in shared memory ([rows][C]) straight to global memory with the
+// (row, part) mapping of common.cuh.  blockDim.x must be a multiple of 32.  Returns false when C is not of the form
+// 4 * NP * F4 with F4 <= 6 (the caller then runs its generic warp-per-row path).
+template <int F4>
+__device__ __forceinline__ void ln_tile_to_global_f(const float *ubuf, int rows, int C, int np, float eps, float *out,
+                                                    float *rstd_out) {
+  const int total = rows * np;
+  for (int base = 0; base < total; base += (int)blockDim.x) {
+    const int item = base + (int)threadIdx.x;
+    const bool ok = item < total;
+    const int r = ok ? item / np : 0, part = ok ? item - r * np : 0;
+    const float4 *ur = reinterpret_cast<const float4 *>(ubuf + (size_t)r * C) + part;
+    float4 v[F4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      v[j] = ok ? ur[j * np] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = group_sum(s, np) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    const float rstd = rsqrtf(group_sum(q, np) / (float)C + eps);
+    if (ok) {
+      float4 *o = reinterpret_cast<float4 *>(out + (size_t)r * C) + part;
+#pragma unroll
+      for (int j = 0; j < F4; ++j) o[j * np] = make_float4(v[j].x * rstd, v[j].y * rstd, v[j].z * rstd, v[j].w * rstd);
+      if (part == 0) rstd_out[r] = rstd;
+    }
+  }
+}
+__device__ __forceinline__ bool ln_tile_to_global(const float *ubuf, int rows, int C, float eps, float *out, float *rstd_out) {
+  const int np = ln_parts(C), f4 = (C >> 2) / np;
+  switch (f4) {
+    case 1: ln_tile_to_global_f<1>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    case 2: ln_tile_to_global_f<2>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    case 3: ln_tile_to_global_f<3>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    case 4: ln_tile_to_global_f<4>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    case 5: ln_tile_to_global_f<5>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    case 6: ln_tile_to_global_f<6>(ubuf, rows, C, np, eps, out, rstd_out); return true;
+    default: return false;
+  }
+}
+
 struct DwTiledArgs {
   DwArgs a;
   const int *vis_patch;  // [B*V] patch index of every slot (null in dense mode)
@@ -119,6 +167,7 @@ __global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
   const int64_t row0 = (int64_t)pu * (P * P);
+  if (p.do_ln && !p.resid && ln_tile_to_global(ubuf, P * P, C, p.eps, p.out + row0 * C, p.rstd + row0)) return;
   if (p.do_ln) {
     for (int o = warp; o < P * P; o += nw) {
       float *ur = ubuf + (size_t)o * C;
@@ -259,6 +308,7 @@ __global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) {
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+  if (p.do_ln && !p.resid && ln_tile_to_global(smem, V, C, p.eps, p.out + row0 * C, p.rstd + row0)) return;
   if (p.do_ln) {
     for (int o = warp; o < V; o += nw) {
       float *ur = smem + (size_t)o * C;
@@ -404,6 +454,7 @@ __global__ void __launch_bounds__(512) dwconv_s2_kernel(DwArgs p, const int *__r
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int rows = V * 4;
+  if (p.do_ln && !p.resid && ln_tile_to_global(ubuf, rows, C, p.eps, p.out + row0 * C, p.rstd + row0)) return;
   if (p.do_ln) {
     for (int o = warp; o < rows; o += nw) {
       float *ur = ubuf + (size_t)o * C;

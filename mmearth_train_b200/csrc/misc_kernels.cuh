@@ -39,8 +39,9 @@ __global__ void mask_kernel(const float *__restrict__ noise, float *__restrict__
 // ------------------------------------------------------------------------------------------------
 // Row LayerNorm without affine: xhat = (x - mean) * rstd ; the affine part is folded into the
 // weights of the GEMM that consumes xhat (fold_kernel).  eps = 1e-6 (sparse_norm_layers.py:61-77).
-__global__ void ln_rows_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat, float *__restrict__ rstd_out,
-                                   int64_t R, int C, float eps) {
+// Generic flavour (warp per row) and the (row, part) flavour of common.cuh for C = 4 * NP * F4.
+__global__ void ln_rows_fwd_generic_kernel(const float *__restrict__ x, float *__restrict__ xhat, float *__restrict__ rstd_out,
+                                           int64_t R, int C, float eps) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -54,11 +55,55 @@ __global__ void ln_rows_fwd_kernel(const float *__restrict__ x, float *__restric
   for (int c = lane; c < C; c += 32) xhat[r * C + c] = (xr[c] - mean) * rstd;
   if (lane == 0) rstd_out[r] = rstd;
 }
+template <int F4>
+__global__ void __launch_bounds__(256) ln_rows_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat,
+                                                          float *__restrict__ rstd_out, int64_t R, int C, int np, float eps) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = item / np;
+  const int part = (int)(item - r * np);
+  const bool ok = r < R;
+  const float4 *xr = reinterpret_cast<const float4 *>(x + r * C) + part;
+  float4 v[F4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < F4; ++j) {
+    v[j] = ok ? __ldg(xr + j * np) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = group_sum(s, np) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < F4; ++j) {
+    v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+    q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
+  const float rstd = rsqrtf(group_sum(q, np) / (float)C + eps);
+  if (!ok) return;
+  float4 *o = reinterpret_cast<float4 *>(xhat + r * C) + part;
+#pragma unroll
+  for (int j = 0; j < F4; ++j) o[j * np] = make_float4(v[j].x * rstd, v[j].y * rstd, v[j].z * rstd, v[j].w * rstd);
+  if (part == 0) rstd_out[r] = rstd;
+}
+inline void launch_ln_rows_fwd(const float *x, float *xhat, float *rstd, int64_t R, int C, float eps, cudaStream_t st) {
+  const int np = ln_parts(C), f4 = (C >> 2) / np;
+  const unsigned grid = (unsigned)cdiv64(R * np, 256);
+  if ((C & 3) == 0 && f4 >= 1 && f4 <= 6) {
+    switch (f4) {
+      case 1: ln_rows_fwd_kernel<1><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      case 2: ln_rows_fwd_kernel<2><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      case 3: ln_rows_fwd_kernel<3><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      case 4: ln_rows_fwd_kernel<4><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      case 5: ln_rows_fwd_kernel<5><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      default: ln_rows_fwd_kernel<6><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+    }
+  }
+  ln_rows_fwd_generic_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, st>>>(x, xhat, rstd, R, C, eps);
+}
 
 // dx = rstd * (dxhat - mean_C(dxhat) - xhat * mean_C(dxhat * xhat))  (+ add)
-__global__ void ln_rows_bwd_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
-                                   const float *__restrict__ rstd, const float *__restrict__ add,
-                                   float *__restrict__ dx, int64_t R, int C) {
+__global__ void ln_rows_bwd_generic_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
+                                           const float *__restrict__ rstd, const float *__restrict__ add,
+                                           float *__restrict__ dx, int64_t R, int C) {
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -74,6 +119,56 @@ __global__ void ln_rows_bwd_kernel(const float *__restrict__ dxhat, const float 
     if (add) v += add[r * C + c];
     dx[r * C + c] = v;
   }
+}
+template <int F4>
+__global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
+                                                          const float *__restrict__ rstd, const float *__restrict__ add,
+                                                          float *__restrict__ dx, int64_t R, int C, int np) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = item / np;
+  const int part = (int)(item - r * np);
+  const bool ok = r < R;
+  const float4 *gr = reinterpret_cast<const float4 *>(dxhat + r * C) + part;
+  const float4 *hr = reinterpret_cast<const float4 *>(xhat + r * C) + part;
+  float4 g[F4], h[F4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < F4; ++j) {
+    g[j] = ok ? __ldg(gr + j * np) : make_float4(0.f, 0.f, 0.f, 0.f);
+    h[j] = ok ? __ldg(hr + j * np) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+    s2 += g[j].x * h[j].x + g[j].y * h[j].y + g[j].z * h[j].z + g[j].w * h[j].w;
+  }
+  s1 = group_sum(s1, np) / (float)C;
+  s2 = group_sum(s2, np) / (float)C;
+  if (!ok) return;
+  const float rs = __ldg(rstd + r);
+  float4 *o = reinterpret_cast<float4 *>(dx + r * C) + part;
+  const float4 *ar = add ? reinterpret_cast<const float4 *>(add + r * C) + part : nullptr;
+#pragma unroll
+  for (int j = 0; j < F4; ++j) {
+    float4 v;
+    v.x = rs * (g[j].x - s1 - h[j].x * s2); v.y = rs * (g[j].y - s1 - h[j].y * s2);
+    v.z = rs * (g[j].z - s1 - h[j].z * s2); v.w = rs * (g[j].w - s1 - h[j].w * s2);
+    if (ar) { const float4 a4 = __ldg(ar + j * np); v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w; }
+    o[j * np] = v;
+  }
+}
+inline void launch_ln_rows_bwd(const float *dxhat, const float *xhat, const float *rstd, const float *add, float *dx,
+                               int64_t R, int C, cudaStream_t st) {
+  const int np = ln_parts(C), f4 = (C >> 2) / np;
+  const unsigned grid = (unsigned)cdiv64(R * np, 256);
+  if ((C & 3) == 0 && f4 >= 1 && f4 <= 6) {
+    switch (f4) {
+      case 1: ln_rows_bwd_kernel<1><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 2: ln_rows_bwd_kernel<2><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 3: ln_rows_bwd_kernel<3><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 4: ln_rows_bwd_kernel<4><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 5: ln_rows_bwd_kernel<5><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      default: ln_rows_bwd_kernel<6><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+    }
+  }
+  ln_rows_bwd_generic_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C);
 }
 
 // ------------------------------------------------------------------------------------------------

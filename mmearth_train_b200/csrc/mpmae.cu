@@ -638,7 +638,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   gemm<EPI_STORE>(c, gv, "dvhat");
   if (c.ok()) {
     c.acct(4.0 * (3.0 * R * C + R), 0);
-    ln_rows_bwd_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, c.st>>>(dv, c.w(bw.vhat), c.w(bw.rstd), nullptr, du, R, C);
+    launch_ln_rows_bwd(dv, c.w(bw.vhat), c.w(bw.rstd), nullptr, du, R, C, c.st);
     c.post("ln_bwd");
   }
   // depthwise: dx = flipped stencil over du + dy (residual) ; dW, db
@@ -880,8 +880,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   for (int i = 0; i < 4; ++i) {
     if (i > 0) {  // downsample: LN + 2x2 stride-2 conv == [R/4, 4Cin] x [4Cin, Cout] on Z-ordered rows
       const int Ci = dm[i - 1], Co = dm[i];
-      ln_rows_fwd_kernel<<<(unsigned)cdiv64(pl->R[i - 1], 8), 256, 0, c.st>>>(x, c.w(pl->o_ds_xhat[i - 1]),
-                                                                           c.w(pl->o_ds_rstd[i - 1]), pl->R[i - 1], Ci, 1e-6f);
+      launch_ln_rows_fwd(x, c.w(pl->o_ds_xhat[i - 1]), c.w(pl->o_ds_rstd[i - 1]), pl->R[i - 1], Ci, 1e-6f, c.st);
       c.post("ds_ln");
       FoldArgs f{};
       f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w);
@@ -1062,9 +1061,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
       g.A = cur; use_slot(c, g, pl->ds_slot[i - 1], true); g.out = dxh; g.M = pl->R[i]; g.N = 4 * Ci; g.K = Co; g.group_rows = 0x7fffffff;
       gemm<EPI_STORE>(c, g, "d_ds_in");
       if (c.ok()) {
-        ln_rows_bwd_kernel<<<(unsigned)cdiv64(pl->R[i - 1], 8), 256, 0, c.st>>>(dxh, c.w(pl->o_ds_xhat[i - 1]),
-                                                                              c.w(pl->o_ds_rstd[i - 1]), nullptr, nxt,
-                                                                              pl->R[i - 1], Ci);
+        launch_ln_rows_bwd(dxh, c.w(pl->o_ds_xhat[i - 1]), c.w(pl->o_ds_rstd[i - 1]), nullptr, nxt, pl->R[i - 1], Ci, c.st);
         c.post("ds_ln_bwd");
       }
       std::swap(cur, nxt);
