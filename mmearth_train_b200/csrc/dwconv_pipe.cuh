@@ -1,0 +1,296 @@
+// Persistent, TMA-pipelined depthwise 7x7 kernels for the patch stages (P = 8, 4).
+//
+// Same maths and register tiling as dwconv_tiled.cuh (one thread = one channel x a strip of TR output rows, 49 taps in
+// registers), but the CTA is persistent and the (P+6)^2 halo window of the NEXT patch is in flight while the current one
+// is computed: every window pixel is one contiguous row of C floats in the Z-ordered layout, so it is fetched with one
+// bulk async copy (cp.async.bulk.shared.global, completion counted on an mbarrier) -- no register staging, no per-float4
+// index arithmetic, and masked / out-of-image pixels are zero-filled with plain shared stores.  Two window buffers
+// alternate; the taps are loaded once per CTA instead of once per patch.
+//
+// Replaces MinkowskiEngine/src/depthwise_convolution_kernel.cu:27-52 (forward) and :69-122 (backward).
+#pragma once
+#include "dwconv_tiled.cuh"
+#include "gemm_tc.cuh"
+
+namespace mpmae {
+namespace pipe {
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+// Source row (or -1) of window pixel wp of the patch (n, l)
+template <int P>
+__device__ __forceinline__ int64_t window_row(const int *__restrict__ slot_of, const Geo &g, int n, int l, int wp) {
+  constexpr int W = P + 6, NBR = (3 + P - 1) / P;
+  const int wy = wp / W, wx = wp - wy * W;
+  const int ry = wy - 3 + NBR * P, rx = wx - 3 + NBR * P;   // >= 0
+  const int by = ry / P, bx = rx / P;
+  const int qy = l / g.G + by - NBR, qx = l % g.G + bx - NBR;
+  if (qy < 0 || qx < 0 || qy >= g.G || qx >= g.G) return -1;
+  const int slot = __ldg(slot_of + n * g.L + qy * g.G + qx);
+  if (slot < 0) return -1;
+  return ((int64_t)n * g.V + slot) * (P * P) + zorder3(ry - by * P, rx - bx * P);
+}
+
+// Every thread fetches its share of the window pixels of patch `pu` into `win` and arrives on `bar` (count = blockDim.x)
+template <int P, int C>
+__device__ __forceinline__ void issue_window(const float *__restrict__ x, const int *__restrict__ slot_of,
+                                             const int *__restrict__ vis_patch, const Geo &g, int pu, float *win, uint64_t *bar) {
+  constexpr int W = P + 6, NPIX = W * W;
+  constexpr uint32_t kRowBytes = C * 4;
+  const int n = pu / g.V, l = __ldg(vis_patch + pu);
+  constexpr int kMaxPer = 4;   // NPIX <= 196, blockDim.x >= 64
+  int64_t rows[kMaxPer];
+  uint32_t bytes = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int wp = (int)threadIdx.x + k * (int)blockDim.x;
+    rows[k] = -2;
+    if (wp < NPIX) {
+      rows[k] = window_row<P>(slot_of, g, n, l, wp);
+      if (rows[k] >= 0) {
+        bytes += kRowBytes;
+      } else {   // masked / out-of-image pixel: zeros, written before this thread arrives
+        float4 *d = reinterpret_cast<float4 *>(win + (size_t)wp * C);
+#pragma unroll
+        for (int j = 0; j < C / 4; ++j) d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (bytes) tc::mbar_expect_tx(bar, bytes);   // arrive (release) + expect_tx
+  else tc::mbar_arrive(bar);
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int wp = (int)threadIdx.x + k * (int)blockDim.x;
+    if (rows[k] >= 0) bulk_g2s(win + (size_t)wp * C, x + rows[k] * C, kRowBytes, bar);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward / dX
+template <int P, int TR, int C>
+__global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledArgs t, int units) {
+  constexpr int W = P + 6, TILES = P / TR, NPIX = W * W;
+  const DwArgs &p = t.a;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  float *win0 = smem, *win1 = smem + (size_t)NPIX * C;
+  float *ubuf = win1 + (size_t)NPIX * C;     // [P*P][C]
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar[0], blockDim.x);
+    tc::mbar_init(&bar[1], blockDim.x);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int pu = blockIdx.x;
+  if (pu < units) issue_window<P, C>(p.x, p.slot_of, t.vis_patch, p.geo, pu, win0, &bar[0]);
+
+  const int c = threadIdx.x % C, y0 = (threadIdx.x / C) * TR;
+  float wreg[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) {
+    const int kh = k / 7, kw = k % 7;
+    const int a = p.flip ? 6 - kh : kh, b = p.flip ? 6 - kw : kw;
+    wreg[k] = __ldg(p.w + a * p.w_skh + b * p.w_skw + c * p.w_sc);
+  }
+  const float b0 = p.bias ? __ldg(p.bias + c) : 0.f;
+
+  for (int i = 0; pu < units; pu += gridDim.x, ++i) {
+    const int b = i & 1;
+    float *win = b ? win1 : win0;
+    const int pn = pu + gridDim.x;
+    if (pn < units) issue_window<P, C>(p.x, p.slot_of, t.vis_patch, p.geo, pn, b ? win0 : win1, &bar[b ^ 1]);
+    tc::mbar_wait(&bar[b], (uint32_t)(i >> 1) & 1u);
+    {
+      float acc[TR][P];
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int ox = 0; ox < P; ++ox) acc[r][ox] = b0;
+#pragma unroll
+      for (int iy = 0; iy < TR + 6; ++iy) {
+        float in[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) in[j] = win[(size_t)((y0 + iy) * W + j) * C + c];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          const int kh = iy - r;
+          if (kh >= 0 && kh < 7) {
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+              for (int ox = 0; ox < P; ++ox) acc[r][ox] = fmaf(in[ox + kw], wreg[kh * 7 + kw], acc[r][ox]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int ox = 0; ox < P; ++ox) ubuf[(size_t)zorder3(y0 + r, ox) * C + c] = acc[r][ox];
+    }
+    __syncthreads();   // window buffer b is free again, ubuf is complete
+    const int64_t row0 = (int64_t)pu * (P * P);
+    if (p.do_ln) {
+      ln_tile_to_global(ubuf, P * P, C, p.eps, p.out + row0 * C, p.rstd + row0);
+    } else {
+      constexpr int n4 = P * P * C / 4;
+      float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+      const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+      for (int k = threadIdx.x; k < n4; k += blockDim.x) {
+        float4 v = reinterpret_cast<const float4 *>(ubuf)[k];
+        if (res) { const float4 r = __ldg(res + k); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        dst[k] = v;
+      }
+    }
+    __syncthreads();   // ubuf is free again
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[tap, c] += sum du[o, c] * x[o + off(tap), c] ; db[c] += sum du[o, c]: 49 partial sums per thread for the whole kernel
+template <int P, int TR, int C>
+__global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_wgrad_pipe_kernel(DwWgradArgs p, const int *__restrict__ vis_patch,
+                                                                             int units) {
+  constexpr int W = P + 6, TILES = P / TR, NPIX = W * W, NOUT = P * P;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  constexpr size_t kBuf = (size_t)(NPIX + NOUT) * C;   // [x window | du tile]
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar[0], blockDim.x + 1);
+    tc::mbar_init(&bar[1], blockDim.x + 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int pu, int b) {
+    float *buf = smem + (size_t)b * kBuf;
+    issue_window<P, C>(p.x, p.slot_of, vis_patch, p.geo, pu, buf, &bar[b]);
+    if (threadIdx.x == 0) {   // the patch's du rows are contiguous: one bulk copy
+      tc::mbar_expect_tx(&bar[b], NOUT * C * 4);
+      bulk_g2s(buf + (size_t)NPIX * C, p.du + (int64_t)pu * NOUT * C, NOUT * C * 4, &bar[b]);
+    }
+  };
+  int pu = blockIdx.x;
+  if (pu < units) issue(pu, 0);
+  const int c = threadIdx.x % C, y0 = (threadIdx.x / C) * TR;
+  float dw[49];
+  float db = 0.f;
+#pragma unroll
+  for (int k = 0; k < 49; ++k) dw[k] = 0.f;
+  for (int i = 0; pu < units; pu += gridDim.x, ++i) {
+    const int b = i & 1;
+    const float *win = smem + (size_t)b * kBuf;
+    const float *dus = win + (size_t)NPIX * C;
+    const int pn = pu + gridDim.x;
+    if (pn < units) issue(pn, b ^ 1);
+    tc::mbar_wait(&bar[b], (uint32_t)(i >> 1) & 1u);
+    float d[TR][P];
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+      for (int ox = 0; ox < P; ++ox) { d[r][ox] = dus[(size_t)zorder3(y0 + r, ox) * C + c]; db += d[r][ox]; }
+#pragma unroll
+    for (int iy = 0; iy < TR + 6; ++iy) {
+      float in[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) in[j] = win[(size_t)((y0 + iy) * W + j) * C + c];
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const int kh = iy - r;
+        if (kh >= 0 && kh < 7) {
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+            for (int ox = 0; ox < P; ++ox) dw[kh * 7 + kw] = fmaf(d[r][ox], in[ox + kw], dw[kh * 7 + kw]);
+        }
+      }
+    }
+    __syncthreads();   // buffer b is free again
+  }
+  // reduce the TILES strips of each channel in shared memory, then one atomic per (tap, channel) per CTA
+  float *red = smem;  // [50][C]
+  for (int k = threadIdx.x; k < 50 * C; k += blockDim.x) red[k] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 49; ++k) atomicAdd(&red[k * C + c], dw[k]);
+  atomicAdd(&red[49 * C + c], db);
+  __syncthreads();
+  for (int k = threadIdx.x; k < 49 * C; k += blockDim.x) {
+    const int tap = k / C, cc = k - tap * C;
+    const int kh = tap / 7, kw = tap - kh * 7;
+    atomicAdd(&p.dw[kh * p.w_skh + kw * p.w_skw + cc * p.w_sc], red[k]);
+  }
+  if (p.dbias)
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) atomicAdd(&p.dbias[cc], red[49 * C + cc]);
+}
+
+template <int P, int TR, int C>
+inline cudaError_t launch_patch_pipe(const DwTiledArgs &t, cudaStream_t st) {
+  constexpr int threads = C * (P / TR);
+  constexpr size_t sm = ((size_t)2 * (P + 6) * (P + 6) + P * P) * C * sizeof(float);
+  static_assert(threads % 32 == 0 && threads <= 1024 && threads >= 64, "thread mapping");
+  if (sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_pipe_kernel<P, TR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(dwconv_patch_pipe_kernel<P, TR, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = true;
+  }
+  const int units = t.a.geo.B * t.a.geo.V;
+  int per_sm = (int)((227 * 1024) / (sm + 1024));
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > units) grid = units;
+  dwconv_patch_pipe_kernel<P, TR, C><<<grid, threads, sm, st>>>(t, units);
+  return cudaGetLastError();
+}
+
+template <int P, int TR, int C>
+inline cudaError_t launch_patch_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  constexpr int threads = C * (P / TR);
+  constexpr size_t sm = (size_t)2 * ((P + 6) * (P + 6) + P * P) * C * sizeof(float);
+  static_assert(sm >= (size_t)50 * C * sizeof(float), "reduction buffer");
+  if (sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_wgrad_pipe_kernel<P, TR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(dwconv_patch_wgrad_pipe_kernel<P, TR, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = true;
+  }
+  const int units = p.geo.B * p.geo.V;
+  int per_sm = (int)((227 * 1024) / (sm + 1024));
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > units) grid = units;
+  dwconv_patch_wgrad_pipe_kernel<P, TR, C><<<grid, threads, sm, st>>>(p, vis_patch, units);
+  return cudaGetLastError();
+}
+
+}  // namespace pipe
+
+// Dispatch for the instantiated (P, C) pairs; cudaErrorInvalidConfiguration = not taken (caller falls back)
+inline cudaError_t launch_dwconv_pipe(const DwArgs &a, const int *vis_patch, cudaStream_t st) {
+  if (!vis_patch || !a.slot_of) return cudaErrorInvalidConfiguration;
+  if (a.do_ln && a.resid) return cudaErrorInvalidConfiguration;
+  DwTiledArgs t{a, vis_patch};
+  if (a.P == 8 && a.C == 40) return pipe::launch_patch_pipe<8, 2, 40>(t, st);
+  if (a.P == 8 && a.C == 96) return pipe::launch_patch_pipe<8, 2, 96>(t, st);
+  if (a.P == 4 && a.C == 80) return pipe::launch_patch_pipe<4, 2, 80>(t, st);
+  if (a.P == 4 && a.C == 192) return pipe::launch_patch_pipe<4, 2, 192>(t, st);
+  return cudaErrorInvalidConfiguration;
+}
+inline cudaError_t launch_dwconv_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  if (!vis_patch || !p.slot_of) return cudaErrorInvalidConfiguration;
+  if (p.P == 8 && p.C == 40) return pipe::launch_patch_wgrad_pipe<8, 2, 40>(p, vis_patch, st);
+  if (p.P == 8 && p.C == 96) return pipe::launch_patch_wgrad_pipe<8, 2, 96>(p, vis_patch, st);
+  if (p.P == 4 && p.C == 80) return pipe::launch_patch_wgrad_pipe<4, 2, 80>(p, vis_patch, st);
+  if (p.P == 4 && p.C == 192) return pipe::launch_patch_wgrad_pipe<4, 2, 192>(p, vis_patch, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace mpmae

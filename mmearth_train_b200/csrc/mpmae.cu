@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "dwconv.cuh"
 #include "dwconv_tiled.cuh"
+#include "dwconv_pipe.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "loss.cuh"
@@ -419,12 +420,20 @@ struct Ctx {
 
 // register-tiled depthwise kernels, generic kernels for the shapes they do not take
 cudaError_t dw_launch(const DwArgs &d, const int *vis, cudaStream_t st) {
-  cudaError_t e = launch_dwconv_tiled(d, vis, st);
+  static const bool no_pipe = getenv("MPMAE_NO_DWPIPE") != nullptr;
+  cudaError_t e = no_pipe ? cudaErrorInvalidConfiguration : launch_dwconv_pipe(d, vis, st);
+  if (e != cudaErrorInvalidConfiguration) return e;
+  (void)cudaGetLastError();
+  e = launch_dwconv_tiled(d, vis, st);
   if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_dwconv_fwd(d, st); }
   return e;
 }
 cudaError_t dw_wgrad_launch(const DwWgradArgs &d, const int *vis, cudaStream_t st) {
-  cudaError_t e = launch_dwconv_wgrad_tiled(d, vis, st);
+  static const bool no_pipe = getenv("MPMAE_NO_DWPIPE") != nullptr;
+  cudaError_t e = no_pipe ? cudaErrorInvalidConfiguration : launch_dwconv_wgrad_pipe(d, vis, st);
+  if (e != cudaErrorInvalidConfiguration) return e;
+  (void)cudaGetLastError();
+  e = launch_dwconv_wgrad_tiled(d, vis, st);
   if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_dwconv_wgrad(d, st); }
   return e;
 }
