@@ -271,6 +271,246 @@ inline cudaError_t launch_patch_wgrad_pipe(const DwWgradArgs &p, const int *vis_
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ stage with 2x2 patches
+// Per-sample processing on a zero-padded 20x20 cell grid (G = 7), 32-channel chunks, one warp per visible patch (lane =
+// channel), persistent CTAs.  The 4V visible rows of the next (sample, chunk) land in the other grid buffer through
+// 128-byte bulk async copies while this one is computed; only the cells a sample touched are re-zeroed afterwards.
+constexpr int kS2GW = 20, kS2Cells = kS2GW * kS2GW, kS2CC = 32;
+
+// Forward / dX: one CTA per sample.  The sample's 4V visible rows are contiguous in HBM, so they arrive with ONE bulk async
+// copy ([4V][C] floats); a 20x20 table maps every padded grid cell to the byte offset of its row (masked / outside cells
+// point at a zero row), so no dense grid is filled or cleared.  Warp = (32-channel chunk, patch subset): the 49 taps of a
+// lane's channel are loaded once; a window row of 8 cells costs four uniform 8-byte table loads + 8 data loads.
+__global__ void __launch_bounds__(768) dwconv_s2_pipe_kernel(DwArgs p, const int *__restrict__ vis_patch) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) uint32_t tab[kS2Cells];
+  __shared__ int vis[32];
+  const int C = p.C, V = p.geo.V, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int nchunks = C / kS2CC, rows = V * 4, n = blockIdx.x;
+  float *xs = smem;                          // [rows + 1][C], last row = zeros
+  float *ubuf = smem + (size_t)(rows + 1) * C;   // [rows][C]
+  const int64_t row0 = (int64_t)n * rows;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tc::mbar_expect_tx(&bar, (uint32_t)(rows * C * 4));
+    bulk_g2s(xs, p.x + row0 * C, (uint32_t)(rows * C * 4), &bar);
+  }
+  for (int i = tid; i < C; i += blockDim.x) xs[(size_t)rows * C + i] = 0.f;
+  for (int i = tid; i < kS2Cells; i += blockDim.x) tab[i] = (uint32_t)(rows * C * 4);
+  if (tid < V) vis[tid] = __ldg(vis_patch + n * V + tid);
+  __syncthreads();
+  if (tid < rows) {
+    const int l = vis[tid >> 2], m = tid & 3;
+    tab[((l / 7) * 2 + (m & 1) + 3) * kS2GW + (l % 7) * 2 + (m >> 1) + 3] = (uint32_t)(tid * C * 4);
+  }
+  const int chunk = warp % nchunks, pg = warp / nchunks, npg = nw / nchunks;
+  const int c = chunk * kS2CC + lane;
+  float w[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) {
+    const int kh = t / 7, kw = t % 7;
+    const int a = p.flip ? 6 - kh : kh, bb = p.flip ? 6 - kw : kw;
+    w[t] = __ldg(p.w + a * p.w_skh + bb * p.w_skw + c * p.w_sc);
+  }
+  const float b0 = p.bias ? __ldg(p.bias + c) : 0.f;
+  __syncthreads();
+  tc::mbar_wait(&bar, 0);
+  if (pg < npg) {
+    const char *xc = reinterpret_cast<const char *>(xs + c);
+    for (int slot = pg; slot < V; slot += npg) {
+      const int l = vis[slot];
+      const uint32_t *trow = tab + (l / 7) * 2 * kS2GW + (l % 7) * 2;   // window origin (8-byte aligned: even column)
+      float acc[2][2] = {{b0, b0}, {b0, b0}};
+#pragma unroll
+      for (int iy = 0; iy < 8; ++iy) {
+        float in[8];
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          const uint2 o = *reinterpret_cast<const uint2 *>(trow + iy * kS2GW + q);
+          in[q] = *reinterpret_cast<const float *>(xc + o.x);
+          in[q + 1] = *reinterpret_cast<const float *>(xc + o.y);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int kh = iy - r;
+          if (kh >= 0 && kh < 7) {
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              acc[r][0] = fmaf(in[kw], w[kh * 7 + kw], acc[r][0]);
+              acc[r][1] = fmaf(in[kw + 1], w[kh * 7 + kw], acc[r][1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) ubuf[(size_t)(slot * 4 + (r | (ox << 1))) * C + c] = acc[r][ox];
+    }
+  }
+  __syncthreads();
+  if (p.do_ln) {
+    ln_tile_to_global(ubuf, rows, C, p.eps, p.out + row0 * C, p.rstd + row0);
+  } else {
+    const int n4 = rows * C / 4;
+    float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+    const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+    for (int i = tid; i < n4; i += blockDim.x) {
+      float4 v = reinterpret_cast<const float4 *>(ubuf)[i];
+      if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+      dst[i] = v;
+    }
+  }
+}
+
+// Weight gradient: persistent CTAs over samples, warp = (32-channel chunk, patch subset) so a lane keeps its channel's 49
+// partial sums in registers for the whole kernel.  Per sample two bulk async copies (x rows, du rows), double buffered,
+// and a cell -> row-offset table computed straight from the slot table.
+__global__ void __launch_bounds__(768) dwconv_s2_wgrad_pipe_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(16) uint32_t tab[2][kS2Cells];
+  __shared__ int vis[2][32];
+  const int C = p.C, V = p.geo.V, B = p.geo.B, L = p.geo.L, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5,
+            nw = blockDim.x >> 5;
+  const int nchunks = C / kS2CC, rows = V * 4;
+  const size_t kTile = (size_t)rows * C;             // floats per [rows][C] tile
+  float *zrow = smem + 4 * kTile;                    // [x0 | du0 | x1 | du1 | zero row]
+  for (int i = tid; i < C; i += blockDim.x) zrow[i] = 0.f;
+  if (tid == 0) {
+    tc::mbar_init(&bar[0], 1);
+    tc::mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int total = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int j) {
+    const int n = (int)blockIdx.x + j * (int)gridDim.x, b = j & 1;
+    float *xs = smem + (size_t)b * 2 * kTile;
+    if (tid == 0) {
+      tc::mbar_expect_tx(&bar[b], (uint32_t)(2 * kTile * 4));
+      bulk_g2s(xs, p.x + (int64_t)n * kTile, (uint32_t)(kTile * 4), &bar[b]);
+      bulk_g2s(xs + kTile, p.du + (int64_t)n * kTile, (uint32_t)(kTile * 4), &bar[b]);
+    }
+    for (int i = tid; i < kS2Cells; i += blockDim.x) {   // byte offset of every padded grid cell's row relative to xs
+      const int gy = i / kS2GW - 3, gx = i % kS2GW - 3;
+      uint32_t off = (uint32_t)((zrow - xs) * 4);
+      if (gy >= 0 && gx >= 0 && gy < 14 && gx < 14) {
+        const int slot = __ldg(p.slot_of + n * L + (gy >> 1) * 7 + (gx >> 1));
+        if (slot >= 0) off = (uint32_t)((slot * 4 + ((gy & 1) | ((gx & 1) << 1))) * C * 4);
+      }
+      tab[b][i] = off;
+    }
+    if (tid < V) vis[b][tid] = __ldg(vis_patch + n * V + tid);
+  };
+  const int chunk = warp % nchunks, pg = warp / nchunks, npg = nw / nchunks;
+  const int c = chunk * kS2CC + lane;
+  float dw[49];
+  float db = 0.f;
+#pragma unroll
+  for (int t = 0; t < 49; ++t) dw[t] = 0.f;
+  if (total > 0) issue(0);
+  for (int j = 0; j < total; ++j) {
+    const int b = j & 1;
+    if (j + 1 < total) issue(j + 1);
+    __syncthreads();                                    // tab / vis of buffer b (written one iteration ago) are visible
+    tc::mbar_wait(&bar[b], (uint32_t)(j >> 1) & 1u);
+    if (pg < npg) {
+      const float *xs = smem + (size_t)b * 2 * kTile;
+      const char *xc = reinterpret_cast<const char *>(xs + c);
+      const float *dc = xs + kTile + c;
+      for (int slot = pg; slot < V; slot += npg) {
+        const int l = vis[b][slot];
+        const uint32_t *trow = &tab[b][(l / 7) * 2 * kS2GW + (l % 7) * 2];
+        float dd[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int ox = 0; ox < 2; ++ox) { dd[r][ox] = dc[(size_t)(slot * 4 + (r | (ox << 1))) * C]; db += dd[r][ox]; }
+#pragma unroll
+        for (int iy = 0; iy < 8; ++iy) {
+          float in[8];
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            const uint2 o = *reinterpret_cast<const uint2 *>(trow + iy * kS2GW + q);
+            in[q] = *reinterpret_cast<const float *>(xc + o.x);
+            in[q + 1] = *reinterpret_cast<const float *>(xc + o.y);
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int kh = iy - r;
+            if (kh >= 0 && kh < 7) {
+#pragma unroll
+              for (int kw = 0; kw < 7; ++kw)
+                dw[kh * 7 + kw] = fmaf(dd[r][0], in[kw], fmaf(dd[r][1], in[kw + 1], dw[kh * 7 + kw]));
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                    // buffer b (tiles, tab, vis) is free again
+  }
+  // warps with the same chunk hold partial sums of the same 32 channels: reduce in shared memory, then global atomics
+  float *red = smem;   // [50][C]
+  for (int i = tid; i < 50 * C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if (pg < npg) {
+#pragma unroll
+    for (int t = 0; t < 49; ++t) atomicAdd(&red[t * C + c], dw[t]);
+    atomicAdd(&red[49 * C + c], db);
+  }
+  __syncthreads();
+  for (int i = tid; i < 49 * C; i += blockDim.x) {
+    const int t = i / C, cc = i - t * C;
+    const int kh = t / 7, kw = t - kh * 7;
+    atomicAdd(&p.dw[kh * p.w_skh + kw * p.w_skw + cc * p.w_sc], red[i]);
+  }
+  if (p.dbias)
+    for (int cc = tid; cc < C; cc += blockDim.x) atomicAdd(&p.dbias[cc], red[49 * C + cc]);
+}
+
+inline cudaError_t launch_s2_pipe(const DwArgs &a, const int *vis_patch, cudaStream_t st) {
+  if (a.geo.G != 7 || a.P != 2 || a.C % kS2CC != 0 || a.geo.V > 32 || (a.do_ln && a.resid)) return cudaErrorInvalidConfiguration;
+  const int np = ln_parts(a.C), f4 = (a.C >> 2) / np;
+  if (a.do_ln && (f4 < 1 || f4 > 6)) return cudaErrorInvalidConfiguration;
+  const int rows = a.geo.V * 4, nchunks = a.C / kS2CC;
+  const size_t sm = (size_t)(2 * rows + 1) * a.C * sizeof(float);
+  if (sm > 222 * 1024 || nchunks > 24 || ((size_t)rows * a.C * 4) % 16 != 0) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_s2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  // two CTAs per SM (smem and registers permitting) hide each other's load phase: ~10 warps per CTA
+  int npg = (2 * sm + 4096 <= 227 * 1024) ? 10 / nchunks : 20 / nchunks;
+  if (npg < 1) npg = 1;
+  int warps = nchunks * npg;
+  if (warps * 32 < rows) warps = (rows + 31) / 32;
+  dwconv_s2_pipe_kernel<<<a.geo.B, warps * 32, sm, st>>>(a, vis_patch);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_s2_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
+  if (p.geo.G != 7 || p.P != 2 || p.C % kS2CC != 0 || p.geo.V > 32 || !p.slot_of) return cudaErrorInvalidConfiguration;
+  const int rows = p.geo.V * 4, nchunks = p.C / kS2CC;
+  const size_t sm = ((size_t)4 * rows + 1) * p.C * sizeof(float);
+  if (sm > 218 * 1024 || nchunks > 24 || ((size_t)rows * p.C * 4) % 16 != 0 || 50 > 4 * rows) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_s2_wgrad_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int npg = 20 / nchunks;
+  if (npg < 1) npg = 1;
+  const int warps = nchunks * npg;
+  const int grid = p.geo.B < 148 ? p.geo.B : 148;
+  dwconv_s2_wgrad_pipe_kernel<<<grid, warps * 32, sm, st>>>(p, vis_patch);
+  return cudaGetLastError();
+}
+
 }  // namespace pipe
 
 // Dispatch for the instantiated (P, C) pairs; cudaErrorInvalidConfiguration = not taken (caller falls back)
@@ -282,6 +522,7 @@ inline cudaError_t launch_dwconv_pipe(const DwArgs &a, const int *vis_patch, cud
   if (a.P == 8 && a.C == 96) return pipe::launch_patch_pipe<8, 2, 96>(t, st);
   if (a.P == 4 && a.C == 80) return pipe::launch_patch_pipe<4, 2, 80>(t, st);
   if (a.P == 4 && a.C == 192) return pipe::launch_patch_pipe<4, 2, 192>(t, st);
+  if (a.P == 2) return pipe::launch_s2_pipe(a, vis_patch, st);
   return cudaErrorInvalidConfiguration;
 }
 inline cudaError_t launch_dwconv_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
@@ -290,6 +531,7 @@ inline cudaError_t launch_dwconv_wgrad_pipe(const DwWgradArgs &p, const int *vis
   if (p.P == 8 && p.C == 96) return pipe::launch_patch_wgrad_pipe<8, 2, 96>(p, vis_patch, st);
   if (p.P == 4 && p.C == 80) return pipe::launch_patch_wgrad_pipe<4, 2, 80>(p, vis_patch, st);
   if (p.P == 4 && p.C == 192) return pipe::launch_patch_wgrad_pipe<4, 2, 192>(p, vis_patch, st);
+  if (p.P == 2) return pipe::launch_s2_wgrad_pipe(p, vis_patch, st);
   return cudaErrorInvalidConfiguration;
 }
 
