@@ -753,6 +753,7 @@ struct TnParams {
   int bn;            // N tile, multiple of 32, <= 256
   int num_m, num_n, splits, chunks_per_split;   // chunk = 32 rows
   int stages;
+  int vec4;          // dW 16-byte aligned and Kw % 4 == 0: vector atomics when the M side is the dW row (swap == 0)
   uint32_t tmem_cols;
 };
 
@@ -874,13 +875,23 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (mi < p.Msz) {
+          const int ni0 = n_blk * bn + c0;
+          if (!p.swap && p.vec4 && ni0 + 16 <= p.Nsz) {
+            // a lane owns 16 consecutive k of one dW row: four 16-byte vector atomics instead of 16 scalar ones
+            const float sc = p.rs ? __ldg(p.rs + mi) : 1.f;
+            float4 *dst = reinterpret_cast<float4 *>(p.dW + (int64_t)mi * p.Kw + ni0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ni = n_blk * bn + c0 + j;
-            if (ni < p.Nsz) {
-              const int n = p.swap ? ni : mi, k = p.swap ? mi : ni;
-              const float sc = p.rs ? __ldg(p.rs + n) : 1.f;
-              atomicAdd(&p.dW[(int64_t)n * p.Kw + k], sc * v[j]);
+            for (int j = 0; j < 4; ++j)
+              atomicAdd(dst + j, make_float4(sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ni = ni0 + j;
+              if (ni < p.Nsz) {
+                const int n = p.swap ? ni : mi, k = p.swap ? mi : ni;
+                const float sc = p.rs ? __ldg(p.rs + n) : 1.f;
+                atomicAdd(&p.dW[(int64_t)n * p.Kw + k], sc * v[j]);
+              }
             }
           }
         }
@@ -1051,7 +1062,12 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   p.num_n = cdiv(p.Nsz, bn);
   const int total_chunks = (int)cdiv64(a.R, 32);
   const int tiles = p.num_m * p.num_n;
-  int splits = cdiv(148 * 2, tiles);
+  // one item per CTA when the output tile is big (the epilogue's atomics dominate), two when it is small (the second
+  // item's MMAs hide the first one's epilogue)
+  const int items_target = ((int64_t)p.Msz * p.Nsz >= 32768) ? 148 : 296;
+  int splits = cdiv(items_target, tiles);
+  p.vec4 = (((uintptr_t)a.dW & 15) == 0 && a.K % 4 == 0) ? 1 : 0;
+  { const char *e = getenv("MPMAE_TN_ITEMS"); if (e && atoi(e) > 0) splits = cdiv(atoi(e), tiles); }
   const int max_splits = cdiv(total_chunks, 8);   // >= 256 rows per item
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
