@@ -254,7 +254,14 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": top[3] / top[1] / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof.update({"traffic": None, "kernel": top[0], "launches_per_step": top[1] // prof_steps,
+        traffic = None
+        try:   # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (committed capture)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if a.config == "cfg2" and top[0] in tr:
+                traffic = tr[top[0]]["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
+        roof.update({"traffic": traffic, "algorithmic_bytes_per_launch": top[3] / top[1], "kernel": top[0], "launches_per_step": top[1] // prof_steps,
                      "avg_launch_ms": top[2] / top[1], "share_of_step": top[2] / tot_ms, "peak_source": pk["src"],
                      "step_hbm_frac": (mb * 1e6 * B * K / (ms / 1e3)) / (pk["hbm"] * 1e9) / 1.0,
                      "step_tf32_frac": (gf * 1e9 * B * K / (ms / 1e3)) / (tf32_peak * 1e12),
