@@ -189,22 +189,35 @@ def main():
         opt.zero_grad(set_to_none=True)
         return loss
 
-    def step_e2e(i):
-        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % NB].items()}
-        loss = model(b, mask_ratio=0.6)[0]
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        return loss.item()                                            # D2H read of the step's result
+    from mmearth_train_b200.data import DevicePrefetcher
 
-    def timed(fn, n):
+    def host_stream(n):                                               # what a DataLoader(pin_memory=True) would yield
+        for i in range(n):
+            yield host[i % NB]
+
+    def run_e2e(n):
+        """n steps through the public API: pinned host batches in (copy stream, overlapped with the previous step),
+        model(batch) -> loss.backward() -> optimizer.step(), and the loss read back to the host every step."""
+        last = None
+        for b in DevicePrefetcher(host_stream(n), dev):
+            loss = model(b, mask_ratio=0.6)[0]
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            last = loss.item()                                        # D2H read of the step's result
+        return last
+
+    def timed(fn, n, whole=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(n):
-            fn(i)
+        if whole:
+            fn(n)
+        else:
+            for i in range(n):
+                fn(i)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -221,10 +234,9 @@ def main():
         sampler.start()
     ms = timed(step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, K)
-    loss_val = step_e2e(0)
+    run_e2e(2)
+    ms_e2e = timed(run_e2e, K, whole=True)
+    loss_val = run_e2e(1)
     flags = model.input_flags()
 
     # ---- per-kernel device times (CUDA events on the launching stream inside the library), rank 0
