@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
-    ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32)")
+    ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32, 3 tcgen05 3xBF16 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -59,7 +59,8 @@ typedef struct mpmae_cfg {
   int32_t mod_kind[MPMAE_MAX_MOD];
   int32_t mod_chans[MPMAE_MAX_MOD];    /* out_chans (classes for categorical) */
   int32_t mod_norm_pix[MPMAE_MAX_MOD]; /* per-patch target normalisation (sentinel2 && norm_pix_loss) */
-  int32_t gemm_backend;  /* 0 = fp32 SIMT tiles, 1 = tcgen05 (TF32x3, fp32-faithful), 2 = tcgen05 single-pass TF32 */
+  int32_t gemm_backend;  /* 0 = fp32 SIMT tiles, 1 = tcgen05 3xTF32 (fp32-faithful), 2 = tcgen05 single-pass TF32,
+                          * 3 = tcgen05 3xBF16 (operands split into bf16 hi + lo, |error| <= 2^-16 per product; the default) */
 } mpmae_cfg;
 
 typedef struct mpmae_plan mpmae_plan; /* opaque: parameter layout, workspace layout, launch plan */
@@ -142,7 +143,7 @@ int mpmae_backward_part_range(const mpmae_plan *plan, int32_t part, int64_t *lo,
 int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw, void *cuda_stream);
 
 /* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias).
- * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32 (needs scratch of 2*N*K floats), 2 = tcgen05 single-pass TF32 */
+ * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32, 3 = tcgen05 3xBF16 (1 and 3 need scratch of 2*N*K floats) */
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
                     int64_t M, int32_t N, int32_t K, float *scratch, void *cuda_stream);
 
@@ -151,7 +152,7 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
  *   mode 1  out = a.b^T + bias ; out2 = gelu(out) ; colsum[g, n] += out2^2           (pw1 + GELU + GRN statistic)
  *   mode 2  out = a.b^T ; colsum[g, n] += out * aux ; colsum2[n] += out              (decoder dg)
  *   mode 3  out = (a.b^T + kg[n] * gelu(aux2)) * gelu'(aux2) ; colsum2[n] += out    (GELU/GRN backward)
- * group_rows = rows per statistics group (>= M: one group).  scratch: 2*N*K floats (backend 1). */
+ * group_rows = rows per statistics group (>= M: one group).  scratch: 2*N*K floats (backends 1 and 3). */
 typedef struct mpmae_gemm_desc {
   const float *a, *b, *bias, *resid, *aux, *aux2, *kg;
   float *out, *out2, *colsum, *colsum2, *scratch;
@@ -161,7 +162,7 @@ typedef struct mpmae_gemm_desc {
 int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void *cuda_stream);
 
 /* stand-alone weight-gradient product (unit tests): dw[N,K] += x[R,N]^T . y[R,K].
- * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 */
+ * backend 0 = fp32 SIMT, 1 or 3 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 */
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
                      void *cuda_stream);
 

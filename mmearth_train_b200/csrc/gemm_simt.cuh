@@ -22,6 +22,7 @@ struct GemmArgs {
   const float *A;      // [M, K] row-major
   const float *Bw;     // [N, K] row-major ("weight [out, in]")
   const float *Bw_lo;  // optional low part of a TF32 hi/lo split of the weight (Bw then holds the high part); null = none
+  int b16;             // 3xBF16: Bw is the full fp32 weight and Bw_lo points at the packed bf16 pair (hi [N,K] | lo [N,K])
   const float *bias;   // [N] or null
   const float *resid;  // [M, N] or null (EPI_STORE)
   float *out;          // [M, N]
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n0 + r < p.N) {
         v = *reinterpret_cast<const float4 *>(p.Bw + (int64_t)(n0 + r) * p.K + k0 + kq);
-        if (p.Bw_lo) {
+        if (p.Bw_lo && !p.b16) {
           const float4 l = *reinterpret_cast<const float4 *>(p.Bw_lo + (int64_t)(n0 + r) * p.K + k0 + kq);
           v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
         }

@@ -90,6 +90,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same for bf16 operands (kind::f16: 16 elements = 32 bytes of K per instruction, twice the TF32 rate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).  cute/arch/mma_sm100_desc.hpp field layout.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -100,6 +109,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// kind::f16 with bf16 A and B, fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// fp32 -> (bf16 hi, bf16 lo) with hi + lo = x up to 2^-17 |x|; two values per 32-bit word, low half = first element
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   uint32_t r[32];
@@ -236,7 +255,11 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const float4 &v) {
 // SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
 // (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
 // tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
-template <int MODE, bool SPLIT, bool WIDE>
+// BF16 (with SPLIT) = 3xBF16: a ring stage covers 64 elements of K.  Two fp32 TMA boxes of A land in the stage and the
+// splitter warps convert them IN PLACE into a bf16 high tile and a bf16 remainder tile ([128 x 64] each, 128-byte
+// swizzle); the weight arrives pre-split as bf16 (hi, lo); D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with kind::f16 MMAs -- the
+// same stage bytes as 3xTF32 carry twice the K and the tensor pipe runs at twice the rate; |error| <= 2^-16 per product.
+template <int MODE, bool SPLIT, bool WIDE, bool BF16>
 __global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
@@ -303,10 +326,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t *sa = smem + (size_t)stage * stage_bytes;
+          if (BF16) {
+            mbar_expect_tx(&full_bar[stage], 2 * a_bytes + 2 * b_bytes);
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * 64, m_blk * BM);
+            tma_load_2d(sa + a_bytes, &map_a, &full_bar[stage], kb * 64 + 32, m_blk * BM);
+            tma_load_2d(sa + a_span, &map_b, &full_bar[stage], kb * 64, n_blk * bn);
+            tma_load_2d(sa + a_span + b_bytes, &map_b_lo, &full_bar[stage], kb * 64, n_blk * bn);
+          } else {
           mbar_expect_tx(&full_bar[stage], a_bytes + (SPLIT ? 2 : 1) * b_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(sa + a_span, &map_b, &full_bar[stage], kb * BK, n_blk * bn);
           if (SPLIT) tma_load_2d(sa + a_span + b_bytes, &map_b_lo, &full_bar[stage], kb * BK, n_blk * bn);
+          }
           if (++stage == nstage) { stage = 0; phase ^= 1; }
         }
       }
@@ -314,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(bn);
+      const uint32_t idesc = BF16 ? make_idesc_bf16(bn) : make_idesc(bn);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -327,6 +358,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_span);
+          if (BF16) {
+            const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sa + a_span + b_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+          } else {
           if (!(p.dbg & 32)) {
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes per instruction: advance the start address by 2 (x16 B)
@@ -338,6 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+          }
           }
           umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
           if (kb == p.num_k - 1) umma_commit(&tfull_bar[as]);
@@ -638,6 +679,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&full_bar[stage], phase);
         float4 *A = reinterpret_cast<float4 *>(smem + (size_t)stage * stage_bytes);
         float4 *Alo = A + a_bytes / 16;
+        if (BF16) {
+          // raw: two [128 rows x 128 B] fp32 boxes (k halves h = 0, 1); result: bf16 hi tile over box 0, lo tile over
+          // box 1.  A pass handles a band of rows: read both boxes' chunks of the band into registers, barrier among the
+          // splitter warps, write the band of both bf16 tiles (rows are independent, so bands do not interfere).
+          constexpr int kST = kSplitThreads > 0 ? kSplitThreads : 32;
+          constexpr int kPasses = 2048 / (8 * kST);              // 2 x 128 x 8 float4 in all, 8 per thread per pass
+          constexpr int kBandRows = 128 / kPasses;
+          uint8_t *base = smem + (size_t)stage * stage_bytes;
+#pragma unroll 1
+          for (int ps = 0; ps < kPasses; ++ps) {
+            float4 x[8];
+            int rr[8], cc[8], hh[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int idx = i * kST + stid;                    // 0 .. kBandRows*16-1: (h, row in band, physical chunk)
+              const int h = idx / (kBandRows * 8), rem = idx - h * (kBandRows * 8);
+              const int r = ps * kBandRows + (rem >> 3), pc = rem & 7;
+              hh[i] = h; rr[i] = r; cc[i] = pc ^ (r & 7);        // logical 16-byte chunk: k = 32 h + 4 c .. + 3
+              x[i] = *reinterpret_cast<const float4 *>(base + h * a_bytes + r * 128 + pc * 16);
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t h0, l0, h1, l1;
+              split_bf16x2(x[i].x, x[i].y, h0, l0);
+              split_bf16x2(x[i].z, x[i].w, h1, l1);
+              const int cb = hh[i] * 4 + (cc[i] >> 1);           // logical 16-byte chunk of the bf16 row
+              const uint32_t off = (uint32_t)rr[i] * 128u + (uint32_t)((cb ^ (rr[i] & 7)) << 4) + (uint32_t)(cc[i] & 1) * 8u;
+              *reinterpret_cast<uint2 *>(base + off) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(base + a_bytes + off) = make_uint2(l0, l1);
+            }
+          }
+        } else
         if (!(p.dbg & 64))
 #pragma unroll
         for (int i = 0; i < (int)(a_bytes / 16) / (kSplitThreads > 0 ? kSplitThreads : 1); ++i) {
@@ -709,17 +783,33 @@ inline bool make_map_out(CUtensorMap *map, const float *ptr, int64_t rows, int64
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows, cols] bf16 row-major, box = [box_rows, 64] with 128-byte swizzle (3xBF16 weight operand)
+inline bool make_map_bf16(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct MapCache {
   std::mutex mu;
   std::map<std::tuple<const void *, int64_t, int64_t, int>, CUtensorMap> maps;
-  // box_rows > 0: operand map (K-major, 128-byte swizzle, box [box_rows x 32]); box_rows == -1: output map
+  // box_rows > 0: fp32 operand map (K-major, 128-byte swizzle, box [box_rows x 32]); box_rows == -1: output map;
+  // box_rows <= -16: bf16 operand map with box [-box_rows x 64]
   bool get(CUtensorMap *out, const float *ptr, int64_t rows, int64_t cols, int box_rows) {
     std::lock_guard<std::mutex> lk(mu);
     auto key = std::make_tuple((const void *)ptr, rows, cols, box_rows);
     auto it = maps.find(key);
     if (it == maps.end()) {
       CUtensorMap m;
-      if (box_rows == -1 ? !make_map_out(&m, ptr, rows, cols) : !make_map(&m, ptr, rows, cols, box_rows)) return false;
+      if (box_rows <= -16 ? !make_map_bf16(&m, ptr, rows, cols, -box_rows)
+                          : (box_rows == -1 ? !make_map_out(&m, ptr, rows, cols) : !make_map(&m, ptr, rows, cols, box_rows)))
+        return false;
       it = maps.emplace(key, m).first;
     }
     *out = it->second;
@@ -958,14 +1048,14 @@ inline bool make_map_box32(CUtensorMap *map, const float *ptr, int64_t rows, int
 
 inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
   if (a.M < 1 || a.N < 8 || a.K < 8) return false;
-  if (a.K % 4 != 0 || a.N % 4 != 0) return false;
+  if (a.K % 8 != 0 || a.N % 4 != 0) return false;
   if (((uintptr_t)a.A | (uintptr_t)a.Bw | (uintptr_t)a.out) & 15) return false;
   if (mode != EPI_STORE && a.group_rows < 32) return false;
   if (a.M < 64) return false;  // a 128-row MMA tile would be mostly padding: tiny products stay on the SIMT path
   return tc::encode_fn() != nullptr;
 }
 
-template <int MODE, bool SPLIT, bool WIDE>
+template <int MODE, bool SPLIT, bool WIDE, bool BF16 = false>
 inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) {
   using namespace tc;
   TcParams p{};
@@ -991,7 +1081,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   while (p.stages < STAGES && smem_for(bn, p.stages + 1) <= 226 * 1024) ++p.stages;
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
-  p.num_k = cdiv(a.K, BK);
+  p.num_k = cdiv(a.K, BF16 ? 64 : BK);
   p.vec8 = (a.N % 8 == 0) && (((uintptr_t)a.out | (uintptr_t)a.out2) & 31) == 0;
   p.vec8_in = (a.N % 8 == 0) && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2) & 31) == 0;
   uint32_t cols = 32;
@@ -999,9 +1089,17 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   p.tmem_cols = cols;
   { const char *e = getenv("MPMAE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap ma, mb, mbl, mo, mo2;
-  if (!map_cache().get(&ma, a.A, a.M, a.K, BM) || !map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
-  mbl = mb;
-  if (SPLIT && !map_cache().get(&mbl, a.Bw_lo, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
+  if (!map_cache().get(&ma, a.A, a.M, a.K, BM)) return cudaErrorInvalidValue;
+  if (BF16) {   // Bw_lo holds the packed bf16 pair: hi [N, K] then lo [N, K]
+    const uint16_t *b16 = reinterpret_cast<const uint16_t *>(a.Bw_lo);
+    if (!map_cache().get(&mb, reinterpret_cast<const float *>(b16), a.N, a.K, -p.bn) ||
+        !map_cache().get(&mbl, reinterpret_cast<const float *>(b16 + (int64_t)a.N * a.K), a.N, a.K, -p.bn))
+      return cudaErrorInvalidValue;
+  } else {
+    if (!map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
+    mbl = mb;
+    if (SPLIT && !map_cache().get(&mbl, a.Bw_lo, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
+  }
   p.tma_out = map_cache().get(&mo, a.out, a.M, a.N, -1) ? 1 : 0;
   mo2 = mo;
   if (MODE == EPI_GELU_SQ && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
@@ -1009,25 +1107,26 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   int grid = p.num_m * p.num_n;
   if (grid > 148) grid = 148;
-  gemm_tc_kernel<MODE, SPLIT, WIDE><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, p);
+  gemm_tc_kernel<MODE, SPLIT, WIDE, BF16><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, p);
   return cudaGetLastError();
 }
 
 template <int MODE>
 inline cudaError_t launch_gemm_rows_tc(const GemmArgs &a, int backend, cudaStream_t st) {
+  const bool wide = MODE == EPI_STORE || a.K >= 256;   // WIDE only changes the roles of the statistics / GELU epilogues
+  if (backend == 3 && a.b16 && a.Bw_lo)
+    return wide ? launch_gemm_rows_tc_impl<MODE, true, true, true>(a, st)
+                : launch_gemm_rows_tc_impl<MODE, true, MODE == EPI_STORE, true>(a, st);
   const bool split = backend == 1 && a.Bw_lo;
-  if (MODE == EPI_STORE) {   // WIDE only changes the roles of the statistics / GELU epilogues
-    return split ? launch_gemm_rows_tc_impl<MODE, true, true>(a, st) : launch_gemm_rows_tc_impl<MODE, false, true>(a, st);
-  }
-  const bool wide = a.K >= 256;
-  if (split) return wide ? launch_gemm_rows_tc_impl<MODE, true, true>(a, st) : launch_gemm_rows_tc_impl<MODE, true, false>(a, st);
-  return wide ? launch_gemm_rows_tc_impl<MODE, false, true>(a, st) : launch_gemm_rows_tc_impl<MODE, false, false>(a, st);
+  if (split) return wide ? launch_gemm_rows_tc_impl<MODE, true, true>(a, st)
+                         : launch_gemm_rows_tc_impl<MODE, true, MODE == EPI_STORE>(a, st);
+  return wide ? launch_gemm_rows_tc_impl<MODE, false, true>(a, st) : launch_gemm_rows_tc_impl<MODE, false, MODE == EPI_STORE>(a, st);
 }
 
 

@@ -41,70 +41,108 @@ __device__ __forceinline__ void block_sum2(float &a, float &b, float *red) {
   a = warp_sum(x); b = warp_sum(y);
 }
 
-__global__ void __launch_bounds__(256) pixel_loss_kernel(LossArgs a) {
-  __shared__ float red[64];
+// One CTA per patch cell, ONE WARP PER PIXEL MODALITY (blockDim.x = 32 * number of pixel modalities): the modalities of
+// a cell are independent, so nothing is block-synchronised and every reduction is a warp shuffle.
+__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) pixel_loss_kernel(LossArgs a) {
   const int cell = blockIdx.x;               // n*L + l
   const int n = cell / a.L, l = cell - n * a.L;
   const int ph = l / a.G, pw = l - ph * a.G;
   const int p = a.p, p2 = p * p;
   const bool masked = a.mask[cell] != 0.f;
-  for (int mi = 0; mi < a.n_mod; ++mi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int mi = -1;
+  for (int i = 0, k = 0; i < a.n_mod; ++i)
+    if (a.mod[i].kind == MPMAE_PIXEL_CONTINUOUS || a.mod[i].kind == MPMAE_PIXEL_CATEGORICAL) {
+      if (k == warp) { mi = i; break; }
+      ++k;
+    }
+  if (mi < 0) return;
+  {
     const LossMod m = a.mod[mi];
-    if (m.kind != MPMAE_PIXEL_CONTINUOUS && m.kind != MPMAE_PIXEL_CATEGORICAL) continue;
     const int len = p2 * m.chans;
     const float *pr = a.pred_pix + (int64_t)cell * a.npix + m.col_off;
     float *dp = a.dpix + (int64_t)cell * a.npix + m.col_off;
     if (!masked) {  // visible patch: no loss, zero gradient
-      for (int j = threadIdx.x; j < len; j += blockDim.x) dp[j] = 0.f;
-      continue;
+      for (int j = lane; j < len; j += 32) dp[j] = 0.f;
+      return;
     }
     if (m.kind == MPMAE_PIXEL_CONTINUOUS) {
       const float *tg = static_cast<const float *>(m.target);
       const int c = m.chans;
+      const float *tbase = tg + ((int64_t)n * c * a.S + ph * p) * a.S + pw * p;   // + (ch*S + pi)*S + qi
+      auto target_at = [&](int j) {
+        const int q = j / c, ch = j - q * c, pi = q / p, qi = q - pi * p;
+        return nan_to_zero(tbase[((int64_t)ch * a.S + pi) * a.S + qi]);
+      };
+      constexpr int NE = 24;   // register-cached path: up to 768 elements per patch (patch 8: 64 pixels x 12 bands)
+      if (len <= 32 * NE) {
+        float tv[NE], pv[NE];
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+          const int j = lane + 32 * k;
+          tv[k] = 0.f; pv[k] = 0.f;
+          if (j < len) { tv[k] = target_at(j); pv[k] = pr[j]; }
+        }
+        float mean = 0.f, inv_std = 1.f;
+        if (m.norm_pix) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < NE; ++k) s += tv[k];
+          mean = warp_sum(s) / (float)len;
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < NE; ++k)
+            if (lane + 32 * k < len) { const float d = tv[k] - mean; v += d * d; }
+          inv_std = rsqrtf(warp_sum(v) / (float)(len - 1) + 1.0e-6f);
+        }
+        float se = 0.f, cnt = 0.f;
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+          if (lane + 32 * k < len) {
+            pv[k] -= (tv[k] - mean) * inv_std;            // d
+            const float e = pv[k] * pv[k];
+            if (e == e) { se += e; cnt += 1.f; }
+          }
+        se = warp_sum(se); cnt = warp_sum(cnt);
+        const float patch_loss = se / cnt;
+        const bool counted = (patch_loss == patch_loss) && patch_loss != 0.f;
+        if (lane == 0 && counted) { atomicAdd(&a.acc[2 * mi], patch_loss); atomicAdd(&a.acc[2 * mi + 1], 1.f); }
+        const float sc = 2.f / cnt;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+          const int j = lane + 32 * k;
+          if (j < len) dp[j] = (counted && pv[k] == pv[k]) ? pv[k] * sc : 0.f;
+        }
+        return;
+      }
       float mean = 0.f, inv_std = 1.f;
       if (m.norm_pix) {  // per-patch (t - mean) / sqrt(var_unbiased + 1e-6), fcmae.py:377-382
-        float s = 0.f, dummy = 0.f;
-        for (int j = threadIdx.x; j < len; j += blockDim.x) {
-          const int ch = j % c, q = j / c, pi = q / p, qi = q - pi * p;
-          s += nan_to_zero(tg[(((int64_t)n * c + ch) * a.S + ph * p + pi) * a.S + pw * p + qi]);
-        }
-        block_sum2(s, dummy, red);
-        mean = s / (float)len;
+        float s = 0.f;
+        for (int j = lane; j < len; j += 32) s += target_at(j);
+        mean = warp_sum(s) / (float)len;
         float v = 0.f;
-        dummy = 0.f;
-        for (int j = threadIdx.x; j < len; j += blockDim.x) {
-          const int ch = j % c, q = j / c, pi = q / p, qi = q - pi * p;
-          const float d = nan_to_zero(tg[(((int64_t)n * c + ch) * a.S + ph * p + pi) * a.S + pw * p + qi]) - mean;
-          v += d * d;
-        }
-        block_sum2(v, dummy, red);
-        inv_std = rsqrtf(v / (float)(len - 1) + 1.0e-6f);
+        for (int j = lane; j < len; j += 32) { const float d = target_at(j) - mean; v += d * d; }
+        inv_std = rsqrtf(warp_sum(v) / (float)(len - 1) + 1.0e-6f);
       }
       float se = 0.f, cnt = 0.f;
-      for (int j = threadIdx.x; j < len; j += blockDim.x) {
-        const int ch = j % c, q = j / c, pi = q / p, qi = q - pi * p;
-        float t = nan_to_zero(tg[(((int64_t)n * c + ch) * a.S + ph * p + pi) * a.S + pw * p + qi]);
-        t = (t - mean) * inv_std;
-        const float d = pr[j] - t;
+      for (int j = lane; j < len; j += 32) {
+        const float d = pr[j] - (target_at(j) - mean) * inv_std;
         const float e = d * d;
         if (e == e) { se += e; cnt += 1.f; }   // NaN squared errors are dropped (fcmae.py:385-388)
       }
-      block_sum2(se, cnt, red);
+      se = warp_sum(se); cnt = warp_sum(cnt);
       const float patch_loss = se / cnt;       // cnt == 0 -> NaN -> dropped below
       const bool counted = (patch_loss == patch_loss) && patch_loss != 0.f;
-      if (threadIdx.x == 0 && counted) { atomicAdd(&a.acc[2 * mi], patch_loss); atomicAdd(&a.acc[2 * mi + 1], 1.f); }
-      for (int j = threadIdx.x; j < len; j += blockDim.x) {
-        const int ch = j % c, q = j / c, pi = q / p, qi = q - pi * p;
-        float t = nan_to_zero(tg[(((int64_t)n * c + ch) * a.S + ph * p + pi) * a.S + pw * p + qi]);
-        t = (t - mean) * inv_std;
-        const float d = pr[j] - t;
+      if (lane == 0 && counted) { atomicAdd(&a.acc[2 * mi], patch_loss); atomicAdd(&a.acc[2 * mi + 1], 1.f); }
+      for (int j = lane; j < len; j += 32) {
+        const float d = pr[j] - (target_at(j) - mean) * inv_std;
         dp[j] = (counted && d == d) ? 2.f * d / cnt : 0.f;
       }
     } else {  // categorical pixels: logits [p2][K], int64 target, -1 ignored (fcmae.py:302-346)
       const long long *tg = static_cast<const long long *>(m.target);
       const int K = m.chans;
       float ls = 0.f, nsel = 0.f;
-      for (int q = threadIdx.x; q < p2; q += blockDim.x) {
+      for (int q = lane; q < p2; q += 32) {
         const int pi = q / p, qi = q - pi * p;
         const long long t = tg[((int64_t)n * a.S + ph * p + pi) * a.S + pw * p + qi];
         const float *lg = pr + q * K;
@@ -122,63 +160,64 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(LossArgs a) {
         nsel += 1.f;
         for (int k = 0; k < K; ++k) dl[k] = expf(lg[k] - lse) - (k == (int)t ? 1.f : 0.f);
       }
-      block_sum2(ls, nsel, red);
-      if (threadIdx.x == 0 && nsel > 0.f) { atomicAdd(&a.acc[2 * mi], ls); atomicAdd(&a.acc[2 * mi + 1], nsel); }
+      ls = warp_sum(ls); nsel = warp_sum(nsel);
+      if (lane == 0 && nsel > 0.f) { atomicAdd(&a.acc[2 * mi], ls); atomicAdd(&a.acc[2 * mi + 1], nsel); }
     }
   }
 }
 
-// image-level heads: one CTA per sample (fcmae.py:281-301)
-__global__ void __launch_bounds__(256) image_loss_kernel(LossArgs a) {
-  __shared__ float red[64];
-  __shared__ int cls_sh;
-  const int n = blockIdx.x;
-  for (int mi = 0; mi < a.n_mod; ++mi) {
-    const LossMod m = a.mod[mi];
-    const int c = m.chans;
-    const float *pr = a.pred_img + (int64_t)n * a.nimg + m.col_off;
-    float *dp = a.dimg + (int64_t)n * a.nimg + m.col_off;
-    if (m.kind == MPMAE_IMAGE_CATEGORICAL) {
-      const long long *tg = static_cast<const long long *>(m.target) + (int64_t)n * c;
-      // argmax of the one-hot row (first maximum, as torch.argmax)
-      if (threadIdx.x == 0) cls_sh = 0x7fffffff;
-      long long best = tg[0];
-      for (int k = 1; k < c; ++k) best = tg[k] > best ? tg[k] : best;  // small c; every thread scans
-      __syncthreads();
-      for (int k = threadIdx.x; k < c; k += blockDim.x)
-        if (tg[k] == best) atomicMin(&cls_sh, k);
-      __syncthreads();
-      const int cls = cls_sh;
-      float mx = -INFINITY, dummy = 0.f;
-      for (int k = threadIdx.x; k < c; k += blockDim.x) mx = fmaxf(mx, pr[k]);
-      mx = warp_max(mx);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-      __syncthreads();
-      mx = red[0];
-      for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
-      float se = 0.f;
-      for (int k = threadIdx.x; k < c; k += blockDim.x) se += expf(pr[k] - mx);
-      block_sum2(se, dummy, red);
-      const float lse = mx + logf(se);
-      if (threadIdx.x == 0) { atomicAdd(&a.acc[2 * mi], lse - pr[cls]); atomicAdd(&a.acc[2 * mi + 1], 1.f); }
-      for (int k = threadIdx.x; k < c; k += blockDim.x) dp[k] = expf(pr[k] - lse) - (k == cls ? 1.f : 0.f);
-      __syncthreads();
-    } else if (m.kind == MPMAE_IMAGE_CONTINUOUS) {
-      const float *tg = static_cast<const float *>(m.target) + (int64_t)n * c;
-      float se = 0.f, cnt = 0.f;
-      for (int k = threadIdx.x; k < c; k += blockDim.x) {
-        const float t = tg[k];
-        if (t == t) {
-          const float d = pr[k] - t;
-          se += d * d; cnt += 1.f; dp[k] = 2.f * d;
-        } else {
-          dp[k] = 0.f;
-        }
-      }
-      block_sum2(se, cnt, red);
-      if (threadIdx.x == 0 && cnt > 0.f) { atomicAdd(&a.acc[2 * mi], se); atomicAdd(&a.acc[2 * mi + 1], cnt); }
+// image-level heads (fcmae.py:281-301): one CTA per sample, one warp per image modality (blockDim.x = 32 * their count)
+__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) image_loss_kernel(LossArgs a) {
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int mi = -1;
+  for (int i = 0, k = 0; i < a.n_mod; ++i)
+    if (a.mod[i].kind == MPMAE_IMAGE_CATEGORICAL || a.mod[i].kind == MPMAE_IMAGE_CONTINUOUS) {
+      if (k == warp) { mi = i; break; }
+      ++k;
     }
+  if (mi < 0) return;
+  const LossMod m = a.mod[mi];
+  const int c = m.chans;
+  const float *pr = a.pred_img + (int64_t)n * a.nimg + m.col_off;
+  float *dp = a.dimg + (int64_t)n * a.nimg + m.col_off;
+  if (m.kind == MPMAE_IMAGE_CATEGORICAL) {
+    const long long *tg = static_cast<const long long *>(m.target) + (int64_t)n * c;
+    // argmax of the one-hot row (first maximum, as torch.argmax): lexicographic (value desc, index asc) reduction
+    long long best = tg[lane < c ? lane : 0];
+    int cls = lane < c ? lane : 0;
+    for (int k = lane + 32; k < c; k += 32) {
+      const long long t = tg[k];
+      if (t > best) { best = t; cls = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, cls, o);
+      if (ob > best || (ob == best && oc < cls)) { best = ob; cls = oc; }
+    }
+    float mx = -INFINITY;
+    for (int k = lane; k < c; k += 32) mx = fmaxf(mx, pr[k]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int k = lane; k < c; k += 32) se += expf(pr[k] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    if (lane == 0) { atomicAdd(&a.acc[2 * mi], lse - pr[cls]); atomicAdd(&a.acc[2 * mi + 1], 1.f); }
+    for (int k = lane; k < c; k += 32) dp[k] = expf(pr[k] - lse) - (k == cls ? 1.f : 0.f);
+  } else {
+    const float *tg = static_cast<const float *>(m.target) + (int64_t)n * c;
+    float se = 0.f, cnt = 0.f;
+    for (int k = lane; k < c; k += 32) {
+      const float t = tg[k];
+      if (t == t) {
+        const float d = pr[k] - t;
+        se += d * d; cnt += 1.f; dp[k] = 2.f * d;
+      } else {
+        dp[k] = 0.f;
+      }
+    }
+    se = warp_sum(se); cnt = warp_sum(cnt);
+    if (lane == 0 && cnt > 0.f) { atomicAdd(&a.acc[2 * mi], se); atomicAdd(&a.acc[2 * mi + 1], cnt); }
   }
 }
 

@@ -2,6 +2,8 @@
 // pooled image-head kernels.  All are HBM-bound row kernels: one warp per row, float4 where the
 // channel count allows, warp-shuffle reductions.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mpmae {
@@ -294,6 +296,9 @@ struct FoldArgs {
   // 3xTF32: when set, Wf / WfT receive the TF32-representable high part and these the remainder (w - hi)
   float *Wf_lo;
   float *WfT_lo;
+  // 3xBF16 (b16 != 0): Wf / WfT receive the full fp32 value and Wf_lo / WfT_lo are reinterpreted as packed bf16 pairs:
+  // hi part [N*K] followed by lo part [N*K] (same footprint as one fp32 array)
+  int b16;
   // fused batch-global GRN statistic (sparse blocks): when gsq is set the K-axis scale is computed here,
   //   s[k] = 1 + gamma[k] * sqrt(gsq[k]) / (mean_k sqrt(gsq) + eps),  and nx / scale / denom are written for the backward
   const float *gsq, *gamma;
@@ -301,6 +306,13 @@ struct FoldArgs {
   float grn_eps;
 };
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void store_bf16_pair(float *lo_array, int64_t idx, int64_t nk, float wf) {
+  uint16_t *b = reinterpret_cast<uint16_t *>(lo_array);
+  const __nv_bfloat16 h = __float2bfloat16_rn(wf);
+  const __nv_bfloat16 l = __float2bfloat16_rn(wf - __bfloat162float(h));
+  b[idx] = __bfloat16_as_ushort(h);
+  b[nk + idx] = __bfloat16_as_ushort(l);
+}
 // 32 x 32 tiles through shared memory: the source is read along its contiguous axis and both orientations (Wf [N, K],
 // WfT [K, N]) leave with coalesced stores.  grid = (K tiles, N tiles), block = (32, 8).  The folded bias of a row block is
 // produced by the CTAs of the first K tile.
@@ -350,7 +362,8 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
     }
   }
   __syncthreads();
-  const bool split = p.Wf_lo != nullptr || p.WfT_lo != nullptr;
+  const bool split = (p.Wf_lo != nullptr || p.WfT_lo != nullptr) && !p.b16;
+  const int64_t nk = (int64_t)p.N * p.K;
   if (p.Wf) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -359,7 +372,10 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
         const float wf = tile[nl][tx] * sks[tx] * (p.scale_n ? p.scale_n[n] : 1.f);
         const float hi = tf32_hi(wf);
         p.Wf[(int64_t)n * p.K + k] = split ? hi : wf;
-        if (p.Wf_lo) p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
+        if (p.Wf_lo) {
+          if (p.b16) store_bf16_pair(p.Wf_lo, (int64_t)n * p.K + k, nk, wf);
+          else p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
+        }
       }
     }
   }
@@ -371,7 +387,10 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
         const float wf = tile[tx][kl] * sks[kl] * (p.scale_n ? p.scale_n[n] : 1.f);
         const float hi = tf32_hi(wf);
         p.WfT[(int64_t)k * p.N + n] = split ? hi : wf;
-        if (p.WfT_lo) p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
+        if (p.WfT_lo) {
+          if (p.b16) store_bf16_pair(p.WfT_lo, (int64_t)k * p.N + n, nk, wf);
+          else p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
+        }
       }
     }
   }
@@ -453,84 +472,134 @@ __global__ void scatter_token_kernel(const float *__restrict__ z, const float *_
     *reinterpret_cast<float4 *>(xd + cell * C + c) = v;
   }
 }
-// backward: dz[n*V+slot] = dxd[cell] for visible cells; dtoken += sum over masked cells
+// backward: dz[n*V+slot] = dxd[cell] for visible cells; dtoken += sum over masked cells.
+// blockDim.x = C/4: a thread owns one float4 column group for every cell its CTA visits (token sums in registers).
 __global__ void gather_token_bwd_kernel(const float *__restrict__ dxd, const int *__restrict__ slot_of,
                                         float *__restrict__ dz, float *__restrict__ dtoken, int64_t cells, int L, int V,
                                         int C) {
-  // grid.x strides cells, threads stride channels; masked-cell sums are accumulated per CTA first
-  extern __shared__ float tok[];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) tok[c] = 0.f;
-  __syncthreads();
+  const int C4 = C >> 2, t = threadIdx.x;
+  if (t >= C4) return;
+  const float4 *src = reinterpret_cast<const float4 *>(dxd);
+  float4 *dst = reinterpret_cast<float4 *>(dz);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t cell = blockIdx.x; cell < cells; cell += gridDim.x) {
-    const int slot = slot_of[cell];
+    const int slot = __ldg(slot_of + cell);
     const int64_t n = cell / L;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const float v = dxd[cell * C + c];
-      if (slot >= 0) dz[(n * V + slot) * C + c] = v;
-      else tok[c] += v;
-    }
+    const float4 v = __ldg(src + cell * C4 + t);
+    if (slot >= 0) dst[(n * V + slot) * C4 + t] = v;
+    else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dtoken[c], tok[c]);
+  atomicAdd(&dtoken[4 * t], acc.x); atomicAdd(&dtoken[4 * t + 1], acc.y);
+  atomicAdd(&dtoken[4 * t + 2], acc.z); atomicAdd(&dtoken[4 * t + 3], acc.w);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Image-level heads: channel LayerNorm of every decoder cell (norm_layers.py:26-31, eps 1e-6) then
-// mean over the L cells (fcmae.py:259-262).  One CTA per sample; warp per cell; smem accumulation.
-__global__ void pool_ln_fwd_kernel(const float *__restrict__ d, const float *__restrict__ w, const float *__restrict__ b,
-                                   float *__restrict__ pooled, float *__restrict__ rstd_out, int L, int C, float eps) {
-  extern __shared__ float acc[];  // [C]
+// mean over the L cells (fcmae.py:259-262).  One CTA per sample, warp per cell; a lane owns the float4 columns
+// lane + 32 j of every row its warp visits, so the per-channel sums over cells live in registers and only the
+// per-warp partials meet in shared memory.  C % 128 == 0, C <= 1024.
+constexpr int kPoolMaxF4 = 8;
+__global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float *__restrict__ d, const float *__restrict__ w,
+                                                          const float *__restrict__ b, float *__restrict__ pooled,
+                                                          float *__restrict__ rstd_out, int L, int C, float eps) {
+  extern __shared__ float part[];  // [nw][C]
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
-  __syncthreads();
+  const int f4 = C >> 7;           // float4 per lane
+  float4 acc[kPoolMaxF4];
+#pragma unroll
+  for (int j = 0; j < kPoolMaxF4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = warp; l < L; l += nw) {
-    const float *xr = d + ((int64_t)n * L + l) * C;
+    const float4 *xr = reinterpret_cast<const float4 *>(d + ((int64_t)n * L + l) * C) + lane;
+    float4 v[kPoolMaxF4];
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) { v[j] = __ldg(xr + 32 * j); s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
     const float mean = warp_sum(s) / (float)C;
-    float v = 0.f;
-    for (int c = lane; c < C; c += 32) { const float t = xr[c] - mean; v += t * t; }
-    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     if (lane == 0) rstd_out[(int64_t)n * L + l] = rstd;
-    for (int c = lane; c < C; c += 32) atomicAdd(&acc[c], (xr[c] - mean) * rstd);
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) { acc[j].x += v[j].x * rstd; acc[j].y += v[j].y * rstd; acc[j].z += v[j].z * rstd; acc[j].w += v[j].w * rstd; }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[(int64_t)n * C + c] = w[c] * (acc[c] / (float)L) + b[c];
-}
-// backward: dpooled [B,C] -> ddec[n,l,:] += LNbwd(dn = w*dpooled/L) ; dw += dpooled * mean_l(nhat) ; db += dpooled
-__global__ void pool_ln_bwd_kernel(const float *__restrict__ d, const float *__restrict__ rstd_in,
-                                   const float *__restrict__ w, const float *__restrict__ dpooled,
-                                   float *__restrict__ ddec, float *__restrict__ dw, float *__restrict__ db, int L, int C,
-                                   float eps) {
-  extern __shared__ float acc[];  // [C] sum_l nhat
-  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
-  __syncthreads();
-  for (int l = warp; l < L; l += nw) {
-    const int64_t row = (int64_t)n * L + l;
-    const float *xr = d + row * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += xr[c];
-    const float mean = warp_sum(s) / (float)C;
-    const float rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float nh = (xr[c] - mean) * rstd;
-      const float g = w[c] * dpooled[(int64_t)n * C + c] / (float)L;
-      s1 += g; s2 += g * nh;
-      atomicAdd(&acc[c], nh);
-    }
-    s1 = warp_sum(s1) / (float)C; s2 = warp_sum(s2) / (float)C;
-    for (int c = lane; c < C; c += 32) {
-      const float nh = (xr[c] - mean) * rstd;
-      const float g = w[c] * dpooled[(int64_t)n * C + c] / (float)L;
-      ddec[row * C + c] += rstd * (g - s1 - nh * s2);
-    }
-  }
+#pragma unroll
+  for (int j = 0; j < kPoolMaxF4; ++j)
+    if (j < f4) reinterpret_cast<float4 *>(part + (size_t)warp * C)[lane + 32 * j] = acc[j];
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < nw; ++k) t += part[(size_t)k * C + c];
+    pooled[(int64_t)n * C + c] = w[c] * (t / (float)L) + b[c];
+  }
+}
+// backward: dpooled [B,C] -> ddec[n,l,:] += LNbwd(dn = w*dpooled/L) ; dw += dpooled * mean_l(nhat) ; db += dpooled
+__global__ void __launch_bounds__(256) pool_ln_bwd_kernel(const float *__restrict__ d, const float *__restrict__ rstd_in,
+                                                          const float *__restrict__ w, const float *__restrict__ dpooled,
+                                                          float *__restrict__ ddec, float *__restrict__ dw,
+                                                          float *__restrict__ db, int L, int C, float eps) {
+  extern __shared__ float part[];  // [nw][C] sum_l nhat
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int f4 = C >> 7;
+  float4 acc[kPoolMaxF4], g[kPoolMaxF4];
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kPoolMaxF4; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g[j] = acc[j];
+    if (j < f4) {   // g = w * dpooled / L is the same for every cell of the sample
+      const float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + lane + 32 * j);
+      const float4 dv = __ldg(reinterpret_cast<const float4 *>(dpooled + (int64_t)n * C) + lane + 32 * j);
+      g[j] = make_float4(wv.x * dv.x / (float)L, wv.y * dv.y / (float)L, wv.z * dv.z / (float)L, wv.w * dv.w / (float)L);
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+    }
+  }
+  s1 = warp_sum(s1) / (float)C;
+  for (int l = warp; l < L; l += nw) {
+    const int64_t row = (int64_t)n * L + l;
+    const float4 *xr = reinterpret_cast<const float4 *>(d + row * C) + lane;
+    float4 v[kPoolMaxF4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) { v[j] = __ldg(xr + 32 * j); s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+    const float mean = warp_sum(s) / (float)C;
+    const float rstd = __ldg(rstd_in + row);
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) {
+        v[j].x = (v[j].x - mean) * rstd; v[j].y = (v[j].y - mean) * rstd;
+        v[j].z = (v[j].z - mean) * rstd; v[j].w = (v[j].w - mean) * rstd;
+        s2 += g[j].x * v[j].x + g[j].y * v[j].y + g[j].z * v[j].z + g[j].w * v[j].w;
+        acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w;
+      }
+    s2 = warp_sum(s2) / (float)C;
+    float4 *o = reinterpret_cast<float4 *>(ddec + row * C) + lane;
+#pragma unroll
+    for (int j = 0; j < kPoolMaxF4; ++j)
+      if (j < f4) {
+        float4 t = o[32 * j];
+        t.x += rstd * (g[j].x - s1 - v[j].x * s2); t.y += rstd * (g[j].y - s1 - v[j].y * s2);
+        t.z += rstd * (g[j].z - s1 - v[j].z * s2); t.w += rstd * (g[j].w - s1 - v[j].w * s2);
+        o[32 * j] = t;
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kPoolMaxF4; ++j)
+    if (j < f4) reinterpret_cast<float4 *>(part + (size_t)warp * C)[lane + 32 * j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < nw; ++k) t += part[(size_t)k * C + c];
     const float dp = dpooled[(int64_t)n * C + c];
-    atomicAdd(&dw[c], dp * acc[c] / (float)L);
+    atomicAdd(&dw[c], dp * t / (float)L);
     atomicAdd(&db[c], dp);
   }
 }

@@ -446,7 +446,8 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
   GemmArgs a = a_in;
   mpmae_plan *pl = c.pl;
   const bool use_tc = pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a);
-  if (pl->cfg.gemm_backend == 1) {
+  if (pl->cfg.gemm_backend == 3) a.b16 = a.Bw_lo ? 1 : 0;
+  if (pl->cfg.gemm_backend == 1 || pl->cfg.gemm_backend == 3) {
     // 3xTF32: the weight operand is consumed as a (hi, lo) pair; folded weights were written that way by fold(),
     // raw parameter matrices are split here into the scratch buffers
     if (!a.Bw_lo && use_tc) {
@@ -454,6 +455,7 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
       f.W = a.Bw; f.s_n = a.K; f.s_k = 1; f.Wf = c.w(pl->o_wf); f.N = a.N; f.K = a.K; f.SL = a.K;
       fold(c, f, "split_w");
       a.Bw = c.w(pl->o_wf); a.Bw_lo = c.w(pl->o_wf_lo);
+      a.b16 = pl->cfg.gemm_backend == 3 ? 1 : 0;
     }
   }
   {
@@ -471,7 +473,7 @@ void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
   if (!c.ok()) return;
   c.acct(4.0 * ((double)a.R * a.N + (double)a.R * a.K + (double)a.N * a.K), 2.0 * (double)a.R * a.N * a.K);
   if (c.pl->cfg.gemm_backend != 0 && tc_wgrad_supported(a)) {
-    c.check(launch_gemm_wgrad_tc(a, a.exact != 0 && c.pl->cfg.gemm_backend == 1, c.st), what);
+    c.check(launch_gemm_wgrad_tc(a, a.exact != 0 && (c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3), c.st), what);
     if (a.db && c.ok()) {   // bias gradient = column sums of X (the tensor-core kernel produces dW only)
       c.acct(4.0 * (double)a.R * a.N, 0);
       launch_colsum(a.X, a.rs, a.db, a.R, a.N, c.st);
@@ -483,9 +485,10 @@ void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
 }
 void fold(Ctx &c, FoldArgs a, const char *what) {
   if (!c.ok()) return;
-  if (c.pl->cfg.gemm_backend == 1) {
+  if (c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3) {
     if (a.Wf == c.w(c.pl->o_wf)) a.Wf_lo = c.w(c.pl->o_wf_lo);
     if (a.WfT == c.w(c.pl->o_wft)) a.WfT_lo = c.w(c.pl->o_wft_lo);
+    a.b16 = c.pl->cfg.gemm_backend == 3 ? 1 : 0;
   }
   launch_fold(a, c.st);
   c.post(what);
@@ -493,7 +496,8 @@ void fold(Ctx &c, FoldArgs a, const char *what) {
 // fold a weight into its slot: both orientations (+ hi/lo split for 3xTF32) and the folded bias in one launch
 void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what) {
   if (!c.ok()) return;
-  const bool split = c.pl->cfg.gemm_backend == 1;
+  const bool split = c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3;
+  a.b16 = c.pl->cfg.gemm_backend == 3 ? 1 : 0;
   a.Wf = c.w(s.wf); a.WfT = c.w(s.wft);
   a.Wf_lo = split ? c.w(s.wf_lo) : nullptr;
   a.WfT_lo = split ? c.w(s.wft_lo) : nullptr;
@@ -504,7 +508,8 @@ void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what) {
 }
 // point a GEMM at a slot: out = A . Wf^T (transposed = false) or A . Wf (transposed = true)
 void use_slot(Ctx &c, GemmArgs &g, const WSlot &s, bool transposed) {
-  const bool split = c.pl->cfg.gemm_backend == 1;
+  const bool split = c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3;
+  g.b16 = c.pl->cfg.gemm_backend == 3 ? 1 : 0;
   g.Bw = c.w(transposed ? s.wft : s.wf);
   g.Bw_lo = split ? c.w(transposed ? s.wft_lo : s.wf_lo) : nullptr;
 }
@@ -750,7 +755,8 @@ int mpmae_plan_create(const mpmae_cfg *cfg, mpmae_plan **out) {
   if (c.patch_size != 8 && c.patch_size != 16)
     return fail(MPMAE_ERR_UNSUPPORTED, "patch_size %d: kernels are instantiated for 8 and 16", c.patch_size);
   if (c.n_mod <= 0 || c.n_mod > MPMAE_MAX_MOD) return fail(MPMAE_ERR_INVALID, "n_mod %d", c.n_mod);
-  if (c.dec_depth < 1 || c.dec_dim % 32 != 0) return fail(MPMAE_ERR_INVALID, "decoder depth/dim");
+  if (c.dec_depth < 1 || c.dec_dim % 128 != 0 || c.dec_dim > 1024)
+    return fail(MPMAE_ERR_INVALID, "decoder depth/dim (dec_dim must be a multiple of 128, at most 1024)");
   for (int i = 0; i < 4; ++i) {
     if (c.depths[i] < 1 || c.dims[i] % 8 != 0) return fail(MPMAE_ERR_UNSUPPORTED, "dims must be multiples of 8");
     if (i > 0 && c.dims[i] < c.dims[i - 1]) return fail(MPMAE_ERR_UNSUPPORTED, "dims must be non-decreasing");
@@ -940,7 +946,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
     gemm<EPI_STORE>(c, g, "pixel_heads");
   }
   if (pl->nimg > 0) {
-    pool_ln_fwd_kernel<<<geo.B, 256, (size_t)D * 4, c.st>>>(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
+    pool_ln_fwd_kernel<<<geo.B, 256, (size_t)8 * D * 4, c.st>>>(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
                                                           c.w(pl->o_pool_rstd), geo.L, D, 1e-6f);
     c.post("pool_ln");
     GemmArgs g{};
@@ -950,8 +956,18 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   }
   {
     LossArgs a = loss_args(c);
-    if (pl->npix > 0) { pixel_loss_kernel<<<(unsigned)pl->cells, 256, 0, c.st>>>(a); c.post("pixel_loss"); }
-    if (pl->nimg > 0) { image_loss_kernel<<<geo.B, 256, 0, c.st>>>(a); c.post("image_loss"); }
+    if (pl->npix > 0) {
+      int npm = 0;
+      for (int m = 0; m < cf.n_mod; ++m) npm += pl->is_img[m] ? 0 : 1;
+      pixel_loss_kernel<<<(unsigned)pl->cells, 32 * npm, 0, c.st>>>(a);
+      c.post("pixel_loss");
+    }
+    if (pl->nimg > 0) {
+      int nim = 0;
+      for (int m = 0; m < cf.n_mod; ++m) nim += pl->is_img[m] ? 1 : 0;
+      image_loss_kernel<<<geo.B, 32 * nim, 0, c.st>>>(a);
+      c.post("image_loss");
+    }
     loss_finalize_kernel<<<1, 32, 0, c.st>>>(c.w(pl->o_acc), pl->logv >= 0 ? c.p(pl->logv) : nullptr, cf.n_mod,
                                              cf.loss_aggr, io->losses);
     c.post("loss_finalize");
@@ -1020,7 +1036,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     w.R = geo.B; w.N = pl->nimg; w.K = D;
     wgrad(c, w, "dW_img");
     if (c.ok()) {
-      pool_ln_bwd_kernel<<<geo.B, 256, (size_t)D * 4, c.st>>>(dec_out, c.w(pl->o_pool_rstd), c.p(pl->lnt_w), c.w(pl->o_dpooled),
+      pool_ln_bwd_kernel<<<geo.B, 256, (size_t)8 * D * 4, c.st>>>(dec_out, c.w(pl->o_pool_rstd), c.p(pl->lnt_w), c.w(pl->o_dpooled),
                                                             dd, c.g(pl->lnt_w), c.g(pl->lnt_b), geo.L, D, 1e-6f);
       c.post("pool_ln_bwd");
     }
@@ -1035,7 +1051,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   {
     float *dz = c.w(pl->o_gdv);
     if (c.ok()) {
-      gather_token_bwd_kernel<<<148 * 2, 128, (size_t)D * 4, c.st>>>(cur, slot_of, dz, c.g(pl->tok), pl->cells, geo.L, geo.V, D);
+      gather_token_bwd_kernel<<<148 * 4, ((D / 4 + 31) / 32) * 32, 0, c.st>>>(cur, slot_of, dz, c.g(pl->tok), pl->cells, geo.L, geo.V, D);
       c.post("gather_token_bwd");
     }
     WgradArgs w{};
@@ -1190,12 +1206,13 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
   cudaError_t e;
   if (backend != 0) {
     if (!tc_gemm_supported(EPI_STORE, g)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
-    if (backend == 1) {  // 3xTF32: split the weight into TF32-exact high part + remainder in the caller's scratch
-      if (!scratch) return fail(MPMAE_ERR_INVALID, "backend 1 needs scratch of 2*N*K floats");
+    if (backend == 1 || backend == 3) {  // split the weight (TF32 hi + remainder, or a bf16 pair) in the caller's scratch
+      if (!scratch) return fail(MPMAE_ERR_INVALID, "backends 1 and 3 need scratch of 2*N*K floats");
       FoldArgs f{};
       f.W = b; f.s_n = K; f.s_k = 1; f.Wf = scratch; f.Wf_lo = scratch + (int64_t)N * K; f.N = N; f.K = K; f.SL = K;
+      f.b16 = backend == 3 ? 1 : 0;
       launch_fold(f, st);
-      g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
+      g.Bw = f.Wf; g.Bw_lo = f.Wf_lo; g.b16 = f.b16;
     }
     e = launch_gemm_rows_tc<EPI_STORE>(g, backend, st);
   } else {
@@ -1215,13 +1232,14 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
   g.group_rows = d->group_rows > 0 ? d->group_rows : 0x7fffffff;
   const bool tc_ok = backend != 0 && tc_gemm_supported(mode, g);
   if (backend != 0 && !tc_ok) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
-  if (backend == 1) {
-    if (!d->scratch) return fail(MPMAE_ERR_INVALID, "backend 1 needs scratch of 2*N*K floats");
+  if (backend == 1 || backend == 3) {
+    if (!d->scratch) return fail(MPMAE_ERR_INVALID, "backends 1 and 3 need scratch of 2*N*K floats");
     FoldArgs f{};
     f.W = d->b; f.s_n = d->K; f.s_k = 1; f.Wf = d->scratch; f.Wf_lo = d->scratch + (int64_t)d->N * d->K; f.N = d->N;
     f.K = d->K; f.SL = d->K;
+    f.b16 = backend == 3 ? 1 : 0;
     launch_fold(f, st);
-    g.Bw = f.Wf; g.Bw_lo = f.Wf_lo;
+    g.Bw = f.Wf; g.Bw_lo = f.Wf_lo; g.b16 = f.b16;
   }
   cudaError_t e = cudaSuccess;
   switch (mode) {
@@ -1243,7 +1261,7 @@ int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw,
   cudaError_t e;
   if (backend != 0) {
     if (!tc_wgrad_supported(w)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
-    e = launch_gemm_wgrad_tc(w, backend == 1, st);
+    e = launch_gemm_wgrad_tc(w, backend == 1 || backend == 3, st);
   } else {
     e = launch_gemm_wgrad(w, st);
   }

@@ -127,7 +127,7 @@ class FCMAE(nn.Module):
                 self.out_chans[m] = len(args.modalities_full[m]) if bands == "all" else len(bands)
         if self.loss_aggr == "uncertainty" and loss_fn is None:
             raise ValueError("loss_aggr='uncertainty' needs loss_fn with a log_vars parameter (custom_loss.py:10-17)")
-        self.gemm_backend = 1 if gemm_backend is None else int(gemm_backend)
+        self.gemm_backend = 3 if gemm_backend is None else int(gemm_backend)
 
         self._plans: Dict[int, nat.Plan] = {}
         plan = self._plan(1)
