@@ -229,10 +229,15 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then the epilogue warps, then (3xTF32 only) the
 // operand-splitter warps.  GELU / statistics epilogues are latency bound and get 16 warps (4 per scheduler) with 2 splitter
 // warps (their K is the narrow side); the plain store epilogue is light and its K is the wide side, so it runs 8 + 8.
+// (Measured with the bf16-converting splitter: 16 + 2 is best for the forward GELU epilogue, 12 + 4 for the backward ones.)
 // 18-20 warps = 5 per scheduler keeps 96 registers per thread.
 // WIDE (K >= 256: the operand stream dominates, e.g. the decoder block) also runs 8 + 8.
-__host__ __device__ constexpr int epi_warps(int mode, bool wide) { return (mode == EPI_STORE || wide) ? 8 : 16; }
-__host__ __device__ constexpr int split_warps(int mode, bool split, bool wide) { return !split ? 0 : ((mode == EPI_STORE || wide) ? 8 : 2); }
+__host__ __device__ constexpr int epi_warps(int mode, bool wide) {
+  return (mode == EPI_STORE || wide) ? 8 : (mode == EPI_GELU_SQ ? 16 : 12);
+}
+__host__ __device__ constexpr int split_warps(int mode, bool split, bool wide) {
+  return !split ? 0 : ((mode == EPI_STORE || wide) ? 8 : (mode == EPI_GELU_SQ ? 2 : 4));
+}
 __host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide) {
   return 64 + 32 * epi_warps(mode, wide) + 32 * split_warps(mode, split, wide);
 }
@@ -435,7 +440,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // hands it to the TMA unit (cp.async.bulk.tensor store: full-sector writes, no LSU work, columns beyond N clipped);
       // column statistics accumulate in shared memory for the whole kernel (flushed once at the end); the next chunk's
       // accumulator (tcgen05.ld) and per-element operand are in flight while this one is computed.
-      if (p.tma_out && single_group && (int64_t)(m_blk + 1) * BM <= g.M && (!pre_src || ((ncols & 7) == 0 && p.vec8_in))) {
+      if (p.tma_out && (single_group || MODE == EPI_GELU_SQ || MODE == EPI_DG) && (int64_t)(m_blk + 1) * BM <= g.M &&
+          (!pre_src || ((ncols & 7) == 0 && p.vec8_in))) {
         const int64_t row_off = m * (int64_t)g.N + n_base;
         const float *prep = pre_src ? pre_src + row_off : nullptr;
         const uint32_t sbuf = smem_u32(stage_out) + (uint32_t)(warp - 2) * out_arrays(MODE) * kStageOutBytes;
@@ -523,8 +529,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             continue;
           }
           if (MODE == EPI_GELU_SQ || MODE == EPI_DG) {
-            const float t = warp_colsum16(s1, lane);
-            if (lane < 16) atomicAdd(&statacc1[n_base + c0 + lane], t);
+            if (single_group) {
+              const float t = warp_colsum16(s1, lane);
+              if (lane < 16) atomicAdd(&statacc1[n_base + c0 + lane], t);
+            } else {
+              // per-sample statistics (decoder): the warp's 32 rows touch at most two groups (group_rows >= 32); each
+              // group's column sums go straight to global memory
+              const bool colv = lane < 16 && n_base + c0 + lane < g.N;
+              if (gw_hi == gw_lo) {
+                const float t = warp_colsum16(s1, lane);
+                if (colv) atomicAdd(&g.colsum[(g_first + gw_lo) * g.N + n_base + c0 + lane], t);
+              } else {
+                float lo[16], hi[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { lo[j] = (my_g == gw_lo) ? s1[j] : 0.f; hi[j] = (my_g == gw_lo) ? 0.f : s1[j]; }
+                const float tl = warp_colsum16(lo, lane), th = warp_colsum16(hi, lane);
+                if (colv) {
+                  atomicAdd(&g.colsum[(g_first + gw_lo) * g.N + n_base + c0 + lane], tl);
+                  atomicAdd(&g.colsum[(g_first + gw_hi) * g.N + n_base + c0 + lane], th);
+                }
+              }
+            }
           }
           if (MODE == EPI_DG || MODE == EPI_DH_GELU) {
             const float t = warp_colsum16(s2, lane);

@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from bench_gemm import bench
 
 B = 256
+BACKEND = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 shapes = [("s0 pw1", 1, B * 19 * 64, 160, 40), ("s2 pw1", 1, B * 19 * 4, 640, 160), ("s0 da", 3, B * 19 * 64, 160, 40),
           ("s0 pw2", 0, B * 19 * 64, 40, 160), ("s2 pw2", 0, B * 19 * 4, 160, 640)]
 knobs = [0, 1, 2, 4, 8, 32, 64, 3, 7, 15, 96, 127]
@@ -13,7 +14,7 @@ for name, mode, M, N, K in shapes:
     row = []
     for k in knobs:
         os.environ["MPMAE_TC_DBG"] = str(k)
-        ms, gbs, tf = bench(mode, 1, M, N, K, iters=5)
+        ms, gbs, tf = bench(mode, BACKEND, M, N, K, iters=5)
         row.append(f"{k}:{ms * 1e3:6.1f}")
     print(f"{name:8s} M={M} N={N} K={K} us: " + "  ".join(row), flush=True)
 os.environ["MPMAE_TC_DBG"] = "0"
