@@ -316,12 +316,12 @@ __device__ __forceinline__ void store_bf16_pair(float *lo_array, int64_t idx, in
 // 32 x 32 tiles through shared memory: the source is read along its contiguous axis and both orientations (Wf [N, K],
 // WfT [K, N]) leave with coalesced stores.  grid = (K tiles, N tiles), block = (32, 8).  The folded bias of a row block is
 // produced by the CTAs of the first K tile.
-__global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
+__device__ __forceinline__ void fold_tile(const FoldArgs &p, int bx, int by) {
   __shared__ float tile[32][33];
   __shared__ float red[8];
   __shared__ float sks[32];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int k0 = bx * 32, n0 = by * 32;
   if (p.gsq) {   // every CTA recomputes the (tiny) GRN denominator; K = SL here
     float s = 0.f;
     for (int d = tid; d < p.K; d += 256) s += sqrtf(p.gsq[d]);
@@ -338,11 +338,11 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
       if (k < p.K) {
         const float nx = sqrtf(p.gsq[k]) / den;
         sk = 1.f + p.gamma[k] * nx;
-        if (blockIdx.y == 0) { p.nx_out[k] = nx; p.scale_out[k] = sk; }
+        if (by == 0) { p.nx_out[k] = nx; p.scale_out[k] = sk; }
       }
       sks[tid] = sk;
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) p.denom_out[0] = den;
+    if (bx == 0 && by == 0 && tid == 0) p.denom_out[0] = den;
   } else if (tid < 32) {
     const int k = k0 + tid;
     sks[tid] = (p.scale_k && k < p.K) ? p.scale_k[k % p.SL] : 1.f;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
       }
     }
   }
-  if (p.bf && blockIdx.x == 0) {   // bf[n] = bias[n] + sum_k W[n, k] * shift[k % SL]: warp ty owns rows ty, ty+8, ...
+  if (p.bf && bx == 0) {   // bf[n] = bias[n] + sum_k W[n, k] * shift[k % SL]: warp ty owns rows ty, ty+8, ...
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + ty + 8 * i;
@@ -407,8 +407,25 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) {
     }
   }
 }
+__global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) { fold_tile(p, blockIdx.x, blockIdx.y); }
 inline void launch_fold(const FoldArgs &a, cudaStream_t st) {
   fold_kernel<<<dim3(cdiv(a.K, 32), cdiv(a.N, 32)), dim3(32, 8), 0, st>>>(a);
+}
+// Many folds in one launch (all the parameter-only folds of a forward pass): jobs and the prefix sum of their tile
+// counts live in device memory; a CTA finds its job by scanning the (short) prefix array.
+__global__ void __launch_bounds__(256) fold_batch_kernel(const FoldArgs *__restrict__ jobs, const int *__restrict__ tile_start,
+                                                         int njobs) {
+  __shared__ FoldArgs job;
+  __shared__ int local;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= tile_start[j + 1]) ++j;
+    job = jobs[j];
+    local = (int)blockIdx.x - tile_start[j];
+  }
+  __syncthreads();
+  const int kt = cdiv(job.K, 32);
+  fold_tile(job, local % kt, local / kt);
 }
 
 // Chain rule back through the fold:  given dWf [N,K] and dbf [N]

@@ -88,6 +88,9 @@ struct mpmae_plan {
   int64_t o_wf, o_wft, o_wf_lo, o_wft_lo, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
   int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
   int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
+  int64_t o_foldjobs = 0;                 // device copy of the batched parameter-only fold jobs + tile prefix
+  const void *fold_key_params = nullptr, *fold_key_ws = nullptr;
+  int fold_njobs = 0, fold_tiles = 0;
   int launches_fwd = 0, launches_bwd = 0;
   int bwd_flip = 0;   // which ping-pong buffer holds the running activation gradient between backward parts
   // optional per-launch CUDA-event profile (bench.py roofline leg)
@@ -363,6 +366,7 @@ void build_workspace(mpmae_plan *pl) {
   pl->o_dbf = ws_alloc(pl, nullptr, 1, pl->max_n);
   pl->o_dsv = ws_alloc(pl, nullptr, B, pl->max_n);
   pl->o_kg = ws_alloc(pl, nullptr, B, pl->max_n);
+  pl->o_foldjobs = ws_alloc(pl, nullptr, 1, (int64_t)(64 * sizeof(FoldArgs) + 65 * sizeof(int) + 3) / 4);
   pl->o_g0 = ws_alloc(pl, nullptr, 1, pl->max_rc);
   pl->o_g1 = ws_alloc(pl, nullptr, 1, pl->max_rc);
   pl->o_gdv = ws_alloc(pl, nullptr, 1, pl->max_rc);
@@ -379,6 +383,8 @@ struct Ctx {
   const float *P;  // params
   float *G;        // grads
   int launches = 0;
+  std::vector<FoldArgs> *collect = nullptr;   // when set, fold_slot() records the job instead of launching it
+  bool folds_done = false;                    // the parameter-only folds were launched as one batch: skip them
   cudaError_t err = cudaSuccess;
   const char *where = "";
   double pend_bytes = 0, pend_flops = 0;
@@ -503,6 +509,9 @@ void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what) {
   a.WfT_lo = split ? c.w(s.wft_lo) : nullptr;
   if (a.bias || a.shift_k) a.bf = c.w(s.bf);
   a.N = s.N; a.K = s.K;
+  const bool param_only = a.gsq == nullptr && a.scale_n == nullptr;   // depends on parameters alone
+  if (param_only && c.collect) { c.collect->push_back(a); return; }
+  if (param_only && c.folds_done) return;
   launch_fold(a, c.st);
   c.post(what);
 }
@@ -523,6 +532,71 @@ int ew_grid(int64_t n4) {
   return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
 }
 
+// ---- fold jobs that depend on parameters alone (shared by the call sites and the batched launch)
+FoldArgs pw1_fold_args(Ctx &c, const BlockP &bp, int C) {
+  FoldArgs f{};
+  f.W = c.p(bp.w1); f.s_n = C; f.s_k = 1; f.scale_k = c.p(bp.ln_w); f.shift_k = c.p(bp.ln_b);
+  f.bias = c.p(bp.b1); f.SL = C;
+  return f;
+}
+FoldArgs dense_pw2_fold_args(Ctx &c, const BlockP &bp, int D4) {   // per-sample GRN cannot be folded: plain (split) copy
+  FoldArgs f{};
+  f.W = c.p(bp.w2); f.s_n = D4; f.s_k = 1; f.SL = D4;
+  return f;
+}
+FoldArgs ds_fold_args(Ctx &c, int i, int Ci, int Co) {
+  FoldArgs f{};
+  f.W = c.p(c.pl->ds[i].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(c.pl->ds[i].ln_w);
+  f.shift_k = c.p(c.pl->ds[i].ln_b); f.bias = c.p(c.pl->ds[i].b); f.SL = Ci;
+  return f;
+}
+FoldArgs proj_fold_args(Ctx &c) {
+  FoldArgs f{};
+  f.W = c.p(c.pl->proj_w); f.s_n = c.pl->cfg.dims[3]; f.s_k = 1; f.SL = c.pl->cfg.dims[3];
+  return f;
+}
+FoldArgs heads_fold_args(Ctx &c) {
+  FoldArgs f{};
+  f.W = c.p(c.pl->pixw); f.s_n = c.pl->cfg.dec_dim; f.s_k = 1; f.SL = c.pl->cfg.dec_dim;
+  return f;
+}
+void fold_slot(Ctx &c, FoldArgs a, const WSlot &s, const char *what);
+// All of them in ONE launch at the start of the forward pass (19 launches otherwise at cfg2)
+void batched_param_folds(Ctx &c, bool encoder_only) {
+  mpmae_plan *pl = c.pl;
+  const mpmae_cfg &cf = pl->cfg;
+  std::vector<FoldArgs> jobs;
+  c.collect = &jobs;
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) fold_slot(c, ds_fold_args(c, i - 1, cf.dims[i - 1], cf.dims[i]), pl->ds_slot[i - 1], "fold_ds");
+    for (int j = 0; j < cf.depths[i]; ++j) fold_slot(c, pw1_fold_args(c, pl->blk[i][j], cf.dims[i]), pl->bw[i][j].s1, "fold_pw1");
+  }
+  if (!encoder_only) {
+    fold_slot(c, proj_fold_args(c), pl->proj_slot, "split_proj");
+    for (int k = 0; k < cf.dec_depth; ++k) {
+      fold_slot(c, pw1_fold_args(c, pl->dec[k], cf.dec_dim), pl->dw[k].s1, "fold_pw1");
+      fold_slot(c, dense_pw2_fold_args(c, pl->dec[k], 4 * cf.dec_dim), pl->dw[k].s2, "split_pw2");
+    }
+    if (pl->npix > 0) fold_slot(c, heads_fold_args(c), pl->pix_slot, "split_heads");
+  }
+  c.collect = nullptr;
+  const int n = (int)jobs.size();
+  if (n == 0 || n > 64 || !c.ok()) return;
+  std::vector<int> start(n + 1, 0);
+  for (int j = 0; j < n; ++j) start[j + 1] = start[j] + cdiv(jobs[j].K, 32) * cdiv(jobs[j].N, 32);
+  FoldArgs *d_jobs = reinterpret_cast<FoldArgs *>(c.w(pl->o_foldjobs));
+  int *d_start = reinterpret_cast<int *>(d_jobs + 64);
+  if (pl->fold_key_params != (const void *)c.P || pl->fold_key_ws != (const void *)c.ws || pl->fold_njobs != n) {
+    c.check(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(FoldArgs), cudaMemcpyHostToDevice, c.st), "memcpy", false);
+    c.check(cudaMemcpyAsync(d_start, start.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st), "memcpy", false);
+    pl->fold_key_params = c.P; pl->fold_key_ws = c.ws; pl->fold_njobs = n; pl->fold_tiles = start[n];
+  }
+  if (!c.ok()) return;
+  fold_batch_kernel<<<pl->fold_tiles, dim3(32, 8), 0, c.st>>>(d_jobs, d_start, n);
+  c.post("fold_batch");
+  c.folds_done = true;
+}
+
 // One ConvNeXt-V2 block forward (sparse: convnextv2_sparse.py:47-56; dense decoder: convnextv2.py:42-55).
 //   dense = per-sample GRN over L cells (eps 1e-4), torch conv weight layout; sparse = batch-global GRN (eps 1e-6)
 void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, int64_t R, int C, int P, bool dense) {
@@ -539,10 +613,7 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   c.acct(4.0 * (2.0 * R * C + R + 50.0 * C), 2.0 * 49 * (double)R * C);
   if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_fwd");
 
-  FoldArgs f{};
-  f.W = c.p(bp.w1); f.s_n = C; f.s_k = 1; f.scale_k = c.p(bp.ln_w); f.shift_k = c.p(bp.ln_b);
-  f.bias = c.p(bp.b1); f.SL = C;
-  fold_slot(c, f, bw.s1, "fold_pw1");
+  fold_slot(c, pw1_fold_args(c, bp, C), bw.s1, "fold_pw1");
 
   const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
   const int groups = dense ? pl->geo.B : 1;
@@ -568,7 +639,7 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
                                                                group_rows);
       c.post("grn_apply");
     }
-    fold_slot(c, f2, bw.s2, "split_pw2");   // per-sample GRN cannot be folded: plain (split) copy of W2
+    fold_slot(c, dense_pw2_fold_args(c, bp, D4), bw.s2, "split_pw2");
     g2.A = c.w(bw.g); g2.bias = c.p(bp.b2);
   } else {
     // GRN is affine in h per channel: fold s = 1 + gamma*Nx into W2's columns and beta into the bias
@@ -869,6 +940,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   c.check(cudaMemsetAsync(io->flags, 0, 4 * sizeof(int32_t), c.st), "memset", false);
   mask_kernel<<<geo.B, 64, (size_t)geo.L * 8, c.st>>>(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
   c.post("mask");
+  batched_param_folds(c, encoder_only);
 
   {  // patch embedding: 3x3 conv + LN (+GELU, stem depthwise, LN)
     InitConvArgs a = init_args(c);
@@ -897,10 +969,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       const int Ci = dm[i - 1], Co = dm[i];
       launch_ln_rows_fwd(x, c.w(pl->o_ds_xhat[i - 1]), c.w(pl->o_ds_rstd[i - 1]), pl->R[i - 1], Ci, 1e-6f, c.st);
       c.post("ds_ln");
-      FoldArgs f{};
-      f.W = c.p(pl->ds[i - 1].k); f.s_n = 1; f.s_k = Co; f.scale_k = c.p(pl->ds[i - 1].ln_w);
-      f.shift_k = c.p(pl->ds[i - 1].ln_b); f.bias = c.p(pl->ds[i - 1].b); f.SL = Ci;
-      fold_slot(c, f, pl->ds_slot[i - 1], "fold_ds");
+      fold_slot(c, ds_fold_args(c, i - 1, Ci, Co), pl->ds_slot[i - 1], "fold_ds");
       GemmArgs g{};
       g.A = c.w(pl->o_ds_xhat[i - 1]); use_slot(c, g, pl->ds_slot[i - 1], false); g.bias = c.w(pl->ds_slot[i - 1].bf);
       g.out = c.w(pl->o_ds_out[i - 1]);
@@ -920,9 +989,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   // decoder entry: proj on visible rows, mask token elsewhere (fcmae.py:251-255)
   const int D = cf.dec_dim;
   {
-    FoldArgs fp{};
-    fp.W = c.p(pl->proj_w); fp.s_n = dm[3]; fp.s_k = 1; fp.SL = dm[3];
-    fold_slot(c, fp, pl->proj_slot, "split_proj");
+    fold_slot(c, proj_fold_args(c), pl->proj_slot, "split_proj");
     GemmArgs g{};
     g.A = x; use_slot(c, g, pl->proj_slot, false); g.bias = c.p(pl->proj_b); g.out = c.w(pl->o_z);
     g.M = (int64_t)geo.B * geo.V; g.N = D; g.K = dm[3]; g.group_rows = 0x7fffffff;
@@ -937,9 +1004,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
     d = c.w(pl->dw[k].y);
   }
   if (pl->npix > 0) {
-    FoldArgs fp{};
-    fp.W = c.p(pl->pixw); fp.s_n = D; fp.s_k = 1; fp.SL = D;
-    fold_slot(c, fp, pl->pix_slot, "split_heads");
+    fold_slot(c, heads_fold_args(c), pl->pix_slot, "split_heads");
     GemmArgs g{};
     g.A = d; use_slot(c, g, pl->pix_slot, false); g.bias = c.p(pl->pixb); g.out = io->pred_pixel;
     g.M = pl->cells; g.N = pl->npix; g.K = D; g.group_rows = 0x7fffffff;
