@@ -442,9 +442,8 @@ struct UnfoldArgs {
   float *dscale, *dshift, *dbias;
   int N, K, SL;
 };
-__global__ void unfold_kernel(UnfoldArgs p) {
+__device__ __forceinline__ void unfold_column(const UnfoldArgs &p, int k) {
   __shared__ float r1[32], r2[32];
-  const int k = blockIdx.x;
   const int j = k % p.SL;
   const float sc = p.scale_k ? p.scale_k[j] : 1.f;
   const float sh = p.shift_k ? p.shift_k[j] : 0.f;
@@ -470,6 +469,20 @@ __global__ void unfold_kernel(UnfoldArgs p) {
       if (p.dshift) atomicAdd(&p.dshift[j], t2);
     }
   }
+}
+__global__ void unfold_kernel(UnfoldArgs p) { unfold_column(p, blockIdx.x); }
+// Several un-folds in one launch (the deferred ones of a backward part): job table + prefix sum of the K's in device memory
+__global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const int *__restrict__ k_start, int njobs) {
+  __shared__ UnfoldArgs job;
+  __shared__ int local;
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= k_start[j + 1]) ++j;
+    job = jobs[j];
+    local = (int)blockIdx.x - k_start[j];
+  }
+  __syncthreads();
+  unfold_column(job, local);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,6 +88,9 @@ struct mpmae_plan {
   int64_t o_wf, o_wft, o_wf_lo, o_wft_lo, o_bf, o_dwf, o_dbf, o_dsv, o_kg;
   int64_t o_g0, o_g1, o_gda, o_gdv, o_gdu;
   int64_t max_wf = 0, max_rc = 0, max_rd = 0, max_n = 0;
+  int64_t o_unfoldjobs[3] = {0, 0, 0};   // device copies of the deferred un-fold jobs of each backward part
+  const void *unfold_key[3][3] = {};
+  int unfold_njobs[3] = {0, 0, 0}, unfold_ctas[3] = {0, 0, 0};
   int64_t o_foldjobs = 0;                 // device copy of the batched parameter-only fold jobs + tile prefix
   const void *fold_key_params = nullptr, *fold_key_ws = nullptr;
   int fold_njobs = 0, fold_tiles = 0;
@@ -367,6 +370,7 @@ void build_workspace(mpmae_plan *pl) {
   pl->o_dsv = ws_alloc(pl, nullptr, B, pl->max_n);
   pl->o_kg = ws_alloc(pl, nullptr, B, pl->max_n);
   pl->o_foldjobs = ws_alloc(pl, nullptr, 1, (int64_t)(64 * sizeof(FoldArgs) + 65 * sizeof(int) + 3) / 4);
+  for (int i = 0; i < 3; ++i) pl->o_unfoldjobs[i] = ws_alloc(pl, nullptr, 1, (int64_t)(64 * sizeof(UnfoldArgs) + 65 * sizeof(int) + 3) / 4);
   pl->o_g0 = ws_alloc(pl, nullptr, 1, pl->max_rc);
   pl->o_g1 = ws_alloc(pl, nullptr, 1, pl->max_rc);
   pl->o_gdv = ws_alloc(pl, nullptr, 1, pl->max_rc);
@@ -385,6 +389,7 @@ struct Ctx {
   int launches = 0;
   std::vector<FoldArgs> *collect = nullptr;   // when set, fold_slot() records the job instead of launching it
   bool folds_done = false;                    // the parameter-only folds were launched as one batch: skip them
+  std::vector<UnfoldArgs> deferred;           // un-folds whose results nothing in the backward pass reads
   cudaError_t err = cudaSuccess;
   const char *where = "";
   double pend_bytes = 0, pend_flops = 0;
@@ -522,10 +527,34 @@ void use_slot(Ctx &c, GemmArgs &g, const WSlot &s, bool transposed) {
   g.Bw = c.w(transposed ? s.wft : s.wf);
   g.Bw_lo = split ? c.w(transposed ? s.wft_lo : s.wf_lo) : nullptr;
 }
-void unfold(Ctx &c, UnfoldArgs a, const char *what) {
+void unfold(Ctx &c, UnfoldArgs a, const char *what, bool deferrable = false) {
   if (!c.ok()) return;
+  if (deferrable && c.deferred.size() < 64) { c.deferred.push_back(a); return; }
   unfold_kernel<<<a.K, 256, 0, c.st>>>(a);
   c.post(what);
+}
+// the deferred un-folds of this call in one launch; slot selects the cached job table (0..2 = backward part)
+void flush_unfolds(Ctx &c, int slot) {
+  const int n = (int)c.deferred.size();
+  if (n == 0 || !c.ok()) return;
+  mpmae_plan *pl = c.pl;
+  std::vector<int> start(n + 1, 0);
+  for (int j = 0; j < n; ++j) start[j + 1] = start[j] + c.deferred[j].K;
+  UnfoldArgs *d_jobs = reinterpret_cast<UnfoldArgs *>(c.w(pl->o_unfoldjobs[slot]));
+  int *d_start = reinterpret_cast<int *>(d_jobs + 64);
+  const void *key[3] = {c.P, c.G, c.ws};
+  if (pl->unfold_key[slot][0] != key[0] || pl->unfold_key[slot][1] != key[1] || pl->unfold_key[slot][2] != key[2] ||
+      pl->unfold_njobs[slot] != n || pl->unfold_ctas[slot] != start[n]) {
+    c.check(cudaMemcpyAsync(d_jobs, c.deferred.data(), n * sizeof(UnfoldArgs), cudaMemcpyHostToDevice, c.st), "memcpy", false);
+    c.check(cudaMemcpyAsync(d_start, start.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st), "memcpy", false);
+    for (int i = 0; i < 3; ++i) pl->unfold_key[slot][i] = key[i];
+    pl->unfold_njobs[slot] = n; pl->unfold_ctas[slot] = start[n];
+  }
+  if (c.ok()) {
+    unfold_batch_kernel<<<start[n], 256, 0, c.st>>>(d_jobs, d_start, n);
+    c.post("unfold_batch");
+  }
+  c.deferred.clear();
 }
 int ew_grid(int64_t n4) {
   int64_t g = cdiv64(n4, 256);
@@ -715,7 +744,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   u1.W = c.p(bp.w1); u1.s_n = C; u1.s_k = 1; u1.scale_k = c.p(bp.ln_w); u1.shift_k = c.p(bp.ln_b);
   u1.dWf = dwf1; u1.dbf = dbf1; u1.dW = c.g(bp.w1); u1.dscale = c.g(bp.ln_w); u1.dshift = c.g(bp.ln_b);
   u1.dbias = c.g(bp.b1); u1.N = D4; u1.K = C; u1.SL = C;
-  unfold(c, u1, "unfold_pw1");
+  unfold(c, u1, "unfold_pw1", true);
   // dvhat = da . W1f
   float *dv = c.w(pl->o_gdv), *du = c.w(pl->o_gdu);
   GemmArgs gv{};
@@ -1145,7 +1174,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
       u.W = c.p(pl->ds[i - 1].k); u.s_n = 1; u.s_k = Co; u.scale_k = c.p(pl->ds[i - 1].ln_w); u.shift_k = c.p(pl->ds[i - 1].ln_b);
       u.dWf = dwf; u.dbf = dbf; u.dW = c.g(pl->ds[i - 1].k); u.dscale = c.g(pl->ds[i - 1].ln_w);
       u.dshift = c.g(pl->ds[i - 1].ln_b); u.dbias = c.g(pl->ds[i - 1].b); u.N = Co; u.K = 4 * Ci; u.SL = Ci;
-      unfold(c, u, "unfold_ds");
+      unfold(c, u, "unfold_ds", true);
       float *dxh = c.w(pl->o_gdv);
       GemmArgs g{};
       g.A = cur; use_slot(c, g, pl->ds_slot[i - 1], true); g.out = dxh; g.M = pl->R[i]; g.N = 4 * Ci; g.K = Co; g.group_rows = 0x7fffffff;
@@ -1190,6 +1219,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
       c.post("initial_conv_wgrad");
     }
   }
+  flush_unfolds(c, parts == 7 ? 0 : (parts == 1 ? 0 : (parts == 2 ? 1 : 2)));
   pl->bwd_flip = (cur == g1) ? 1 : 0;
   int n = 0;
   rc = finish(c, &n);
