@@ -22,6 +22,8 @@ struct GemmArgs {
   const float *A;      // [M, K] row-major
   const float *Bw;     // [N, K] row-major ("weight [out, in]")
   const float *Bw_lo;  // optional low part of a TF32 hi/lo split of the weight (Bw then holds the high part); null = none
+  const float *ln_xhat;  // EPI_STORE on the tcgen05 path only: when set (with ln_rstd) the epilogue applies the LayerNorm
+  const float *ln_rstd;  // backward to the product row: out = rstd * (acc - mean(acc) - xhat * mean(acc * xhat))
   int b16;             // 3xBF16: Bw is the full fp32 weight and Bw_lo points at the packed bf16 pair (hi [N,K] | lo [N,K])
   const float *bias;   // [N] or null
   const float *resid;  // [M, N] or null (EPI_STORE)

@@ -470,6 +470,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (c0 + 8 < ncols) ld_global_v8(prep + c0 + 8, dst[2], dst[3]);
           }
         };
+        if (MODE == EPI_STORE && g.ln_rstd) {
+          // fused LayerNorm backward (the product row is dvhat): pass 1 reads the whole row for the two row means (each of
+          // the kParts warps of a lane quarter does it redundantly: no cross-warp exchange), pass 2 writes this warp's chunks
+          const float *xh = g.ln_xhat + row_off;
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+          float s1 = 0.f, s2 = 0.f;
+          for (int cc = 0; cc < ncols; cc += 16) {
+            float v[16];
+            float4 hq[4];
+            tmem_ld16(taddr + cc, v);
+            ld_global_v8(xh + cc, hq[0], hq[1]);
+            if (cc + 8 < ncols) ld_global_v8(xh + cc + 8, hq[2], hq[3]);
+            else hq[2] = hq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s1 += (v[4 * j] + v[4 * j + 1]) + (v[4 * j + 2] + v[4 * j + 3]);
+              s2 += v[4 * j] * hq[j].x + v[4 * j + 1] * hq[j].y + v[4 * j + 2] * hq[j].z + v[4 * j + 3] * hq[j].w;
+            }
+          }
+          const float inv_n = 1.f / (float)g.N;
+          s1 *= inv_n; s2 *= inv_n;
+          const float rs = __ldg(g.ln_rstd + m);
+          for (int cc = part * 16; cc < ncols; cc += 16 * kParts) {
+            float v[16];
+            float4 hq[4];
+            tmem_ld16(taddr + cc, v);
+            ld_global_v8(xh + cc, hq[0], hq[1]);
+            if (cc + 8 < ncols) ld_global_v8(xh + cc + 8, hq[2], hq[3]);
+            else hq[2] = hq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 o;
+              o.x = rs * (v[4 * j] - s1 - hq[j].x * s2); o.y = rs * (v[4 * j + 1] - s1 - hq[j].y * s2);
+              o.z = rs * (v[4 * j + 2] - s1 - hq[j].z * s2); o.w = rs * (v[4 * j + 3] - s1 - hq[j].w * s2);
+              sts_v4(srow + (((uint32_t)j ^ sx) << 4), o);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_out, sbuf, n_base + cc, row0); bulk_commit(); }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+          continue;
+        }
         int c0 = part * 16;
         float4 pre[4];
         uint32_t vr[16];
@@ -1088,6 +1137,11 @@ inline bool make_map_box32(CUtensorMap *map, const float *ptr, int64_t rows, int
 
 }  // namespace tc
 
+// the fused LayerNorm-backward epilogue needs every tile on the fast path with the whole row in one tile
+inline bool tc_ln_bwd_ok(const GemmArgs &a) {
+  return a.M % tc::BM == 0 && a.N <= 256 && a.N % 8 == 0 && a.ln_xhat && a.ln_rstd && !a.resid && !a.bias &&
+         (((uintptr_t)a.ln_xhat | (uintptr_t)a.out) & 31) == 0;
+}
 inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
   if (a.M < 1 || a.N < 8 || a.K < 8) return false;
   if (a.K % 8 != 0 || a.N % 4 != 0) return false;
@@ -1150,6 +1204,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   mo2 = mo;
   if (MODE == EPI_GELU_SQ && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
   if (!p.tma_out) mo = mo2 = ma;
+  if (a.ln_rstd && (MODE != EPI_STORE || !p.tma_out || p.num_n != 1 || !tc_ln_bwd_ok(a))) return cudaErrorInvalidConfiguration;
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {

@@ -430,6 +430,9 @@ struct Ctx {
 };
 
 // register-tiled depthwise kernels, generic kernels for the shapes they do not take
+// N <= 256 always lands in one N tile of the tcgen05 GEMM (bn = N rounded up to 16) unless shared memory forces a split;
+// the launcher re-checks (num_n == 1) and refuses otherwise
+bool pick_single_tile(const GemmArgs &a) { return a.N <= 256; }
 cudaError_t dw_launch(const DwArgs &d, const int *vis, cudaStream_t st) {
   static const bool no_pipe = getenv("MPMAE_NO_DWPIPE") != nullptr;
   cudaError_t e = no_pipe ? cudaErrorInvalidConfiguration : launch_dwconv_pipe(d, vis, st);
@@ -749,11 +752,20 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   float *dv = c.w(pl->o_gdv), *du = c.w(pl->o_gdu);
   GemmArgs gv{};
   gv.A = da; use_slot(c, gv, bw.s1, true); gv.out = dv; gv.M = R; gv.N = C; gv.K = D4; gv.group_rows = group_rows;
-  gemm<EPI_STORE>(c, gv, "dvhat");
-  if (c.ok()) {
-    c.acct(4.0 * (3.0 * R * C + R), 0);
-    launch_ln_rows_bwd(dv, c.w(bw.vhat), c.w(bw.rstd), nullptr, du, R, C, c.st);
-    c.post("ln_bwd");
+  {
+    GemmArgs gl = gv;   // LayerNorm backward fused into the epilogue when the whole row sits in one tile
+    gl.out = du; gl.ln_xhat = c.w(bw.vhat); gl.ln_rstd = c.w(bw.rstd);
+    static const bool no_fuse = getenv("MPMAE_NO_LNFUSE") != nullptr;
+    if (!no_fuse && pl->cfg.gemm_backend != 0 && tc_gemm_supported(EPI_STORE, gl) && tc_ln_bwd_ok(gl) && pick_single_tile(gl)) {
+      gemm<EPI_STORE>(c, gl, "dvhat_ln");
+    } else {
+      gemm<EPI_STORE>(c, gv, "dvhat");
+      if (c.ok()) {
+        c.acct(4.0 * (3.0 * R * C + R), 0);
+        launch_ln_rows_bwd(dv, c.w(bw.vhat), c.w(bw.rstd), nullptr, du, R, C, c.st);
+        c.post("ln_bwd");
+      }
+    }
   }
   // depthwise: dx = flipped stencil over du + dy (residual) ; dW, db
   DwArgs d{};
