@@ -31,6 +31,8 @@ struct DwArgs {
   int do_ln;           // write (u - mean) * rstd and rstd
   float eps;
   int w_in_smem;
+  float *colsum_out;   // optional [C]: += column sums of the result rows (the bias gradient of whatever consumes them);
+                       // honoured by the pipelined kernels, the dispatcher runs colsum_kernel after the others
 };
 
 // row of stage-grid pixel (gy, gx) of sample n, or -1

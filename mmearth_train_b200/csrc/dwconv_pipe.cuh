@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledA
     wreg[k] = __ldg(p.w + a * p.w_skh + b * p.w_skw + c * p.w_sc);
   }
   const float b0 = p.bias ? __ldg(p.bias + c) : 0.f;
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  static_assert((C * (P / TR)) % (C / 4) == 0, "copy-out column ownership");
 
   for (int i = 0; pu < units; pu += gridDim.x, ++i) {
     const int b = i & 1;
@@ -138,13 +140,22 @@ __global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledA
       constexpr int n4 = P * P * C / 4;
       float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
       const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
-      for (int k = threadIdx.x; k < n4; k += blockDim.x) {
+      for (int k = threadIdx.x; k < n4; k += blockDim.x) {   // blockDim.x % (C/4) == 0: a thread keeps its 4 columns
         float4 v = reinterpret_cast<const float4 *>(ubuf)[k];
         if (res) { const float4 r = __ldg(res + k); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
         dst[k] = v;
+        csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
       }
     }
     __syncthreads();   // ubuf is free again
+  }
+  if (p.colsum_out) {   // column sums of everything this CTA wrote: shared-memory reduce, one atomic per channel
+    for (int k = threadIdx.x; k < C; k += blockDim.x) ubuf[k] = 0.f;
+    __syncthreads();
+    const int c4 = (threadIdx.x % (C / 4)) * 4;
+    atomicAdd(&ubuf[c4], csum.x); atomicAdd(&ubuf[c4 + 1], csum.y); atomicAdd(&ubuf[c4 + 2], csum.z); atomicAdd(&ubuf[c4 + 3], csum.w);
+    __syncthreads();
+    for (int k = threadIdx.x; k < C; k += blockDim.x) atomicAdd(&p.colsum_out[k], ubuf[k]);
   }
 }
 
@@ -357,10 +368,21 @@ __global__ void __launch_bounds__(768) dwconv_s2_pipe_kernel(DwArgs p, const int
     const int n4 = rows * C / 4;
     float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
     const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
-    for (int i = tid; i < n4; i += blockDim.x) {
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n4; i += blockDim.x) {   // blockDim.x % (C/4) == 0 when colsum_out is set (launcher)
       float4 v = reinterpret_cast<const float4 *>(ubuf)[i];
       if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
       dst[i] = v;
+      csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+    }
+    if (p.colsum_out) {
+      __syncthreads();
+      for (int k = tid; k < C; k += blockDim.x) xs[k] = 0.f;
+      __syncthreads();
+      const int c4 = (tid % (C / 4)) * 4;
+      atomicAdd(&xs[c4], csum.x); atomicAdd(&xs[c4 + 1], csum.y); atomicAdd(&xs[c4 + 2], csum.z); atomicAdd(&xs[c4 + 3], csum.w);
+      __syncthreads();
+      for (int k = tid; k < C; k += blockDim.x) atomicAdd(&p.colsum_out[k], xs[k]);
     }
   }
 }
@@ -489,6 +511,7 @@ inline cudaError_t launch_s2_pipe(const DwArgs &a, const int *vis_patch, cudaStr
   if (npg < 1) npg = 1;
   int warps = nchunks * npg;
   if (warps * 32 < rows) warps = (rows + 31) / 32;
+  if (a.colsum_out && (a.do_ln || (warps * 32) % (a.C / 4) != 0)) return cudaErrorInvalidConfiguration;
   dwconv_s2_pipe_kernel<<<a.geo.B, warps * 32, sm, st>>>(a, vis_patch);
   return cudaGetLastError();
 }
@@ -516,7 +539,7 @@ inline cudaError_t launch_s2_wgrad_pipe(const DwWgradArgs &p, const int *vis_pat
 // Dispatch for the instantiated (P, C) pairs; cudaErrorInvalidConfiguration = not taken (caller falls back)
 inline cudaError_t launch_dwconv_pipe(const DwArgs &a, const int *vis_patch, cudaStream_t st) {
   if (!vis_patch || !a.slot_of) return cudaErrorInvalidConfiguration;
-  if (a.do_ln && a.resid) return cudaErrorInvalidConfiguration;
+  if (a.do_ln && (a.resid || a.colsum_out)) return cudaErrorInvalidConfiguration;
   DwTiledArgs t{a, vis_patch};
   if (a.P == 8 && a.C == 40) return pipe::launch_patch_pipe<8, 2, 40>(t, st);
   if (a.P == 8 && a.C == 96) return pipe::launch_patch_pipe<8, 2, 96>(t, st);

@@ -436,10 +436,15 @@ bool pick_single_tile(const GemmArgs &a) { return a.N <= 256; }
 cudaError_t dw_launch(const DwArgs &d, const int *vis, cudaStream_t st) {
   static const bool no_pipe = getenv("MPMAE_NO_DWPIPE") != nullptr;
   cudaError_t e = no_pipe ? cudaErrorInvalidConfiguration : launch_dwconv_pipe(d, vis, st);
-  if (e != cudaErrorInvalidConfiguration) return e;
+  if (e != cudaErrorInvalidConfiguration) return e;   // the pipelined kernels also produce colsum_out
   (void)cudaGetLastError();
   e = launch_dwconv_tiled(d, vis, st);
   if (e == cudaErrorInvalidConfiguration) { (void)cudaGetLastError(); e = launch_dwconv_fwd(d, st); }
+  if (e == cudaSuccess && d.colsum_out) {
+    const int64_t R = (int64_t)d.geo.B * d.geo.V * d.P * d.P;
+    launch_colsum(d.out, nullptr, d.colsum_out, R, d.C, st);
+    e = cudaGetLastError();
+  }
   return e;
 }
 cudaError_t dw_wgrad_launch(const DwWgradArgs &d, const int *vis, cudaStream_t st) {
@@ -686,8 +691,10 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
 }
 
 // Backward of one block.  dy -> dx (both [R, C]); parameter grads accumulate.
+// dy_colsum_done: sum_rows dy was already accumulated into bw.s2.dbf by the kernel that produced dy;
+// dx_colsum: where the column sums of dx go (the bias gradient of the layer that consumes dx), or null
 void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, const float *dy, float *dx, int64_t R,
-                    int C, int P, bool dense) {
+                    int C, int P, bool dense, bool dy_colsum_done = false, float *dx_colsum = nullptr) {
   mpmae_plan *pl = c.pl;
   const int D4 = 4 * C;
   const int group_rows = dense ? pl->geo.L : (int)(R > 0x7fffffff ? 0x7fffffff : R);
@@ -720,7 +727,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
     // folded pw2:  dW2f = dy^T . h, db2f = sum dy  ->  dW2, ds (= A), dbeta, db2 by the chain rule of the fold
     float *dwf2 = c.w(bw.s2.dwf), *dbf2 = c.w(bw.s2.dbf);
     WgradArgs wg{};
-    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf2; wg.db = dbf2; wg.R = R; wg.N = C; wg.K = D4;
+    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf2; wg.db = dy_colsum_done ? nullptr : dbf2; wg.R = R; wg.N = C; wg.K = D4;
     wg.exact = 1;   // ds (GRN statistic gradient) is derived from dW2f and feeds every row's gradient
     wgrad(c, wg, "dW2f");
     UnfoldArgs u{};
@@ -776,6 +783,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   d.geo = pl->geo;
   if (dense) d.geo.V = pl->geo.L;
   d.P = P; d.C = C; d.flip = 1; d.do_ln = 0; d.eps = 0.f;
+  d.colsum_out = dense ? nullptr : dx_colsum;
   c.acct(4.0 * (3.0 * R * C + 49.0 * C), 2.0 * 49 * (double)R * C);
   if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_dx");
   DwWgradArgs dwg{};
@@ -1173,14 +1181,18 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     if (!(parts & (i >= 2 ? 2 : 4))) continue;
     for (int j = cf.depths[i] - 1; j >= 0; --j) {
       const float *xin = j > 0 ? c.w(pl->bw[i][j - 1].y) : (i > 0 ? c.w(pl->o_ds_out[i - 1]) : c.w(pl->o_x0));
-      block_backward(c, pl->blk[i][j], pl->bw[i][j], xin, cur, nxt, pl->R[i], dm[i], pl->P[i], false);
+      // the depthwise dX kernel of this block also sums its output columns: the bias gradient of the pw2 of the block
+      // below, or of the downsample conv when this is the first block of the stage
+      float *dx_cs = j > 0 ? c.w(pl->bw[i][j - 1].s2.dbf) : (i > 0 ? c.w(pl->ds_slot[i - 1].dbf) : nullptr);
+      block_backward(c, pl->blk[i][j], pl->bw[i][j], xin, cur, nxt, pl->R[i], dm[i], pl->P[i], false,
+                     /*dy_colsum_done=*/j < cf.depths[i] - 1, dx_cs);
       std::swap(cur, nxt);
     }
     if (i > 0) {
       const int Ci = dm[i - 1], Co = dm[i];
       float *dwf = c.w(pl->ds_slot[i - 1].dwf), *dbf = c.w(pl->ds_slot[i - 1].dbf);
       WgradArgs w{};
-      w.X = cur; w.Y = c.w(pl->o_ds_xhat[i - 1]); w.dW = dwf; w.db = dbf; w.R = pl->R[i]; w.N = Co; w.K = 4 * Ci;
+      w.X = cur; w.Y = c.w(pl->o_ds_xhat[i - 1]); w.dW = dwf; w.db = nullptr; w.R = pl->R[i]; w.N = Co; w.K = 4 * Ci;
       wgrad(c, w, "dW_ds");
       UnfoldArgs u{};
       u.W = c.p(pl->ds[i - 1].k); u.s_n = 1; u.s_k = Co; u.scale_k = c.p(pl->ds[i - 1].ln_w); u.shift_k = c.p(pl->ds[i - 1].ln_b);
