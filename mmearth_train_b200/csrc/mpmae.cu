@@ -991,26 +991,41 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   c.post("mask");
   batched_param_folds(c, encoder_only);
 
-  {  // patch embedding: 3x3 conv + LN (+GELU, stem depthwise, LN)
+  {  // patch embedding: 3x3 conv + LN (+GELU, stem depthwise, LN); the stem is fused into the conv kernel when k = s = 1
     InitConvArgs a = init_args(c);
-    const size_t sm = ((size_t)a.Cin * 100 + 9 * (size_t)a.Cin * a.C0 + 64 * (size_t)(a.C0 + 1)) * 4;
+    StemArgs s = stem_args(c);
+    const int f4 = (a.C0 >> 2) / ln_parts(a.C0);
+    if (a.C0 % 8 != 0 || f4 < 1 || f4 > 6) return fail(MPMAE_ERR_UNSUPPORTED, "dims[0] = %d: unsupported by the patch-embedding kernel", a.C0);
+    const int fuse = (s.s2 == 1) ? 1 : 0;
+    const size_t sm = ((size_t)a.Cin * 100 + 9 * (size_t)a.Cin * a.C0 + 64 * (size_t)(a.C0 + 4) + 6 * (size_t)a.C0) * 4;
     static size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) {
       c.check(cudaFuncSetAttribute(initial_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "attr");
       configured = sm;
     }
     const int tiles = (pl->Ppre / 8) * (pl->Ppre / 8);
-    initial_conv_fwd_kernel<<<geo.B * geo.V * tiles, 32 * (a.C0 / 8), sm, c.st>>>(a);
-    c.post("initial_conv");
-    StemArgs s = stem_args(c);
-    const unsigned sg = (unsigned)cdiv64(s.R0, 8);
-    switch (cdiv(s.C0, 32)) {
-      case 1: stem_fwd_kernel<1><<<sg, 256, 0, c.st>>>(s); break;
-      case 2: stem_fwd_kernel<2><<<sg, 256, 0, c.st>>>(s); break;
-      case 3: stem_fwd_kernel<3><<<sg, 256, 0, c.st>>>(s); break;
-      default: stem_fwd_kernel<4><<<sg, 256, 0, c.st>>>(s); break;
+    const int64_t units = (int64_t)geo.B * geo.V * tiles;
+    const int threads = 32 * (a.C0 / 8);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, initial_conv_fwd_kernel, threads, sm) != cudaSuccess || per_sm < 1) {
+      (void)cudaGetLastError();
+      per_sm = 1;
     }
-    c.post("stem");
+    int64_t grid = (int64_t)148 * per_sm;
+    if (grid > units) grid = units;
+    initial_conv_fwd_kernel<<<(unsigned)grid, threads, sm, c.st>>>(a, units, s.ln0_w, s.ln0_b, s.kernel, s.bias, s.ln1_w, s.ln1_b,
+                                                                  s.shat, s.rstd_s, s.x0, fuse);
+    c.post("initial_conv");
+    if (!fuse) {
+      const unsigned sg = (unsigned)cdiv64(s.R0, 8);
+      switch (cdiv(s.C0, 32)) {
+        case 1: stem_fwd_kernel<1><<<sg, 256, 0, c.st>>>(s); break;
+        case 2: stem_fwd_kernel<2><<<sg, 256, 0, c.st>>>(s); break;
+        case 3: stem_fwd_kernel<3><<<sg, 256, 0, c.st>>>(s); break;
+        default: stem_fwd_kernel<4><<<sg, 256, 0, c.st>>>(s); break;
+      }
+      c.post("stem");
+    }
   }
   const float *x = c.w(pl->o_x0);
   for (int i = 0; i < 4; ++i) {

@@ -38,78 +38,162 @@ __device__ __forceinline__ void load_input_window(const InitConvArgs &p, int n, 
   }
 }
 
-__global__ void __launch_bounds__(512) initial_conv_fwd_kernel(InitConvArgs p) {
+struct StemArgs;
+// LayerNorm of the 64 conv outputs of a tile ((row, part) mapping of common.cuh) and, when `fuse` is set (stem k = s = 1:
+// patch 8), the whole stem on top of it: LN0 affine -> GELU -> per-channel scale + bias -> LN1 -> shat, x0.
+// vec = [ln0_w | ln0_b | kernel | bias | ln1_w | ln1_b] (6 x C0 floats in shared memory)
+template <int F4>
+__device__ __forceinline__ void embed_ln_phase(const float *cbuf, int pitch, int C0, int np, float eps, int64_t row0,
+                                               float *chat, float *rstd_c, bool fuse, const float *vec, float *shat,
+                                               float *rstd_s, float *x0) {
+  const int total = 64 * np;
+  for (int base = 0; base < total; base += (int)blockDim.x) {
+    const int item = base + (int)threadIdx.x;
+    const bool ok = item < total;
+    const int px = ok ? item / np : 0, part = ok ? item - px * np : 0;
+    const float4 *cr = reinterpret_cast<const float4 *>(cbuf + (size_t)px * pitch) + part;
+    float4 v[F4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      v[j] = ok ? cr[j * np] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = group_sum(s, np) / (float)C0;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    const float rstd = rsqrtf(group_sum(q, np) / (float)C0 + eps);
+    const int64_t row = row0 + px;
+    if (ok) {
+      float4 *o = reinterpret_cast<float4 *>(chat + row * C0) + part;
+#pragma unroll
+      for (int j = 0; j < F4; ++j) {
+        v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;
+        o[j * np] = v[j];
+      }
+      if (part == 0) rstd_c[row] = rstd;
+    }
+    if (!fuse) continue;
+    float s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      const int c = (part + j * np) * 4;
+      const float4 w0 = *reinterpret_cast<const float4 *>(vec + c), b0 = *reinterpret_cast<const float4 *>(vec + C0 + c);
+      const float4 kk = *reinterpret_cast<const float4 *>(vec + 2 * C0 + c), bb = *reinterpret_cast<const float4 *>(vec + 3 * C0 + c);
+      v[j].x = fmaf(gelu_f(fmaf(v[j].x, w0.x, b0.x)), kk.x, bb.x);
+      v[j].y = fmaf(gelu_f(fmaf(v[j].y, w0.y, b0.y)), kk.y, bb.y);
+      v[j].z = fmaf(gelu_f(fmaf(v[j].z, w0.z, b0.z)), kk.z, bb.z);
+      v[j].w = fmaf(gelu_f(fmaf(v[j].w, w0.w, b0.w)), kk.w, bb.w);
+      s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean1 = group_sum(s1, np) / (float)C0;
+    float q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < F4; ++j) {
+      v[j].x -= mean1; v[j].y -= mean1; v[j].z -= mean1; v[j].w -= mean1;
+      q1 += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    const float rstd1 = rsqrtf(group_sum(q1, np) / (float)C0 + eps);
+    if (ok) {
+      float4 *os = reinterpret_cast<float4 *>(shat + row * C0) + part;
+      float4 *ox = reinterpret_cast<float4 *>(x0 + row * C0) + part;
+#pragma unroll
+      for (int j = 0; j < F4; ++j) {
+        const int c = (part + j * np) * 4;
+        const float4 w1 = *reinterpret_cast<const float4 *>(vec + 4 * C0 + c), b1 = *reinterpret_cast<const float4 *>(vec + 5 * C0 + c);
+        const float4 nh = make_float4(v[j].x * rstd1, v[j].y * rstd1, v[j].z * rstd1, v[j].w * rstd1);
+        os[j * np] = nh;
+        ox[j * np] = make_float4(fmaf(nh.x, w1.x, b1.x), fmaf(nh.y, w1.y, b1.y), fmaf(nh.z, w1.z, b1.z), fmaf(nh.w, w1.w, b1.w));
+      }
+      if (part == 0) rstd_s[row] = rstd1;
+    }
+  }
+}
+
+// Persistent CTAs over the 8x8 pixel tiles: the 3x3 kernel is staged in shared memory once per CTA.
+// fuse_vec != null: [ln0_w | ln0_b | stem kernel | stem bias | ln1_w | ln1_b] and the stem outputs (k = s = 1 only).
+__global__ void __launch_bounds__(512) initial_conv_fwd_kernel(InitConvArgs p, int64_t units, const float *ln0_w,
+                                                               const float *ln0_b, const float *st_k, const float *st_b,
+                                                               const float *ln1_w, const float *ln1_b, float *shat,
+                                                               float *rstd_s, float *x0, int fuse) {
   extern __shared__ __align__(16) float smem[];
-  const int C0 = p.C0, Cin = p.Cin;
+  const int C0 = p.C0, Cin = p.Cin, pitch = C0 + 4;
   float *xin = smem;                       // [Cin][10][10]
   float *wsm = xin + Cin * 100;            // [9*Cin][C0]
-  float *cbuf = wsm + 9 * Cin * C0;        // [64][C0+1]
+  float *cbuf = wsm + 9 * Cin * C0;        // [64][C0+4]
+  float *vec = cbuf + 64 * pitch;          // [6][C0]
   const int tiles = (p.Ppre / 8) * (p.Ppre / 8);
-  const int pu = blockIdx.x / tiles, tile = blockIdx.x - pu * tiles;  // pu = n*V + slot
-  const int n = pu / p.geo.V;
-  const int l = p.vis_patch[pu];
-  int ty, tx;
-  morton_decode(tile, ty, tx);
-  const int gy0 = (l / p.geo.G) * p.Ppre + ty * 8, gx0 = (l % p.geo.G) * p.Ppre + tx * 8;
-  load_input_window(p, n, gy0, gx0, xin);
   for (int i = threadIdx.x; i < 9 * Cin * C0; i += blockDim.x) wsm[i] = p.kernel[i];
-  __syncthreads();
-
+  if (fuse)
+    for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+      vec[i] = ln0_w[i]; vec[C0 + i] = ln0_b[i]; vec[2 * C0 + i] = st_k[i]; vec[3 * C0 + i] = st_b[i];
+      vec[4 * C0 + i] = ln1_w[i]; vec[5 * C0 + i] = ln1_b[i];
+    }
+  const int np = ln_parts(C0), f4 = (C0 >> 2) / np;
   // thread = (vertical pixel pair, 8 output channels); blockDim.x = 32 * (C0 / 8).  Per (ci, kw) four window loads
   // serve 3 taps x 2 pixels and six 16-byte weight loads (warp-broadcast) feed 48 FMAs.
   const int pp = threadIdx.x & 31, q = threadIdx.x >> 5;
   int iy, ix;
   morton_decode(2 * pp, iy, ix);          // pixels 2pp and 2pp+1 are (iy, ix) and (iy+1, ix)
-  if (q == 0) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int ci = 0; ci < Cin; ++ci) {
-      s0 += fabsf(xin[ci * 100 + (iy + 1) * 10 + ix + 1]);
-      s1 += fabsf(xin[ci * 100 + (iy + 2) * 10 + ix + 1]);
-    }
-    if (s0 == 0.f) atomicAdd(&p.flags[0], 1);
-    if (s1 == 0.f) atomicAdd(&p.flags[0], 1);
-  }
-  {
-    float acc[2][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = p.bias[q * 8 + j];
-    for (int kw = 0; kw < 3; ++kw)
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int pu = (int)(u / tiles), tile = (int)(u - (int64_t)pu * tiles);  // pu = n*V + slot
+    const int n = pu / p.geo.V;
+    const int l = p.vis_patch[pu];
+    int ty, tx;
+    morton_decode(tile, ty, tx);
+    const int gy0 = (l / p.geo.G) * p.Ppre + ty * 8, gx0 = (l % p.geo.G) * p.Ppre + tx * 8;
+    __syncthreads();                       // previous tile's cbuf / xin readers are done (and wsm / vec are staged)
+    load_input_window(p, n, gy0, gx0, xin);
+    __syncthreads();
+    if (q == 0) {
+      float s0 = 0.f, s1 = 0.f;
       for (int ci = 0; ci < Cin; ++ci) {
-        const float *xc = xin + ci * 100 + iy * 10 + ix + kw;
-        const float x0 = xc[0], x1 = xc[10], x2 = xc[20], x3 = xc[30];
-        const float xr[4] = {x0, x1, x2, x3};
+        s0 += fabsf(xin[ci * 100 + (iy + 1) * 10 + ix + 1]);
+        s1 += fabsf(xin[ci * 100 + (iy + 2) * 10 + ix + 1]);
+      }
+      if (s0 == 0.f) atomicAdd(&p.flags[0], 1);
+      if (s1 == 0.f) atomicAdd(&p.flags[0], 1);
+    }
+    {
+      float acc[2][8];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const float *wk = wsm + (size_t)((kh + 3 * kw) * Cin + ci) * C0 + q * 8;
-          const float4 w0 = *reinterpret_cast<const float4 *>(wk);
-          const float4 w1 = *reinterpret_cast<const float4 *>(wk + 4);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = p.bias[q * 8 + j];
+      for (int kw = 0; kw < 3; ++kw)
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float *xc = xin + ci * 100 + iy * 10 + ix + kw;
+          const float xr[4] = {xc[0], xc[10], xc[20], xc[30]};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc[0][j] = fmaf(xr[kh], wv[j], acc[0][j]);
-            acc[1][j] = fmaf(xr[kh + 1], wv[j], acc[1][j]);
+          for (int kh = 0; kh < 3; ++kh) {
+            const float *wk = wsm + (size_t)((kh + 3 * kw) * Cin + ci) * C0 + q * 8;
+            const float4 w0 = *reinterpret_cast<const float4 *>(wk);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wk + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[0][j] = fmaf(xr[kh], wv[j], acc[0][j]);
+              acc[1][j] = fmaf(xr[kh + 1], wv[j], acc[1][j]);
+            }
           }
         }
-      }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      cbuf[(2 * pp) * (C0 + 1) + q * 8 + j] = acc[0][j];
-      cbuf[(2 * pp + 1) * (C0 + 1) + q * 8 + j] = acc[1][j];
+      float4 *c0p = reinterpret_cast<float4 *>(cbuf + (size_t)(2 * pp) * pitch + q * 8);
+      float4 *c1p = reinterpret_cast<float4 *>(cbuf + (size_t)(2 * pp + 1) * pitch + q * 8);
+      c0p[0] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]); c0p[1] = make_float4(acc[0][4], acc[0][5], acc[0][6], acc[0][7]);
+      c1p[0] = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]); c1p[1] = make_float4(acc[1][4], acc[1][5], acc[1][6], acc[1][7]);
     }
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
-  for (int px = warp; px < 64; px += (int)(blockDim.x >> 5)) {
-    const float *cr = cbuf + px * (C0 + 1);
-    float s = 0.f;
-    for (int c = lane; c < C0; c += 32) s += cr[c];
-    const float mean = warp_sum(s) / (float)C0;
-    float v = 0.f;
-    for (int c = lane; c < C0; c += 32) { const float d = cr[c] - mean; v += d * d; }
-    const float rstd = rsqrtf(warp_sum(v) / (float)C0 + p.eps);
-    for (int c = lane; c < C0; c += 32) p.chat[(row0 + px) * C0 + c] = (cr[c] - mean) * rstd;
-    if (lane == 0) p.rstd[row0 + px] = rstd;
+    __syncthreads();
+    const int64_t row0 = (int64_t)pu * p.Ppre * p.Ppre + tile * 64;
+    switch (f4) {
+      case 1: embed_ln_phase<1>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+      case 2: embed_ln_phase<2>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+      case 3: embed_ln_phase<3>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+      case 4: embed_ln_phase<4>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+      case 5: embed_ln_phase<5>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+      default: embed_ln_phase<6>(cbuf, pitch, C0, np, p.eps, row0, p.chat, p.rstd, fuse != 0, vec, shat, rstd_s, x0); break;
+    }
   }
 }
 
