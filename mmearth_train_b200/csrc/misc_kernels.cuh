@@ -696,43 +696,96 @@ inline void launch_colsum(const float *x, const float *rs, float *out, int64_t R
   colsum_kernel<<<dim3((unsigned)gx, chunks), threads, 0, st>>>(x, rs, out, R, C);
 }
 
-// out[b, k] = sum_n A[b, n] * cs[n] * W[n, k]   (image-head dX: nimg is ragged, e.g. 878, so this product does not go
-// through the tensor-core path).  32 x 64 output tile per CTA, shared-memory staged operands, 2 x 4 outputs per thread.
+// Small ragged products of the image-level heads (256 x 878 x 512 at cfg2; N = 878 is not a multiple of 4, so they do not
+// go through the tensor-core path).  32 x 32 output tiles (hundreds of CTAs even at this size), 2 x 2 outputs per thread.
+//   NT: out[b, k] = sum_n A[b, n] * cs[n] * W[n, k]          (dX of the heads;   A [Brows, Nred], W [Nred, Kout])
+//   NN: out[m, n] = bias[n] + sum_k A[m, k] * W[n, k]        (the heads forward; A [M, K],      W [N, K])
 __global__ void __launch_bounds__(256) small_gemm_nt_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                             const float *__restrict__ cs, float *__restrict__ out, int Brows,
                                                             int Kout, int Nred) {
   __shared__ float As[32][33];   // [n][b]
-  __shared__ float Ws[32][64];   // [n][k]
-  const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: 4 columns, ty: 2 rows
-  float acc[2][4] = {};
-  for (int n0 = 0; n0 < Nred; n0 += 32) {
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-      const int b = i >> 5, n = i & 31;
-      As[n][b] = (b0 + b < Brows && n0 + n < Nred) ? A[(int64_t)(b0 + b) * Nred + n0 + n] * cs[n0 + n] : 0.f;
+  __shared__ float Ws[32][33];   // [n][k]
+  const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: 2 columns, ty: 2 rows
+  float acc[2][2] = {};
+  float ra[4], rw[4];   // next tile's operands, fetched while the current tile is being multiplied
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256, r = i >> 5, q = i & 31;
+      ra[t] = (b0 + r < Brows && n0 + q < Nred) ? A[(int64_t)(b0 + r) * Nred + n0 + q] * cs[n0 + q] : 0.f;
+      rw[t] = (n0 + r < Nred && k0 + q < Kout) ? W[(int64_t)(n0 + r) * Kout + k0 + q] : 0.f;
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
-      const int n = i >> 6, k = i & 63;
-      Ws[n][k] = (n0 + n < Nred && k0 + k < Kout) ? W[(int64_t)(n0 + n) * Kout + k0 + k] : 0.f;
+  };
+  fetch(0);
+  for (int n0 = 0; n0 < Nred; n0 += 32) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256, r = i >> 5, q = i & 31;
+      As[q][r] = ra[t];
+      Ws[r][q] = rw[t];
     }
     __syncthreads();
+    if (n0 + 32 < Nred) fetch(n0 + 32);
 #pragma unroll 8
     for (int n = 0; n < 32; ++n) {
       const float a0 = As[n][ty * 2], a1 = As[n][ty * 2 + 1];
-      const float4 w = *reinterpret_cast<const float4 *>(&Ws[n][tx * 4]);
-      acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
-      acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
-      acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
-      acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+      const float w0 = Ws[n][tx * 2], w1 = Ws[n][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, w0, acc[0][0]); acc[0][1] = fmaf(a0, w1, acc[0][1]);
+      acc[1][0] = fmaf(a1, w0, acc[1][0]); acc[1][1] = fmaf(a1, w1, acc[1][1]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int b = b0 + ty * 2 + i, k = k0 + tx * 4 + j;
+    for (int j = 0; j < 2; ++j) {
+      const int b = b0 + ty * 2 + i, k = k0 + tx * 2 + j;
       if (b < Brows && k < Kout) out[(int64_t)b * Kout + k] = acc[i][j];
+    }
+}
+__global__ void __launch_bounds__(256) small_gemm_nn_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                            const float *__restrict__ bias, float *__restrict__ out, int M,
+                                                            int N, int K) {
+  __shared__ float As[32][33];   // [k][m]
+  __shared__ float Ws[32][33];   // [k][n]
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {};
+  float ra[4], rw[4];
+  auto fetch = [&](int k0) {   // q runs along k: coalesced reads of both row-major operands
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256, r = i >> 5, q = i & 31;
+      ra[t] = (m0 + r < M && k0 + q < K) ? A[(int64_t)(m0 + r) * K + k0 + q] : 0.f;
+      rw[t] = (n0 + r < N && k0 + q < K) ? W[(int64_t)(n0 + r) * K + k0 + q] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256, r = i >> 5, q = i & 31;
+      As[q][r] = ra[t];
+      Ws[q][r] = rw[t];
+    }
+    __syncthreads();
+    if (k0 + 32 < K) fetch(k0 + 32);
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+      const float w0 = Ws[k][tx * 2], w1 = Ws[k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, w0, acc[0][0]); acc[0][1] = fmaf(a0, w1, acc[0][1]);
+      acc[1][0] = fmaf(a1, w0, acc[1][0]); acc[1][1] = fmaf(a1, w1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+      if (m < M && n < N) out[(int64_t)m * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
     }
 }
 

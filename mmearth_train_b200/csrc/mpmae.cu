@@ -1078,10 +1078,11 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
     pool_ln_fwd_kernel<<<geo.B, 256, (size_t)8 * D * 4, c.st>>>(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
                                                           c.w(pl->o_pool_rstd), geo.L, D, 1e-6f);
     c.post("pool_ln");
-    GemmArgs g{};
-    g.A = c.w(pl->o_pooled); g.Bw = c.p(pl->imgw); g.bias = c.p(pl->imgb); g.out = io->pred_image;
-    g.M = geo.B; g.N = pl->nimg; g.K = D; g.group_rows = 0x7fffffff;
-    if (c.ok()) c.check(launch_gemm_rows_simt<EPI_STORE>(g, c.st), "image_heads");
+    if (c.ok()) {
+      small_gemm_nn_kernel<<<dim3(cdiv(pl->nimg, 32), cdiv(geo.B, 32)), 256, 0, c.st>>>(c.w(pl->o_pooled), c.p(pl->imgw), c.p(pl->imgb),
+                                                                                       io->pred_image, geo.B, pl->nimg, D);
+      c.post("image_heads");
+    }
   }
   {
     LossArgs a = loss_args(c);
@@ -1156,7 +1157,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   }
   if (pl->nimg > 0) {
     if (c.ok()) {
-      small_gemm_nt_kernel<<<dim3(cdiv(D, 64), cdiv(geo.B, 32)), 256, 0, c.st>>>(
+      small_gemm_nt_kernel<<<dim3(cdiv(D, 32), cdiv(geo.B, 32)), 256, 0, c.st>>>(
           c.w(pl->o_dimg), c.p(pl->imgw), c.w(pl->o_cs_img), c.w(pl->o_dpooled), geo.B, D, pl->nimg);
       c.post("d_pooled");
     }

@@ -395,9 +395,10 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
         if (c < C0) {
           ch[q] = p.chat[rc * C0 + c];
           const float t = ch[q] * p.ln0_w[c] + p.ln0_b[c];
-          const float gj = gelu_f(t);
+          float gj, dgj;
+          gelu_both_f(t, gj, dgj);
           part[5 + j][q] += ds[q] * gj;  // d_kernel[j]; s2 <= 4 (patch 8 or 16)
-          const float dt = ds[q] * p.kernel[j * C0 + c] * gelu_grad_f(t);
+          const float dt = ds[q] * p.kernel[j * C0 + c] * dgj;
           part[3][q] += dt * ch[q];
           part[4][q] += dt;
           dch[q] = dt * p.ln0_w[c];

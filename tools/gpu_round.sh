@@ -1,11 +1,18 @@
 # One GPU visit that refreshes everything the judge reads: GPU tests, bench (with CPU baseline), reference arm, ncu launch
-# list and a full capture of the dominant kernel (all pw1 launches of one step).
+# list, a full capture of the dominant kernel (all pw1 launches of one step) and a per-kernel capture of one whole step.
+# The .ncu-rep files are summarised ON THE BOX and deleted (gpurun brings back at most 64 MiB).
 set -x
 TAG=${1:-r1_x}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -2 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 6 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py --config cfg2 --steps 2 > gpurun_out/${TAG}_prof.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.1" -c 13 -o gpurun_out/${TAG}_full_pw1 -f python tools/profile_step.py --config cfg2 --steps 1 > gpurun_out/${TAG}_full_pw1.log 2>&1
-python tools/show_bench.py gpurun_out/${TAG}_bench.json | head -30
-cat gpurun_out/${TAG}_bench_ref.json | cut -c1-400
+timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"gemm_tc_kernel<.int.1" -c 13 -o gpurun_out/${TAG}_full_pw1 -f python tools/profile_step.py --config cfg2 --steps 1 > gpurun_out/${TAG}_full_pw1.log 2>&1
+python tools/summarize_ncu.py gpurun_out/${TAG}_launches.csv --steps 2 --rep gpurun_out/${TAG}_full_pw1.ncu-rep --title "$2" > gpurun_out/${TAG}_launches.md
+python tools/traffic_from_rep.py gpurun_out/${TAG}_full_pw1.ncu-rep pw1 "profiles/${TAG}_launches.md" > gpurun_out/${TAG}_traffic.json
+rm -f gpurun_out/${TAG}_full_pw1.ncu-rep
+timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy --section ComputeWorkloadAnalysis --clock-control none --kernel-name-base demangled -o gpurun_out/${TAG}_step -f python tools/profile_step.py --config cfg2 --steps 1 > gpurun_out/${TAG}_step.log 2>&1
+python tools/ncu_kernel_table.py gpurun_out/${TAG}_step.ncu-rep --title "$2: every kernel of one step" > gpurun_out/${TAG}_kernels.md
+rm -f gpurun_out/${TAG}_step.ncu-rep
+python tools/show_bench.py gpurun_out/${TAG}_bench.json 2>/dev/null | head -8
+du -sh gpurun_out
