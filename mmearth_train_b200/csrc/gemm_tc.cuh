@@ -204,6 +204,9 @@ struct TcParams {
   int vec8;      // N % 8 == 0 and 32-byte aligned outputs: 256-bit stores
   int vec8_in;   // same for the prefetched per-element operand
   int tma_out;   // output tensor maps are valid: the fast path stores through TMA
+  // wave-quantisation fix: the tiles beyond the last full wave of the persistent grid (tile index >= tail_start) are cut
+  // into tail_S column slices of tail_ws columns each, one slice per otherwise idle CTA
+  int tail_start, tail_items, tail_S, tail_ws;
   int b_res;     // 3xBF16 with one K block and one N tile: the weight pair is loaded once and stays resident next to the
                  // ring, whose stages then hold only the activation tile
   uint32_t tmem_cols;
@@ -262,6 +265,24 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const float4 &v) {
 // SPLIT = 3xTF32: A tiles are split in shared memory into a TF32-exact high part (in place) and the remainder
 // (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
 // tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
+struct WorkItem { int m_blk, n0, wn; };   // 128-row block, first column, column count of the MMA / epilogue
+__device__ __forceinline__ bool get_work(const TcParams &p, int it, WorkItem &w) {
+  const int idx = (int)blockIdx.x + it * (int)gridDim.x;
+  if (idx < p.tail_start) {
+    w.m_blk = idx / p.num_n;
+    w.n0 = (idx - w.m_blk * p.num_n) * p.bn;
+    w.wn = p.bn;
+    return true;
+  }
+  const int t = idx - p.tail_start;
+  if (t >= p.tail_items) return false;
+  const int tq = t / p.tail_S, tile = p.tail_start + tq;
+  w.m_blk = tile / p.num_n;
+  w.n0 = (tile - w.m_blk * p.num_n) * p.bn + (t - tq * p.tail_S) * p.tail_ws;
+  w.wn = p.tail_ws;
+  return true;
+}
+
 // BF16 (with SPLIT) = 3xBF16: a ring stage covers 64 elements of K.  Two fp32 TMA boxes of A land in the stage and the
 // splitter warps convert them IN PLACE into a bf16 high tile and a bf16 remainder tile ([128 x 64] each, 128-byte
 // swizzle); the weight arrives pre-split as bf16 (hi, lo); D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with kind::f16 MMAs -- the
@@ -270,7 +291,8 @@ template <int MODE, bool SPLIT, bool WIDE, bool BF16>
 __global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
-               const __grid_constant__ CUtensorMap map_out2, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_out2, const __grid_constant__ CUtensorMap map_bt,
+               const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) {
   constexpr int kEpiWarps = epi_warps(MODE, WIDE), kEpiThreads = 32 * kEpiWarps;
   constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE), kSplitThreads = 32 * kSplitWarps;
   constexpr int kThreadsNoSplit = 64 + kEpiThreads;
@@ -337,24 +359,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_load_2d(b_resident, &map_b, bres_bar, 0, 0);
         tma_load_2d(b_resident + b_bytes, &map_b_lo, bres_bar, 0, 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n, n_blk = tile - m_blk * p.num_n;
+      WorkItem w;
+      for (int it = 0; get_work(p, it, w); ++it) {
+        const int m_blk = w.m_blk;
+        const bool tail = w.wn != bn;
+        const uint32_t wb_bytes = (uint32_t)w.wn * BK * 4;   // bytes of one weight box of this item
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t *sa = smem + (size_t)stage * stage_bytes;
           if (BF16) {
-            mbar_expect_tx(&full_bar[stage], 2 * a_bytes + (b_res ? 0 : 2 * b_bytes));
+            mbar_expect_tx(&full_bar[stage], 2 * a_bytes + (b_res ? 0 : 2 * wb_bytes));
             tma_load_2d(sa, &map_a, &full_bar[stage], kb * 64, m_blk * BM);
             tma_load_2d(sa + a_bytes, &map_a, &full_bar[stage], kb * 64 + 32, m_blk * BM);
             if (!b_res) {
-              tma_load_2d(sa + a_span, &map_b, &full_bar[stage], kb * 64, n_blk * bn);
-              tma_load_2d(sa + a_span + b_bytes, &map_b_lo, &full_bar[stage], kb * 64, n_blk * bn);
+              tma_load_2d(sa + a_span, tail ? &map_bt : &map_b, &full_bar[stage], kb * 64, w.n0);
+              tma_load_2d(sa + a_span + b_bytes, tail ? &map_bt_lo : &map_b_lo, &full_bar[stage], kb * 64, w.n0);
             }
           } else {
-          mbar_expect_tx(&full_bar[stage], a_bytes + (SPLIT ? 2 : 1) * b_bytes);
+          mbar_expect_tx(&full_bar[stage], a_bytes + (SPLIT ? 2 : 1) * wb_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + a_span, &map_b, &full_bar[stage], kb * BK, n_blk * bn);
-          if (SPLIT) tma_load_2d(sa + a_span + b_bytes, &map_b_lo, &full_bar[stage], kb * BK, n_blk * bn);
+          tma_load_2d(sa + a_span, tail ? &map_bt : &map_b, &full_bar[stage], kb * BK, w.n0);
+          if (SPLIT) tma_load_2d(sa + a_span + b_bytes, tail ? &map_bt_lo : &map_b_lo, &full_bar[stage], kb * BK, w.n0);
           }
           if (++stage == nstage) { stage = 0; phase ^= 1; }
         }
@@ -363,11 +388,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = BF16 ? make_idesc_bf16(bn) : make_idesc(bn);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       if (b_res && (int)blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      WorkItem w;
+      for (int it = 0; get_work(p, it, w); ++it) {
+        const uint32_t idesc = BF16 ? make_idesc_bf16(w.wn) : make_idesc(w.wn);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
@@ -421,11 +447,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool single_group = (int64_t)g.group_rows >= g.M;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n, n_blk = tile - m_blk * p.num_n;
+    WorkItem w;
+    for (int it = 0; get_work(p, it, w); ++it) {
+      const int m_blk = w.m_blk;
       const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
       const bool row_ok = m < g.M;
-      const int n_base = n_blk * bn;
+      const int n_base = w.n0;
       const float *vec_bias = vec_bias_all + n_base, *vec_kg = vec_kg_all + n_base;
       const int64_t g_first = ((int64_t)m_blk * BM) / g.group_rows;
       const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
@@ -451,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       };
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
-      const int ncols = (g.N - n_base < bn) ? g.N - n_base : bn;
+      const int ncols = (g.N - n_base < w.wn) ? g.N - n_base : w.wn;
       // ---- fast path: full 128-row tile, one statistics group.  No per-element predicates; every warp stages its
       // [32 rows x 16 columns] result chunk in shared memory (64-byte swizzle: conflict-free 16-byte stores) and one lane
       // hands it to the TMA unit (cp.async.bulk.tensor store: full-sector writes, no LSU work, columns beyond N clipped);
@@ -765,7 +792,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int stid = threadIdx.x - kThreadsNoSplit;   // 0..kSplitThreads-1
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    WorkItem w;
+    for (int it = 0; get_work(p, it, w); ++it) {
       for (int kb = 0; kb < p.num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         float4 *A = reinterpret_cast<float4 *>(smem + (size_t)stage * stage_bytes);
@@ -1205,6 +1233,37 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   if (MODE == EPI_GELU_SQ && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
   if (!p.tma_out) mo = mo2 = ma;
   if (a.ln_rstd && (MODE != EPI_STORE || !p.tma_out || p.num_n != 1 || !tc_ln_bwd_ok(a))) return cudaErrorInvalidConfiguration;
+  int grid = p.num_m * p.num_n;
+  if (grid > 148) grid = 148;
+  // tail splitting (see TcParams): only when every tile takes the predicate-free epilogue path and N tiles are whole
+  const int total = p.num_m * p.num_n;
+  p.tail_start = total; p.tail_items = 0; p.tail_S = 1; p.tail_ws = p.bn;
+  CUtensorMap mbt = mb, mbtl = mbl;
+  {
+    const bool single_group = (int64_t)a.group_rows >= a.M;
+    const float *pre = MODE == EPI_STORE ? a.resid : MODE == EPI_DG ? a.aux : MODE == EPI_DH_GELU ? a.aux2 : nullptr;
+    const bool all_fast = p.tma_out && a.M % BM == 0 && (single_group || MODE == EPI_GELU_SQ || MODE == EPI_DG) &&
+                          (!pre || (a.N % 8 == 0 && p.vec8_in)) && !a.ln_rstd && a.N % p.bn == 0 && !p.b_res;
+    const int full = (total / grid) * grid, rem = total - full;
+    static const bool no_tail = getenv("MPMAE_TC_NO_TAIL") != nullptr;
+    if (all_fast && !no_tail && total > grid && rem > 0 && rem * 2 <= grid) {
+      for (int ws = 16; ws < p.bn; ws += 16) {
+        if (p.bn % ws != 0 || rem * (p.bn / ws) > grid) continue;
+        bool ok;
+        if (BF16) {
+          const uint16_t *b16 = reinterpret_cast<const uint16_t *>(a.Bw_lo);
+          ok = map_cache().get(&mbt, reinterpret_cast<const float *>(b16), a.N, a.K, -ws) &&
+               map_cache().get(&mbtl, reinterpret_cast<const float *>(b16 + (int64_t)a.N * a.K), a.N, a.K, -ws);
+        } else {
+          ok = map_cache().get(&mbt, a.Bw, a.N, a.K, ws);
+          mbtl = mbt;
+          if (ok && SPLIT) ok = map_cache().get(&mbtl, a.Bw_lo, a.N, a.K, ws);
+        }
+        if (ok) { p.tail_start = full; p.tail_S = p.bn / ws; p.tail_ws = ws; p.tail_items = rem * p.tail_S; }
+        break;
+      }
+    }
+  }
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
@@ -1212,9 +1271,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int grid = p.num_m * p.num_n;
-  if (grid > 148) grid = 148;
-  gemm_tc_kernel<MODE, SPLIT, WIDE, BF16><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, p);
+  gemm_tc_kernel<MODE, SPLIT, WIDE, BF16><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, mbt, mbtl, p);
   return cudaGetLastError();
 }
 
