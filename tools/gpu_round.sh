@@ -11,7 +11,7 @@ timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k 
 python tools/summarize_ncu.py gpurun_out/${TAG}_launches.csv --steps 2 --rep gpurun_out/${TAG}_full_pw1.ncu-rep --title "$2" > gpurun_out/${TAG}_launches.md
 python tools/traffic_from_rep.py gpurun_out/${TAG}_full_pw1.ncu-rep pw1 "profiles/${TAG}_launches.md" > gpurun_out/${TAG}_traffic.json
 rm -f gpurun_out/${TAG}_full_pw1.ncu-rep
-timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy --section ComputeWorkloadAnalysis --clock-control none --kernel-name-base demangled -o gpurun_out/${TAG}_step -f python tools/profile_step.py --config cfg2 --steps 1 > gpurun_out/${TAG}_step.log 2>&1
+timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy --section ComputeWorkloadAnalysis --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base demangled -o gpurun_out/${TAG}_step -f python tools/profile_step.py --config cfg2 --steps 1 > gpurun_out/${TAG}_step.log 2>&1
 python tools/ncu_kernel_table.py gpurun_out/${TAG}_step.ncu-rep --title "$2: every kernel of one step" > gpurun_out/${TAG}_kernels.md
 rm -f gpurun_out/${TAG}_step.ncu-rep
 python tools/show_bench.py gpurun_out/${TAG}_bench.json 2>/dev/null | head -8

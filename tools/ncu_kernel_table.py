@@ -64,13 +64,15 @@ print(f"`ncu` replay of every launch of one step ({len(rows)} launches, {tot / 1
       f"(dram__bytes_read.sum + dram__bytes_write.sum) / duration; `% of copy peak` is against the measured {peak:.0f} GB/s "
       f"(`MEASURED_PEAKS.json`).  Write-back that is still in the 126 MB L2 when a kernel ends is not counted by the DRAM "
       f"counters.\n")
-print("| kernel | launches | ms | share | DRAM MB | GB/s | % of copy peak | ncu DRAM % | SM % | tensor pipe % | warps active % | IPC | regs | smem KB |")
-print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+have_bytes = "dram__bytes_read.sum" in col
+bcols = " DRAM MB | GB/s | % of copy peak |" if have_bytes else ""
+print(f"| kernel | launches | ms | share |{bcols} ncu DRAM % | SM % | tensor pipe % | warps active % | IPC | regs | smem KB |")
+print("|---|---:|---:|---:|" + ("---:|---:|---:|" if have_bytes else "") + "---:|---:|---:|---:|---:|---:|---:|")
 for k, e in sorted(agg.items(), key=lambda kv: -kv[1]["t"]):
     t = e["t"]
     if t <= 0:
         continue
     gbs = (e["rd"] + e["wr"]) / (t * 1e-6) / 1e9
-    print(f"| `{k}` | {e['n']} | {t / 1e3:.3f} | {100 * t / tot:.1f}% | {(e['rd'] + e['wr']) / 1e6:.0f} | {gbs:.0f} | "
-          f"{100 * gbs / peak:.1f}% | {e['dram'] / t:.1f} | {e['sm'] / t:.1f} | {e['tc'] / t:.1f} | {e['occ'] / t:.1f} | "
-          f"{e['ipc'] / t:.2f} | {e['regs']} | {e['smem']:.0f} |")
+    b = f" {(e['rd'] + e['wr']) / 1e6:.0f} | {gbs:.0f} | {100 * gbs / peak:.1f}% |" if have_bytes else ""
+    print(f"| `{k}` | {e['n']} | {t / 1e3:.3f} | {100 * t / tot:.1f}% |{b} {e['dram'] / t:.1f} | {e['sm'] / t:.1f} | "
+          f"{e['tc'] / t:.1f} | {e['occ'] / t:.1f} | {e['ipc'] / t:.2f} | {e['regs']} | {e['smem']:.0f} |")
