@@ -974,13 +974,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
-constexpr int kTnThreads = 192;
+constexpr int kTnThreads = 192, kTnSplitThreads = 256;   // 8 splitter warps: both operand tiles are split every chunk
 
 // SPLIT = 3xTF32: both operand tiles are split in shared memory (hi in place, remainder in a second buffer) by four
 // splitter warps; D += Mhi.Nhi + Mlo.Nhi + Mhi.Nlo.  Used where the product feeds back into the data path (the GRN
 // statistic gradient is derived from dW2f by the chain rule of the weight fold).
 template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kTnThreads + 128 : kTnThreads, 1)
+__global__ void __launch_bounds__(SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
@@ -1000,7 +1000,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_m)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_n)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], kTnSplitThreads / 32); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1111,11 +1111,11 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else if (SPLIT) {
-    const int stid = threadIdx.x - kTnThreads;   // 0..127
+    const int stid = threadIdx.x - kTnThreads;   // 0..kTnSplitThreads-1
     int stage = 0;
     uint32_t phase = 0;
     auto split_region = [&](float4 *src, float4 *lo, int n4) {
-      for (int i = stid; i < n4; i += 128) {
+      for (int i = stid; i < n4; i += kTnSplitThreads) {
         const float4 x = src[i];
         float4 hi, l;
         hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - hi.x;
@@ -1364,7 +1364,7 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   }
   int grid = tiles * p.splits;
   if (grid > 148) grid = 148;
-  gemm_tn_tc_kernel<SPLIT><<<grid, SPLIT ? kTnThreads + 128 : kTnThreads, smem, st>>>(mm, mn, p);
+  gemm_tn_tc_kernel<SPLIT><<<grid, SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, smem, st>>>(mm, mn, p);
   return cudaGetLastError();
 }
 
