@@ -67,3 +67,48 @@ class DevicePrefetcher:
             self._free[cur_slot].record(torch.cuda.current_stream(self.device))   # everything that read the batch is queued
             if nxt is None:
                 return
+
+
+class LossReader:
+    """Per-step device -> host read of a scalar without stalling the launch queue.
+
+    The reference calls ``loss.item()`` right after the forward pass of every iteration (``engine_pretrain.py:72``), which
+    drains the GPU before the next step can even be queued.  ``push(loss)`` copies the 0-d tensor into one of ``depth`` pinned
+    host slots (non-blocking, event-tracked) and returns the value pushed ``depth`` calls earlier, whose copy has had at
+    least a whole step to land; ``flush()`` returns the values still in flight.  Every step's result is still read on the
+    host, ``depth`` steps late (engine-loop hygiene).
+    """
+
+    def __init__(self, device: torch.device, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.device = torch.device(device)
+        self.depth = depth
+        self._host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._ev = [torch.cuda.Event() for _ in range(depth)]
+        self._busy = [False] * depth
+        self._n = 0
+        self.bytes_read = 0
+
+    def _take(self, slot: int) -> float:
+        self._ev[slot].synchronize()
+        self._busy[slot] = False
+        return float(self._host[slot][0])
+
+    def push(self, value: torch.Tensor) -> Optional[float]:
+        slot = self._n % self.depth
+        out = self._take(slot) if self._busy[slot] else None
+        self._host[slot].copy_(value.detach().reshape(1), non_blocking=True)
+        self._ev[slot].record(torch.cuda.current_stream(self.device))
+        self._busy[slot] = True
+        self._n += 1
+        self.bytes_read += 4
+        return out
+
+    def flush(self) -> list:
+        out = []
+        for k in range(self.depth):
+            slot = (self._n + k) % self.depth
+            if self._busy[slot]:
+                out.append(self._take(slot))
+        return out

@@ -28,3 +28,16 @@ def test_prefetcher_rejects_cpu_target():
     from mmearth_train_b200.data import DevicePrefetcher
     with pytest.raises(ValueError):
         DevicePrefetcher(iter([]), torch.device("cpu"))
+
+
+def test_loss_reader_returns_every_value_one_step_late():
+    from mmearth_train_b200.data import LossReader
+    dev = torch.device("cuda", 0)
+    r = LossReader(dev, depth=2)
+    got = []
+    for i in range(5):
+        v = r.push(torch.tensor(float(i) + 0.5, device=dev) * 2.0)
+        if v is not None:
+            got.append(v)
+    got += r.flush()
+    assert got == [1.0, 3.0, 5.0, 7.0, 9.0] and r.bytes_read == 20
