@@ -231,11 +231,11 @@ def main():
             ms = float(t)
         return ms
 
-    for i in range(W):
-        step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # started before the warm-up so that nvidia-smi is already sampling when the timed steps run
+    for i in range(W):
+        step_resident(i)
     ms = timed(step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
     run_e2e(W)

@@ -1185,7 +1185,10 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   TcParams p{};
   p.g = a;
   // resident weights: measured no faster (the epilogue, not the operand stream, bounds these shapes): opt-in only
-  auto b_resident = [&](int bn) { return BF16 && a.K <= 64 && a.N <= bn && getenv("MPMAE_TC_BRES") != nullptr; };
+  static const bool env_bres = getenv("MPMAE_TC_BRES") != nullptr;      // environment knobs are read once per process
+  static const int env_bn = getenv("MPMAE_TC_BN") ? atoi(getenv("MPMAE_TC_BN")) : 0;
+  static const bool env_dbg = getenv("MPMAE_TC_DBG") != nullptr;        // timing experiments re-read their mask per launch
+  auto b_resident = [&](int bn) { return BF16 && a.K <= 64 && a.N <= bn && env_bres; };
   auto smem_for = [&](int bn, int stages) {
     const size_t a_stage = (size_t)(SPLIT ? 2 : 1) * BM * BK * 4, b_stage = (size_t)(SPLIT ? 2 : 1) * bn * BK * 4;
     const size_t ring = b_resident(bn) ? (size_t)stages * a_stage + b_stage : (size_t)stages * (a_stage + b_stage);
@@ -1201,7 +1204,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     if ((a.N % c == 0 || c >= a.N) && smem_for(c, 2) <= 226 * 1024) bn = c;
   for (int c = cap; c >= 16 && !bn; c -= 16)
     if (smem_for(c, 2) <= 226 * 1024) bn = c;
-  { const char *e = getenv("MPMAE_TC_BN"); if (e && atoi(e) > 0 && atoi(e) % 16 == 0 && smem_for(atoi(e), 2) <= 226 * 1024) bn = atoi(e); }
+  if (env_bn > 0 && env_bn % 16 == 0 && smem_for(env_bn, 2) <= 226 * 1024) bn = env_bn;
   if (!bn) return cudaErrorInvalidConfiguration;
   p.bn = bn;
   p.stages = 2;
@@ -1215,7 +1218,8 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   uint32_t cols = 32;
   while (cols < (uint32_t)(ACC_STAGES * p.bn)) cols <<= 1;
   p.tmem_cols = cols;
-  { const char *e = getenv("MPMAE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = 0;
+  if (env_dbg) { const char *e = getenv("MPMAE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap ma, mb, mbl, mo, mo2;
   if (!map_cache().get(&ma, a.A, a.M, a.K, BM)) return cudaErrorInvalidValue;
   if (BF16) {   // Bw_lo holds the packed bf16 pair: hi [N, K] then lo [N, K]
@@ -1324,7 +1328,8 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   const int items_target = ((int64_t)p.Msz * p.Nsz >= 32768) ? 148 : 296;
   int splits = cdiv(items_target, tiles);
   p.vec4 = (((uintptr_t)a.dW & 15) == 0 && a.K % 4 == 0) ? 1 : 0;
-  { const char *e = getenv("MPMAE_TN_ITEMS"); if (e && atoi(e) > 0) splits = cdiv(atoi(e), tiles); }
+  static const int env_items = getenv("MPMAE_TN_ITEMS") ? atoi(getenv("MPMAE_TN_ITEMS")) : 0;
+  if (env_items > 0) splits = cdiv(env_items, tiles);
   const int max_splits = cdiv(total_chunks, 8);   // >= 256 rows per item
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

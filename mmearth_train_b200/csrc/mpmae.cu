@@ -1006,11 +1006,17 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
     const int tiles = (pl->Ppre / 8) * (pl->Ppre / 8);
     const int64_t units = (int64_t)geo.B * geo.V * tiles;
     const int threads = 32 * (a.C0 / 8);
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, initial_conv_fwd_kernel, threads, sm) != cudaSuccess || per_sm < 1) {
-      (void)cudaGetLastError();
-      per_sm = 1;
+    static int occ_threads = 0, occ_per_sm = 1;
+    static size_t occ_sm = 0;
+    if (occ_threads != threads || occ_sm != sm) {   // queried once per (block size, shared memory) pair
+      int v = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, initial_conv_fwd_kernel, threads, sm) != cudaSuccess || v < 1) {
+        (void)cudaGetLastError();
+        v = 1;
+      }
+      occ_threads = threads; occ_sm = sm; occ_per_sm = v;
     }
+    const int per_sm = occ_per_sm;
     int64_t grid = (int64_t)148 * per_sm;
     if (grid > units) grid = units;
     initial_conv_fwd_kernel<<<(unsigned)grid, threads, sm, c.st>>>(a, units, s.ln0_w, s.ln0_b, s.kernel, s.bias, s.ln1_w, s.ln1_b,

@@ -136,6 +136,8 @@ class FCMAE(nn.Module):
         self._flat = torch.zeros(self._n_flat, dtype=torch.float32)
         self._gacc: Optional[torch.Tensor] = None
         self._gstep: Optional[torch.Tensor] = None
+        self._grad_views: Optional[list] = None      # persistent views of _gacc, one per parameter (built once)
+        self._grads_cleared = False                  # zero_grad(set_to_none=True) was called: next backward overwrites
         self._workspace: Optional[torch.Tensor] = None
         self._flags: Optional[torch.Tensor] = None
         self._param_list: List[nn.Parameter] = []
@@ -262,6 +264,7 @@ class FCMAE(nn.Module):
             p.data = self._flat[off:off + numel].view(shape)
             p.grad = None
         self._gacc = self._gstep = self._workspace = self._flags = None
+        self._grad_views, self._grads_cleared = None, False
         return self
 
     @property
@@ -280,13 +283,37 @@ class FCMAE(nn.Module):
                 m[off:off + numel] = 1
         return m.to(self._flat.device)
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """Gradients are views of ONE flat buffer: ``set_to_none=True`` (the reference's default, ``helpers.py:487`` /
+        ``optimizer.zero_grad()``) only marks that buffer as cleared -- the next backward overwrites it -- instead of
+        dropping and re-creating hundreds of view tensors every step (2 ms of host time at cfg2).  ``p.grad`` keeps
+        pointing at the (stale until the next backward) view."""
+        if set_to_none:
+            if self._gacc is None:
+                super().zero_grad(set_to_none=True)
+            self._grads_cleared = True
+        else:
+            if self._gacc is not None:
+                self._gacc.zero_()
+            self._grads_cleared = False
+
     def _grad_views_fresh(self) -> bool:
-        """True when every p.grad is None (zero_grad(set_to_none=True) or first step)."""
-        return all(p.grad is None for p in self._param_list)
+        """True when the next backward starts a new accumulation: zero_grad(set_to_none=True), the first step, or an
+        external optimizer that set every p.grad to None."""
+        if self._grads_cleared or self._gacc is None:
+            return True
+        first, last = self._param_list[0], self._param_list[-1]
+        if first.grad is None and last.grad is None:        # torch.optim's own zero_grad(set_to_none=True)
+            return all(p.grad is None for p in self._param_list)
+        return False
 
     def _bind_grads(self) -> None:
-        for p, (off, numel, shape) in zip(self._param_list, self._param_slices):
-            p.grad = self._gacc[off:off + numel].view(shape)
+        if self._grad_views is None or self._grad_views[0].untyped_storage().data_ptr() != self._gacc.untyped_storage().data_ptr():
+            self._grad_views = [self._gacc[off:off + numel].view(shape) for (off, numel, shape) in self._param_slices]
+        for p, g in zip(self._param_list, self._grad_views):
+            if p.grad is not g:
+                p.grad = g
+        self._grads_cleared = False
 
     # ------------------------------------------------------------------ native calls
     def _device_check(self, t: torch.Tensor) -> None:

@@ -1,6 +1,7 @@
 """Timing experiments on the tcgen05 GEMM (MPMAE_TC_DBG knobs disable pieces of the kernel; results are invalid, only the
 times mean something): which of stats / GELU / stores / tcgen05.ld / MMA / operand split bounds each shape."""
 import os, sys
+os.environ.setdefault("MPMAE_TC_DBG", "0")   # the library only re-reads the knob per launch when it is set at load time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from bench_gemm import bench
 
