@@ -73,3 +73,63 @@ def test_gemm_wgrad(native_lib, shape, backend, tol):
 
 def gu_rel(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _gelu_ref(x):
+    return 0.5 * x * (1.0 + torch.erf(x / 2.0 ** 0.5))
+
+
+def _gelu_grad_ref(x):
+    return 0.5 * (1.0 + torch.erf(x / 2.0 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2.0 * torch.pi) ** 0.5
+
+
+# (M, N, K, group_rows): full-size stage-2 shape (tile count just over a multiple of 148: tail splitting), a wide-K
+# grouped shape (per-sample statistics on the fast path), a ragged one (generic epilogue path)
+EPI_SHAPES = [(19456, 640, 160, 0), (12544 // 4, 512, 256, 49), (2500, 160, 40, 0), (38912, 160, 40, 0)]
+
+
+@pytest.mark.parametrize("backend,tol", [(0, 2e-5), (1, 1e-4), (3, 2e-4)])
+@pytest.mark.parametrize("shape", EPI_SHAPES)
+def test_gemm_epilogues(native_lib, shape, backend, tol):
+    """mpmae_gemm_epi modes 1 (bias + GELU + sum h^2) and 3 (GELU / GRN backward + column sums) against torch fp64."""
+    nat = native_lib
+    M, N, K, gr = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    b = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    G = 1 if gr == 0 else (M + gr - 1) // gr
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call(mode, **ptrs):
+        d = nat.GemmDesc()
+        for k, v in ptrs.items():
+            setattr(d, k, v.data_ptr())
+        d.M, d.N, d.K, d.group_rows = M, N, K, gr
+        nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(d), C.c_void_p(st)), "gemm_epi")
+        torch.cuda.synchronize()
+
+    scratch = torch.empty(2 * N * K, device="cuda")
+    # mode 1
+    out, out2 = torch.full((M, N), float("nan"), device="cuda"), torch.full((M, N), float("nan"), device="cuda")
+    colsum = torch.zeros(G, N, device="cuda")
+    call(1, a=a, b=b, bias=bias, out=out, out2=out2, colsum=colsum, scratch=scratch)
+    ref_a = a.double() @ b.double().t() + bias.double()
+    ref_h = _gelu_ref(ref_a)
+    assert float((out.double() - ref_a).abs().max() / ref_a.abs().max()) < tol
+    assert float((out2.double() - ref_h).abs().max() / ref_h.abs().max()) < tol
+    rows = torch.arange(M, device="cuda") // (gr if gr else M)
+    ref_cs = torch.zeros(G, N, dtype=torch.float64, device="cuda").index_add_(0, rows, ref_h ** 2)
+    assert float((colsum.double() - ref_cs).norm() / ref_cs.norm()) < tol
+    if gr:   # mode 3 takes one kg vector: single-group launches only
+        return
+    # mode 3: out = (a.b^T + kg * gelu(aux2)) * gelu'(aux2) ; colsum2 = column sums of out
+    aux2 = torch.randn(M, N, generator=g).cuda()
+    kg = torch.randn(1, N, generator=g).cuda() * 0.1
+    out3, cs2 = torch.full((M, N), float("nan"), device="cuda"), torch.zeros(N, device="cuda")
+    h2 = torch.nn.functional.gelu(aux2)          # the SIMT baseline reads h, the tcgen05 path recomputes it from aux2
+    call(3, a=a, b=b, aux=h2, aux2=aux2, kg=kg, out=out3, colsum2=cs2, scratch=scratch)
+    x2 = aux2.double()
+    ref3 = (a.double() @ b.double().t() + kg.double() * _gelu_ref(x2)) * _gelu_grad_ref(x2)
+    assert float((out3.double() - ref3).abs().max() / ref3.abs().max()) < tol
+    assert float((cs2.double() - ref3.sum(0)).norm() / ref3.sum(0).norm()) < 20 * tol   # sums of sign-mixed terms
