@@ -236,12 +236,13 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
 // warps (their K is the narrow side); the plain store epilogue is light and its K is the wide side, so it runs 8 + 8.
 // (Measured with the bf16-converting splitter: 16 + 2 is best for the forward GELU epilogue, 12 + 4 for the backward ones.)
 // 18-20 warps = 5 per scheduler keeps 96 registers per thread.
-// WIDE (K >= 256: the operand stream dominates, e.g. the decoder block) also runs 8 + 8.
+// WIDE (K >= 256, e.g. the decoder block): measured best is 8 + 8 for the forward GELU epilogue and 12 + 4 for the backward
+// ones (same as their narrow-K setting).
 __host__ __device__ constexpr int epi_warps(int mode, bool wide) {
-  return (mode == EPI_STORE || wide) ? 8 : (mode == EPI_GELU_SQ ? 16 : 12);
+  return mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 16) : 12);
 }
 __host__ __device__ constexpr int split_warps(int mode, bool split, bool wide) {
-  return !split ? 0 : ((mode == EPI_STORE || wide) ? 8 : (mode == EPI_GELU_SQ ? 2 : 4));
+  return !split ? 0 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 2) : 4));
 }
 __host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide) {
   return 64 + 32 * epi_warps(mode, wide) + 32 * split_warps(mode, split, wide);
