@@ -169,3 +169,46 @@ def test_full_size_properties_cfg2():
     # batch consistency: the first 4 samples alone give the same predictions for per-sample heads up to the
     # batch-global GRN statistic (so only check the mask / shapes here) and the same mask rows
     assert pred["sentinel2"].shape == (B, 768, 7, 7) and pred["eco_region"].shape == (B, 846)
+
+
+@pytest.mark.parametrize("backend", [3, 1])
+def test_loss_trajectory_20_steps_matches_oracle(backend):
+    """per-step total and per-modality losses over 20 optimizer steps from identical init / data / masks.
+    Native: FCMAE step + FlatAdamW; oracle: CPU restatement + torch.optim.AdamW with timm's no-decay rule
+    (main_pretrain.py:312-320).  Tolerance 1e-3 relative on every step."""
+    from mmearth_train_b200.optim import FlatAdamW
+    z, meta, orc, batch, noise = gu.inputs("atto_p8_all_unc")
+    cfg = meta["cfg"]
+    model = build_native(cfg, orc, backend)
+    lr = 3e-4
+    opt_n = FlatAdamW(model, lr=lr, betas=(0.9, 0.95), weight_decay=0.05)
+    decay, no_decay, seen = [], [], set()
+    for n, p in orc.named_parameters():
+        if id(p) in seen:
+            continue
+        seen.add(id(p))
+        (no_decay if (p.ndim <= 1 or n.endswith(".bias")) else decay).append(p)
+    opt_o = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}], lr=lr,
+                              betas=(0.9, 0.95))
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    gen = torch.Generator().manual_seed(2024)
+    worst = 0.0
+    for step in range(20):
+        nz = torch.randn(noise.shape, generator=gen)
+        model.noise_override = nz
+        loss, _, mask, ld, _, _ = model(dev_batch, mask_ratio=0.6)
+        loss.backward()
+        opt_n.step()
+        opt_n.zero_grad(set_to_none=True)
+        o_loss, _, o_mask, o_ld, _, _ = orc(batch, mask_ratio=0.6, noise=nz)
+        opt_o.zero_grad(set_to_none=True)
+        o_loss.backward()
+        opt_o.step()
+        assert torch.equal(mask.cpu(), o_mask), step
+        e = abs(float(loss) - float(o_loss)) / abs(float(o_loss))
+        worst = max(worst, e)
+        assert e < 1e-3, (step, float(loss), float(o_loss))
+        for m in meta["modalities"]:
+            a, b = float(ld[m]), float(o_ld[m])
+            assert abs(a - b) <= 1e-3 * abs(b) + 1e-6, (step, m, a, b)
+    assert float(loss) < float(z["loss"])          # and it actually trained
