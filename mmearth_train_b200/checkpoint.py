@@ -1,0 +1,80 @@
+"""Checkpoint / weight interchange.
+
+``FCMAE.state_dict()`` already uses the reference's key names and shapes (MinkowskiEngine kernel layout included), so a
+checkpoint written by either side loads on the other.  This module adds the two pieces the reference keeps in
+``helpers.py``: the sparse -> dense key / layout conversion that finetuning applies to a pretraining checkpoint
+(``helpers.remap_checkpoint_keys``, ``helpers.py:668-707``) and a save / load pair for the model + ``FlatAdamW`` state
+(``helpers.save_model`` / ``auto_load_model``, ``helpers.py:541-610``).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import torch
+
+
+def _dense_conv_weight(kernel: torch.Tensor) -> torch.Tensor:
+    """MinkowskiEngine kernel -> torch conv weight.  ME orders the taps with the FIRST spatial axis fastest
+    (k = kh + ks * kw, ``MinkowskiEngine/src/kernel_region.hpp:199-221``): dense[o, i, kh, kw] = kernel[kh + ks*kw, i, o]."""
+    if kernel.dim() == 3:                       # [ks*ks, Cin, Cout] standard convolution
+        kv, cin, cout = kernel.shape
+        ks = math.isqrt(kv)
+        return kernel.reshape(ks, ks, cin, cout).permute(3, 2, 1, 0).contiguous()      # [kw, kh, i, o] -> [o, i, kh, kw]
+    if kernel.dim() == 2:                       # [ks*ks, C] depthwise convolution
+        kv, c = kernel.shape
+        ks = math.isqrt(kv)
+        return kernel.reshape(ks, ks, c).permute(2, 1, 0).unsqueeze(1).contiguous()    # [kw, kh, c] -> [c, 1, kh, kw]
+    raise ValueError(f"unexpected kernel rank {kernel.dim()}")
+
+
+def to_dense_state_dict(ckpt: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tensor]":
+    """Sparse pretraining checkpoint -> keys / layouts of the dense ``ConvNeXtV2`` (``models/convnextv2.py``).
+
+    Same mapping as ``helpers.remap_checkpoint_keys``: the ``encoder.`` prefix goes, ``*.kernel`` becomes ``*.weight`` in
+    torch layout, the ``ln`` / ``linear`` wrapper level of the Minkowski modules goes, biases flatten to 1-D and the GRN
+    affine parameters become ``[1, 1, 1, C]``.
+    """
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, value in ckpt.items():
+        parts = key.split(".")
+        if parts[0] == "encoder":
+            parts = parts[1:]
+        if parts[-1] == "kernel":
+            out[".".join(parts[:-1] + ["weight"])] = _dense_conv_weight(value)
+            continue
+        name = ".".join(parts)
+        if "ln" in name or "linear" in name:
+            parts = parts[:-2] + parts[-1:]                 # drop the wrapper level (norm.ln.weight -> norm.weight)
+        elif "backbone.resnet." in name:
+            parts = name.split("backbone.resnet.")[1].split(".")
+        out[".".join(parts)] = value
+    for key in list(out.keys()):
+        value = out[key]
+        if key.endswith("bias") and value.dim() != 1:
+            out[key] = value.reshape(-1)
+        elif "grn" in key:
+            out[key] = value.unsqueeze(0).unsqueeze(1)
+    return out
+
+
+def save_checkpoint(path: str, model, optimizer=None, epoch: Optional[int] = None, extra: Optional[dict] = None) -> None:
+    """``{"model": state_dict, "optimizer": ..., "epoch": ...}`` -- the layout ``helpers.save_model`` writes (``helpers.py:541-547``)."""
+    blob = {"model": {k: v.detach().cpu() for k, v in model.state_dict().items()}}
+    if optimizer is not None:
+        blob["optimizer"] = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()}
+    if epoch is not None:
+        blob["epoch"] = int(epoch)
+    if extra:
+        blob.update(extra)
+    torch.save(blob, path)
+
+
+def load_checkpoint(path: str, model, optimizer=None, strict: bool = True) -> dict:
+    """Loads what :func:`save_checkpoint` (or the reference's ``save_model``) wrote; returns the remaining entries."""
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    model.load_state_dict(blob["model"], strict=strict)
+    if optimizer is not None and "optimizer" in blob and hasattr(optimizer, "load_state_dict"):
+        optimizer.load_state_dict(blob["optimizer"])
+    return {k: v for k, v in blob.items() if k not in ("model", "optimizer")}

@@ -54,6 +54,18 @@ class FlatAdamW:
                 self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, grad_scale_inv,
                 C.c_void_p(stream)), "mpmae_adamw_step")
 
+    def grad_norm(self, clip: float = None) -> torch.Tensor:
+        """2-norm of the whole gradient as a 0-d device tensor (no host sync): ``helpers.get_grad_norm_``
+        (``helpers.py:509-526``) over ONE flat buffer instead of a stack of per-parameter norms.  With ``clip`` the gradients
+        are rescaled in place like ``torch.nn.utils.clip_grad_norm_`` (``helpers.py:489-497``)."""
+        g = self.model.flat_grads
+        if g is None:
+            raise RuntimeError("no gradients: call loss.backward() first")
+        n = torch.linalg.vector_norm(g)
+        if clip is not None:
+            g.mul_(torch.clamp(clip / (n + 1e-6), max=1.0))
+        return n
+
     def state_dict(self):
         return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "t": self.t, "lr": self.lr}
 
