@@ -26,7 +26,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, SRC]
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("MPMAE_BUILD_KNOBS"):      # timing experiments of tools/dbg_sweep.py (never in the shipped library)
+        flags.append("-DMPMAE_TC_KNOBS=1")
+    cmd = [nvcc] + flags + ["-o", OUT, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "lib", "build.log")
     with open(log, "w") as f:

@@ -26,6 +26,14 @@
 
 #include "gemm_simt.cuh"
 
+// Timing knobs (tools/dbg_sweep.py): compiled in only with -DMPMAE_TC_KNOBS (build.py: MPMAE_BUILD_KNOBS=1); the
+// production build sees a constant 0 and the guarded code disappears.
+#ifdef MPMAE_TC_KNOBS
+#define TC_DBG(p) ((p).dbg)
+#else
+#define TC_DBG(p) 0
+#endif
+
 namespace mpmae {
 namespace tc {
 
@@ -407,7 +415,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
           if (BF16) {
             const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sb + b_bytes);
-            if (!(p.dbg & 32)) {
+            if (!(TC_DBG(p) & 32)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
 #pragma unroll
@@ -416,12 +424,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
             }
           } else {
-          if (!(p.dbg & 32)) {
+          if (!(TC_DBG(p) & 32)) {
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes per instruction: advance the start address by 2 (x16 B)
             umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          if (SPLIT && !(p.dbg & 32)) {
+          if (SPLIT && !(TC_DBG(p) & 32)) {
             const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sa + a_span + b_bytes);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) umma_tf32(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
@@ -555,18 +563,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (c0 < ncols) load_pre(c0, pre);
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
-        if (c0 < ncols && !(p.dbg & 8)) tmem_ld16_issue(taddr + c0, vr);
+        if (c0 < ncols && !(TC_DBG(p) & 8)) tmem_ld16_issue(taddr + c0, vr);
         for (; c0 < ncols; c0 += 16 * kParts) {
           const int cn = c0 + 16 * kParts;
           float v[16];
           float4 cur[4];
-          if (!(p.dbg & 8)) tmem_ld_wait16(vr);
+          if (!(TC_DBG(p) & 8)) tmem_ld_wait16(vr);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vr[j]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) cur[j] = pre[j];
           if (cn < ncols) {
-            if (!(p.dbg & 8)) tmem_ld16_issue(taddr + cn, vr);
+            if (!(TC_DBG(p) & 8)) tmem_ld16_issue(taddr + cn, vr);
 #pragma unroll
             for (int j = 0; j < 4; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             load_pre(cn, pre);
@@ -584,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               r = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
             } else if (MODE == EPI_GELU_SQ) {
               r = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
-              r2 = (p.dbg & 2) ? r : make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
+              r2 = (TC_DBG(p) & 2) ? r : make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
               s1[j] = r2.x * r2.x; s1[j + 1] = r2.y * r2.y; s1[j + 2] = r2.z * r2.z; s1[j + 3] = r2.w * r2.w;
             } else if (MODE == EPI_DG) {
               r = acc;
@@ -602,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             o[q4] = r; o2[q4] = r2;
           }
-          if (!(p.dbg & 4)) {
+          if (!(TC_DBG(p) & 4)) {
             if (lane == 0) bulk_wait_read0();   // the previous chunk's TMA store has finished reading the staging buffer
             __syncwarp();
 #pragma unroll
@@ -618,7 +626,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               bulk_commit();
             }
           }
-          if (p.dbg & 1) {
+          if (TC_DBG(p) & 1) {
             if (s1[0] + s1[5] + s1[10] + s1[15] + s2[3] == 123.456f) atomicAdd(&statacc1[n_base + c0 + lane], s1[7]);
             continue;
           }
@@ -808,7 +816,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           constexpr int kBandRows = 128 / kPasses;
           uint8_t *base = smem + (size_t)stage * stage_bytes;
 #pragma unroll 1
-          for (int ps = 0; ps < ((p.dbg & 64) ? 0 : kPasses); ++ps) {
+          for (int ps = 0; ps < ((TC_DBG(p) & 64) ? 0 : kPasses); ++ps) {
             float4 x[8];
             int rr[8], cc[8], hh[8];
 #pragma unroll
@@ -832,7 +840,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         } else
-        if (!(p.dbg & 64))
+        if (!(TC_DBG(p) & 64))
 #pragma unroll
         for (int i = 0; i < (int)(a_bytes / 16) / (kSplitThreads > 0 ? kSplitThreads : 1); ++i) {
           const float4 x = A[i * kSplitThreads + stid];

@@ -1,5 +1,6 @@
-"""Timing experiments on the tcgen05 GEMM (MPMAE_TC_DBG knobs disable pieces of the kernel; results are invalid, only the
-times mean something): which of stats / GELU / stores / tcgen05.ld / MMA / operand split bounds each shape."""
+"""Timing experiments on the tcgen05 GEMM (needs a library built with MPMAE_BUILD_KNOBS=1: python -c "import os;
+os.environ['MPMAE_BUILD_KNOBS']='1'; from mmearth_train_b200 import build; build.build(force=True)").  The MPMAE_TC_DBG knobs
+disable pieces of the kernel; results are invalid, only the times mean something: which of stats / GELU / stores / tcgen05.ld / MMA / operand split bounds each shape."""
 import os, sys
 os.environ.setdefault("MPMAE_TC_DBG", "0")   # the library only re-reads the knob per launch when it is set at load time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
