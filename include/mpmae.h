@@ -127,6 +127,16 @@ int mpmae_forward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
 /* FCMAE.forward_encoder (models/fcmae.py:242-247): mask + sparse encoder only; needs params, workspace,
  * noise, s2_input, mask, flags.  Read the features with mpmae_encoder_features. */
 int mpmae_forward_encoder(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
+/* The forward in stages, for the reference's step-wise methods (models/fcmae.py:242-265 forward_encoder /
+ * forward_decoder, :267-412 forward_loss).  `stages` is a mask of MPMAE_STAGE_*; stages that are left out read what an
+ * earlier call (or the caller) left in the workspace / io buffers:
+ *   MASK    noise -> mask, slot tables          (a {0,1} mask passed as noise reproduces itself: ranks are stable)
+ *   ENCODER s2_input -> encoder rows            (tap "stage3.block<last>.y", [B*V, C3], visible cells in patch order)
+ *   DECODER encoder rows -> pred_pixel / pred_image
+ *   LOSS    pred_pixel / pred_image + targets + mask -> losses
+ * Inference-style calls: mpmae_backward is only defined after a full mpmae_forward. */
+enum { MPMAE_STAGE_MASK = 1, MPMAE_STAGE_ENCODER = 2, MPMAE_STAGE_DECODER = 4, MPMAE_STAGE_LOSS = 8 };
+int mpmae_forward_stages(mpmae_plan *plan, const mpmae_io *io, int32_t stages, void *cuda_stream);
 /* hand-derived backward of the same step; accumulates into io->grads.  Must follow mpmae_forward
  * on the same workspace. */
 int mpmae_backward(mpmae_plan *plan, const mpmae_io *io, void *cuda_stream);
@@ -172,6 +182,14 @@ int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw,
 int mpmae_adamw_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                      const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
                      float weight_decay, int64_t step, float grad_scale_inv, void *cuda_stream);
+
+/* The same step with its per-step scalars in DEVICE memory, for a loss-scaler loop without the host sync of
+ * torch.cuda.amp.GradScaler.step (helpers.py:470-506): dev_state[0] = factor applied to the gradient (1 / loss scale,
+ * times a clipping coefficient), dev_state[1] != 0 = a non-finite gradient was found: parameters and moments are left
+ * untouched (the step is skipped), dev_state[2] = 1-based number of this step.  n % 4 == 0, 16-byte aligned buffers. */
+int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                         const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, const float *dev_state, void *cuda_stream);
 
 #ifdef __cplusplus
 }

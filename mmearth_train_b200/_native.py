@@ -11,6 +11,7 @@ import os
 
 MAX_MOD = 16
 PIXEL_CONTINUOUS, PIXEL_CATEGORICAL, IMAGE_CATEGORICAL, IMAGE_CONTINUOUS = 0, 1, 2, 3
+STAGE_MASK, STAGE_ENCODER, STAGE_DECODER, STAGE_LOSS = 1, 2, 4, 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmpmae.so")
@@ -74,6 +75,7 @@ def _load():
         "mpmae_profile_report": (C.c_int, [P, C.c_char_p, I32]),
         "mpmae_forward": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_forward_encoder": (C.c_int, [P, C.POINTER(IO), P]),
+        "mpmae_forward_stages": (C.c_int, [P, C.POINTER(IO), I32, P]),
         "mpmae_backward": (C.c_int, [P, C.POINTER(IO), P]),
         "mpmae_backward_part": (C.c_int, [P, C.POINTER(IO), I32, P]),
         "mpmae_backward_part_range": (C.c_int, [P, I32, C.POINTER(I64), C.POINTER(I64)]),
@@ -82,6 +84,7 @@ def _load():
         "mpmae_gemm_epi": (C.c_int, [I32, I32, C.POINTER(GemmDesc), P]),
         "mpmae_gemm_wgrad": (C.c_int, [I32, P, P, P, I64, I32, I32, P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
+        "mpmae_adamw_step_dev": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly
@@ -94,7 +97,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_adamw_step"]
+           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
 
 
 def check(rc: int, what: str = "") -> None:

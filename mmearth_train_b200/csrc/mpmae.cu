@@ -834,14 +834,21 @@ LossArgs loss_args(Ctx &c) {
   return a;
 }
 
-int check_io(const mpmae_plan *pl, const mpmae_io *io, bool backward, bool encoder_only = false) {
+// forward stages (mpmae.h: MPMAE_STAGE_*)
+constexpr int ST_MASK = 1, ST_ENC = 2, ST_DEC = 4, ST_LOSS = 8, ST_ALL = 15;
+
+int check_io(const mpmae_plan *pl, const mpmae_io *io, bool backward, int stages = ST_ALL) {
   if (!pl || !io) return fail(MPMAE_ERR_INVALID, "null plan/io");
-  if (!io->params || !io->workspace || !io->noise || !io->s2_input || !io->mask || !io->flags)
+  if (!io->params || !io->workspace || !io->mask || !io->flags)
     return fail(MPMAE_ERR_INVALID, "null device pointer in mpmae_io");
-  if (!encoder_only) {
-    if (!io->losses) return fail(MPMAE_ERR_INVALID, "losses is null");
+  if ((stages & ST_MASK) && !io->noise) return fail(MPMAE_ERR_INVALID, "noise is null");
+  if ((stages & ST_ENC) && !io->s2_input) return fail(MPMAE_ERR_INVALID, "s2_input is null");
+  if (stages & (ST_DEC | ST_LOSS)) {
     if (pl->npix > 0 && !io->pred_pixel) return fail(MPMAE_ERR_INVALID, "pred_pixel is null");
     if (pl->nimg > 0 && !io->pred_image) return fail(MPMAE_ERR_INVALID, "pred_image is null");
+  }
+  if (stages & ST_LOSS) {
+    if (!io->losses) return fail(MPMAE_ERR_INVALID, "losses is null");
     for (int m = 0; m < pl->cfg.n_mod; ++m)
       if (!io->targets[m]) return fail(MPMAE_ERR_INVALID, "target %d is null", m);
   }
@@ -974,9 +981,10 @@ int32_t mpmae_launch_count(const mpmae_plan *plan, int32_t backward) {
 }
 
 // -------------------------------------------------------------------------------------------------
-static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, bool encoder_only) {
-  int rc = check_io(pl, io, false, encoder_only);
+static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, int stages) {
+  int rc = check_io(pl, io, false, stages);
   if (rc) return rc;
+  const bool encoder_only = !(stages & ST_DEC);
   Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
   c.mark("start");
   const mpmae_cfg &cf = pl->cfg;
@@ -986,11 +994,15 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
   int *vis = reinterpret_cast<int *>(c.w(pl->o_vis));
 
   c.zero(c.w(pl->o_zero_begin), pl->o_zero_end - pl->o_zero_begin, "zero_stats");
-  c.check(cudaMemsetAsync(io->flags, 0, 4 * sizeof(int32_t), c.st), "memset", false);
-  mask_kernel<<<geo.B, 64, (size_t)geo.L * 8, c.st>>>(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
-  c.post("mask");
-  batched_param_folds(c, encoder_only);
+  if (stages & ST_MASK) {
+    c.check(cudaMemsetAsync(io->flags, 0, 4 * sizeof(int32_t), c.st), "memset", false);
+    mask_kernel<<<geo.B, 64, (size_t)geo.L * 8, c.st>>>(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
+    c.post("mask");
+  }
+  if (stages & (ST_ENC | ST_DEC)) batched_param_folds(c, encoder_only);
 
+  const float *x = c.w(pl->bw[3][cf.depths[3] - 1].y);   // encoder output rows (written by the caller when ST_ENC is off)
+  if (stages & ST_ENC) {
   {  // patch embedding: 3x3 conv + LN (+GELU, stem depthwise, LN); the stem is fused into the conv kernel when k = s = 1
     InitConvArgs a = init_args(c);
     StemArgs s = stem_args(c);
@@ -1033,7 +1045,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       c.post("stem");
     }
   }
-  const float *x = c.w(pl->o_x0);
+  x = c.w(pl->o_x0);
   for (int i = 0; i < 4; ++i) {
     if (i > 0) {  // downsample: LN + 2x2 stride-2 conv == [R/4, 4Cin] x [4Cin, Cout] on Z-ordered rows
       const int Ci = dm[i - 1], Co = dm[i];
@@ -1052,10 +1064,8 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       x = c.w(pl->bw[i][j].y);
     }
   }
-  if (encoder_only) {
-    int dummy = 0;
-    return finish(c, &dummy);
-  }
+  }  // ST_ENC
+  if (stages & ST_DEC) {
   // decoder entry: proj on visible rows, mask token elsewhere (fcmae.py:251-255)
   const int D = cf.dec_dim;
   {
@@ -1090,7 +1100,8 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
       c.post("image_heads");
     }
   }
-  {
+  }  // ST_DEC
+  if (stages & ST_LOSS) {
     LossArgs a = loss_args(c);
     if (pl->npix > 0) {
       int npm = 0;
@@ -1108,12 +1119,17 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, b
                                              cf.loss_aggr, io->losses);
     c.post("loss_finalize");
   }
-  return finish(c, &pl->launches_fwd);
+  int partial = 0;
+  return finish(c, stages == ST_ALL ? &pl->launches_fwd : &partial);
 }
 
-int mpmae_forward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) { return forward_impl(pl, io, cuda_stream, false); }
+int mpmae_forward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) { return forward_impl(pl, io, cuda_stream, ST_ALL); }
 int mpmae_forward_encoder(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) {
-  return forward_impl(pl, io, cuda_stream, true);
+  return forward_impl(pl, io, cuda_stream, ST_MASK | ST_ENC);
+}
+int mpmae_forward_stages(mpmae_plan *pl, const mpmae_io *io, int32_t stages, void *cuda_stream) {
+  if (stages <= 0 || (stages & ~ST_ALL)) return fail(MPMAE_ERR_INVALID, "stages %d: expected a non-empty MPMAE_STAGE_* mask", stages);
+  return forward_impl(pl, io, cuda_stream, stages);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1416,6 +1432,17 @@ int mpmae_adamw_step(float *params, const float *grads, float *exp_avg, float *e
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(MPMAE_ERR_INVALID, "adamw args");
   cudaError_t e = launch_adamw(params, grads, exp_avg, exp_avg_sq, decay_mask, n, lr, beta1, beta2, eps, weight_decay, step,
                                grad_scale_inv, static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "adamw: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, const uint8_t *decay_mask,
+                         int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                         const float *dev_state, void *cuda_stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !dev_state || n <= 0) return fail(MPMAE_ERR_INVALID, "adamw args");
+  cudaError_t e = launch_adamw_dev(params, grads, exp_avg, exp_avg_sq, decay_mask, n, lr, beta1, beta2, eps, weight_decay,
+                                   dev_state, static_cast<cudaStream_t>(cuda_stream));
+  if (e == cudaErrorInvalidValue) return fail(MPMAE_ERR_UNSUPPORTED, "adamw_step_dev needs n % 4 == 0 and 16-byte aligned buffers");
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "adamw: %s", cudaGetErrorString(e));
   return MPMAE_OK;
 }

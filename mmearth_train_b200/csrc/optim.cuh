@@ -46,6 +46,48 @@ __global__ void adamw_vec4_kernel(float4 *__restrict__ p, const float4 *__restri
   }
 }
 
+// The same update with the per-step scalars read from DEVICE memory, so a GradScaler-style loop (helpers.py:470-506) needs no
+// host sync: state[0] = factor applied to the gradient (1 / loss scale, times the clipping coefficient), state[1] != 0 =
+// non-finite gradient found -> the launch leaves parameters and moments untouched (GradScaler.step skips the step),
+// state[2] = 1-based number of this step (bias corrections).
+__global__ void adamw_vec4_dev_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float4 *__restrict__ m,
+                                      float4 *__restrict__ v, const uchar4 *__restrict__ decay, int64_t n4, float lr, float b1,
+                                      float b2, float eps, float wd, const float *__restrict__ state) {
+  const float ginv = state[0];
+  if (state[1] != 0.f) return;
+  const double t = (double)state[2];
+  const float bc1 = 1.f - (float)pow((double)b1, t);
+  const float bc2_sqrt = sqrtf(1.f - (float)pow((double)b2, t));
+  const float keep = 1.f - lr * wd, step = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g4 = g[i];
+    float4 p4 = p[i], m4 = m[i], v4 = v[i];
+    const uchar4 d4 = decay ? decay[i] : make_uchar4(1, 1, 1, 1);
+    auto upd = [&](float &pp, float &mm, float &vv, float gg, unsigned char dd) {
+      gg *= ginv;
+      if (dd) pp *= keep;
+      mm = b1 * mm + (1.f - b1) * gg;
+      vv = b2 * vv + (1.f - b2) * gg * gg;
+      pp -= step * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    };
+    upd(p4.x, m4.x, v4.x, g4.x, d4.x); upd(p4.y, m4.y, v4.y, g4.y, d4.y);
+    upd(p4.z, m4.z, v4.z, g4.z, d4.z); upd(p4.w, m4.w, v4.w, g4.w, d4.w);
+    p[i] = p4; m[i] = m4; v[i] = v4;
+  }
+}
+
+inline cudaError_t launch_adamw_dev(float *p, const float *g, float *m, float *v, const uint8_t *decay, int64_t n, float lr,
+                                    float b1, float b2, float eps, float wd, const float *state, cudaStream_t st) {
+  const uintptr_t al = (uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v;
+  if (n % 4 != 0 || (al & 15) != 0 || ((uintptr_t)decay & 3) != 0) return cudaErrorInvalidValue;
+  int64_t g4 = cdiv64(n / 4, 256);
+  if (g4 > 148 * 8) g4 = 148 * 8;
+  adamw_vec4_dev_kernel<<<(unsigned)g4, 256, 0, st>>>(reinterpret_cast<float4 *>(p), reinterpret_cast<const float4 *>(g),
+                                                     reinterpret_cast<float4 *>(m), reinterpret_cast<float4 *>(v),
+                                                     reinterpret_cast<const uchar4 *>(decay), n / 4, lr, b1, b2, eps, wd, state);
+  return cudaGetLastError();
+}
+
 inline cudaError_t launch_adamw(float *p, const float *g, float *m, float *v, const uint8_t *decay, int64_t n, float lr,
                                 float b1, float b2, float eps, float wd, int64_t step, float ginv, cudaStream_t st) {
   const float bc1 = 1.f - (float)pow((double)b1, (double)step);

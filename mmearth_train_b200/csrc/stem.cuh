@@ -32,7 +32,10 @@ __device__ __forceinline__ void load_input_window(const InitConvArgs &p, int n, 
     float v = 0.f;
     if (gy >= 0 && gx >= 0 && gy < p.S && gx < p.S) {
       const int l = (gy / p.Ppre) * p.geo.G + gx / p.Ppre;
-      if (p.slot_of[n * p.geo.L + l] >= 0) v = p.img[(((int64_t)n * p.Cin + ci) * p.S + gy) * p.S + gx];
+      if (p.slot_of[n * p.geo.L + l] >= 0) {
+        v = p.img[(((int64_t)n * p.Cin + ci) * p.S + gy) * p.S + gx];
+        if (!isfinite(v)) v = 0.f;   // torch.nan_to_num(nan=0, posinf=0, neginf=0) on the input, models/fcmae.py:445-449
+      }
     }
     xin[i] = v;
   }

@@ -79,30 +79,33 @@ class LossReader:
     host, ``depth`` steps late (engine-loop hygiene).
     """
 
-    def __init__(self, device: torch.device, depth: int = 2):
-        if depth < 1:
-            raise ValueError("depth must be >= 1")
+    def __init__(self, device: torch.device, depth: int = 2, width: int = 1):
+        if depth < 1 or width < 1:
+            raise ValueError("depth and width must be >= 1")
         self.device = torch.device(device)
-        self.depth = depth
-        self._host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.depth, self.width = depth, width
+        self._host = [torch.zeros(width, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self._ev = [torch.cuda.Event() for _ in range(depth)]
         self._busy = [False] * depth
         self._n = 0
         self.bytes_read = 0
 
-    def _take(self, slot: int) -> float:
+    def _take(self, slot: int):
         self._ev[slot].synchronize()
         self._busy[slot] = False
-        return float(self._host[slot][0])
+        if self.width == 1:
+            return float(self._host[slot][0])
+        return self._host[slot].tolist()
 
-    def push(self, value: torch.Tensor) -> Optional[float]:
+    def push(self, value: torch.Tensor):
+        """``value``: 0-d tensor (``width`` 1, returns floats) or a ``[width]`` vector (returns lists of floats)."""
         slot = self._n % self.depth
         out = self._take(slot) if self._busy[slot] else None
-        self._host[slot].copy_(value.detach().reshape(1), non_blocking=True)
+        self._host[slot].copy_(value.detach().reshape(self.width), non_blocking=True)
         self._ev[slot].record(torch.cuda.current_stream(self.device))
         self._busy[slot] = True
         self._n += 1
-        self.bytes_read += 4
+        self.bytes_read += 4 * self.width
         return out
 
     def flush(self) -> list:

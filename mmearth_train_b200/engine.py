@@ -1,0 +1,189 @@
+"""The training loop on the far side of the step: ``engine_pretrain.train_one_epoch`` without its per-step host syncs.
+
+The reference loop (``engine_pretrain.py:21-126``) works unchanged with the native ``FCMAE`` -- the module keeps the
+reference's surface -- but it drains the GPU several times per iteration: ``loss.item()`` plus one ``.item()`` per modality
+(``:72-75``), ``normalized_loss_list.cpu()`` (``:66-70``), ``GradScaler.step``'s non-finite check (``helpers.py:498``) and
+``torch.cuda.empty_cache()`` (``:96``), on top of H2D copies issued on the compute stream (``:59-61``).  With a 7.8 ms step
+those stalls are a visible fraction of the iteration.  ``train_one_epoch`` below has the same signature, bookkeeping and return
+value, and differs only in how the host learns what happened:
+
+* batches go through ``DevicePrefetcher`` (copy stream, persistent buffers);
+* every step's ``2T + 1`` loss values (per modality, weighted, total -- one contiguous device vector written by the loss
+  kernel) are copied to pinned memory without blocking and read ``lag`` steps later (``LossReader``), so the meters see every
+  step's values, late by ``lag`` iterations; the non-finite check (``:77-79``) fires with the same delay;
+* ``FlatGradScaler`` + ``FlatAdamW.step_dev`` keep the scale / skip decision on the device;
+* no ``empty_cache``: nothing is allocated per step.
+
+SURVEY.md section 8f ranks 1, 2 and 4.
+"""
+from __future__ import annotations
+
+import math
+import sys
+import time
+from collections import defaultdict, deque
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from .data import DevicePrefetcher, LossReader
+from .optim import cosine_lr
+
+
+class SmoothedValue:
+    """Windowed + global average of a series (the part of ``helpers.SmoothedValue`` the loop uses, ``helpers.py:33-96``)."""
+
+    def __init__(self, window_size: int = 20):
+        self.deque = deque(maxlen=window_size)
+        self.total, self.count = 0.0, 0
+
+    def update(self, value: float, n: int = 1) -> None:
+        self.deque.append(value)
+        self.count += n
+        self.total += value * n
+
+    @property
+    def value(self) -> float:
+        return self.deque[-1]
+
+    @property
+    def avg(self) -> float:
+        return sum(self.deque) / max(len(self.deque), 1)
+
+    @property
+    def global_avg(self) -> float:
+        return self.total / max(self.count, 1)
+
+    def synchronize_between_processes(self) -> None:
+        """Sum count / total over ranks (``helpers.py:51-63``)."""
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([self.count, self.total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        self.count, self.total = int(t[0].item()), float(t[1].item())
+
+
+class MetricLogger:
+    """Named meters (``helpers.MetricLogger``, ``helpers.py:99-186``), without the reference's per-iteration CUDA memory query."""
+
+    def __init__(self, delimiter: str = "  "):
+        self.meters: Dict[str, SmoothedValue] = defaultdict(SmoothedValue)
+        self.delimiter = delimiter
+
+    def add_meter(self, name: str, meter: SmoothedValue) -> None:
+        self.meters[name] = meter
+
+    def update(self, **kwargs) -> None:
+        for k, v in kwargs.items():
+            if v is None:
+                continue
+            self.meters[k].update(float(v))
+
+    def synchronize_between_processes(self) -> None:
+        for m in self.meters.values():
+            m.synchronize_between_processes()
+
+    def __str__(self) -> str:
+        return self.delimiter.join(f"{k}: {m.avg:.4f} ({m.global_avg:.4f})" for k, m in self.meters.items())
+
+
+def _len_or_none(it) -> Optional[int]:
+    try:
+        return len(it)
+    except TypeError:
+        return None
+
+
+def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, optimizer, device: torch.device, epoch: int,
+                    use_mixed: bool, loss_scaler, log_writer=None, args=None, lag: int = 2, print_freq: int = 20,
+                    quiet: bool = False):
+    """``engine_pretrain.train_one_epoch`` (``engine_pretrain.py:21-126``): same arguments (``lag`` / ``print_freq`` / ``quiet``
+    are extra), same return ``(averaged stats, loss_dict, log_var_list, normalized_loss_list)``.
+
+    ``optimizer`` = ``FlatAdamW`` and ``loss_scaler`` = ``FlatGradScaler`` (or any pair with the reference's call
+    signatures: ``helpers.NativeScalerWithGradNormCount`` + ``torch.optim.AdamW`` also work, with their syncs).
+    """
+    if use_mixed:
+        raise NotImplementedError("the native step computes in fp32 (the reference runs this path with use_mixed False: "
+                                  "MinkowskiEngine has no half kernels)")
+    model.train()
+    core = model.module if hasattr(model, "module") else model
+    device = torch.device(device)
+    metric_logger = MetricLogger()
+    metric_logger.add_meter("lr", SmoothedValue(window_size=1))
+    header = "Epoch: [{}]".format(epoch)
+    update_freq = args.update_freq
+    n_iter = _len_or_none(data_loader)
+    if n_iter is None:
+        raise TypeError("data_loader needs __len__ (the per-iteration schedule divides by it, engine_pretrain.py:53-56)")
+    T = len(core.out_modalities)
+    names = list(core.out_modalities)
+    reader = LossReader(device, depth=max(lag, 1), width=2 * T + 1)
+    last = {"loss_dict": None, "weighted": None}
+
+    def consume(vals: Optional[List[float]]) -> None:
+        if vals is None:
+            return
+        loss_value = vals[2 * T]
+        if not math.isfinite(loss_value):                                       # engine_pretrain.py:77-79
+            print("Loss is {}, stopping training".format(loss_value))
+            sys.exit(1)
+        metric_logger.update(loss=loss_value)
+        last["loss_dict"] = {m: vals[i] for i, m in enumerate(names)}
+        last["weighted"] = vals[T:2 * T]
+        if log_writer is not None:
+            log_writer.update(train_loss=_all_reduce_mean(loss_value, device), head="loss", step=consume.step)
+
+    consume.step = 0
+
+    def as_dict(data):
+        if isinstance(data, dict):
+            return data
+        if getattr(args, "no_ffcv", True):
+            return data[1]                                                       # engine_pretrain.py:50
+        return {m: data[i] for i, m in enumerate(modalities)}                    # helpers.make_modality_dict
+
+    batches = DevicePrefetcher((as_dict(d) for d in data_loader), device)
+    optimizer.zero_grad()
+    log_var_list = None
+    t0 = time.time()
+    for data_iter_step, samples in enumerate(batches):
+        if data_iter_step % update_freq == 0:                                   # per-iteration schedule, :53-56
+            lr = cosine_lr(data_iter_step / n_iter + epoch, args.lr, args.min_lr, args.warmup_epochs, args.epochs)
+            for group in optimizer.param_groups:
+                group["lr"] = lr * group["lr_scale"] if "lr_scale" in group else lr
+        loss, _pred, _mask, _loss_dict, log_var_list, _norm = model(samples, mask_ratio=args.mask_ratio)
+        consume.step = int((data_iter_step / n_iter + epoch) * 1000)            # epoch_1000x, :108
+        consume(reader.push(core.last_run["losses"]))
+        update = (data_iter_step + 1) % update_freq == 0
+        loss_scaler(loss / update_freq if update_freq != 1 else loss, optimizer, parameters=None, update_grad=update)
+        if update:
+            optimizer.zero_grad()
+        metric_logger.update(lr=optimizer.param_groups[0]["lr"])
+        if log_writer is not None and update:
+            log_writer.update(lr=optimizer.param_groups[0]["lr"], head="opt", step=consume.step)
+        if not quiet and (data_iter_step % print_freq == 0 or data_iter_step == n_iter - 1):
+            print(f"{header} [{data_iter_step}/{n_iter}]  {metric_logger}  time: {(time.time() - t0) / (data_iter_step + 1):.4f}")
+    for vals in reader.flush():
+        consume(vals)
+    metric_logger.synchronize_between_processes()
+    if not quiet:
+        print("Averaged stats:", metric_logger)
+    normalized = None
+    if last["weighted"] is not None and core.loss_aggr == "uncertainty":
+        import numpy as np
+        normalized = np.asarray(last["weighted"], dtype=np.float32)
+    return ({k: m.global_avg for k, m in metric_logger.meters.items()}, last["loss_dict"],
+            list(log_var_list) if log_var_list is not None else None, normalized)
+
+
+def _all_reduce_mean(x: float, device: torch.device) -> float:
+    """``helpers.all_reduce_mean`` (``helpers.py:393-401``)."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor(x, device=device)
+    dist.all_reduce(t)
+    return float(t.item() / dist.get_world_size())

@@ -322,40 +322,52 @@ class FCMAE(nn.Module):
         if self._flat.device != t.device:
             raise RuntimeError(f"model is on {self._flat.device}, input on {t.device}: call model.to(device) first")
 
-    def _prepare(self, imgs_dict: Dict[str, torch.Tensor], with_targets: bool = True) -> dict:
-        imgs = imgs_dict["sentinel2"]
-        self._device_check(imgs)
-        B, S = imgs.shape[0], imgs.shape[2]
-        if S != self.img_size:
-            imgs_dict = self._random_crop(imgs_dict)
+    def _targets(self, imgs_dict: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
+        targets = []
+        for m in self.out_modalities:
+            t = imgs_dict[m]
+            kind = modality_kind(m)
+            t = t.contiguous()
+            if kind in (nat.PIXEL_CATEGORICAL, nat.IMAGE_CATEGORICAL):
+                t = t.long() if t.dtype != torch.int64 else t
+            else:
+                t = t.float() if t.dtype != torch.float32 else t
+            targets.append(t)
+        return targets
+
+    def _prepare(self, imgs_dict: Optional[Dict[str, torch.Tensor]], with_targets: bool = True, with_preds: bool = True,
+                 mask: Optional[torch.Tensor] = None) -> dict:
+        """Buffers of one native call.  ``mask`` (step-wise methods): a given {0,1} mask is passed as the noise -- the
+        stable ranking of the mask kernel reproduces it -- instead of drawing new noise."""
+        if imgs_dict is not None and "sentinel2" in imgs_dict:
             imgs = imgs_dict["sentinel2"]
-        dev = imgs.device
+            self._device_check(imgs)
+            B, S = imgs.shape[0], imgs.shape[2]
+            if S != self.img_size:
+                imgs_dict = self._random_crop(imgs_dict)
+                imgs = imgs_dict["sentinel2"]
+            dev = imgs.device
+        else:
+            imgs = None
+            self._device_check(mask)
+            B, dev = mask.shape[0], mask.device
         plan = self._plan(B)
         T = len(self.out_modalities)
         run = {"B": B, "T": T, "plan": plan, "dev": dev}
-        run["s2"] = imgs.contiguous().float()
-        keep = [run["s2"]]
-        targets = []
-        if with_targets:
-            for m in self.out_modalities:
-                t = imgs_dict[m]
-                kind = modality_kind(m)
-                t = t.contiguous()
-                if kind in (nat.PIXEL_CATEGORICAL, nat.IMAGE_CATEGORICAL):
-                    t = t.long() if t.dtype != torch.int64 else t
-                else:
-                    t = t.float() if t.dtype != torch.float32 else t
-                targets.append(t)
-        run["targets"] = targets
+        run["s2"] = imgs.contiguous().float() if imgs is not None else None
+        run["targets"] = self._targets(imgs_dict) if with_targets else []
         L = self.num_patches
-        if self.noise_override is not None:                   # parity tests inject the oracle's noise
+        if mask is not None:
+            run["noise"] = mask.to(dev).float().contiguous()
+        elif self.noise_override is not None:                 # parity tests inject the oracle's noise
             run["noise"] = self.noise_override.to(dev).float().contiguous()
-            assert run["noise"].shape == (B, L)
         else:
             run["noise"] = torch.randn(B, L, device=dev)      # the reference's RNG call, fcmae.py:220
+        if run["noise"].shape != (B, L):
+            raise ValueError(f"mask / noise shape {tuple(run['noise'].shape)}, expected {(B, L)}")
         run["mask"] = torch.empty(B, L, device=dev)
-        run["pred_pixel"] = torch.empty(B * L, max(plan.npix, 1), device=dev) if with_targets else None
-        run["pred_image"] = torch.empty(B, max(plan.nimg, 1), device=dev) if with_targets else None
+        run["pred_pixel"] = torch.empty(B * L, max(plan.npix, 1), device=dev) if with_preds else None
+        run["pred_image"] = torch.empty(B, max(plan.nimg, 1), device=dev) if with_preds else None
         run["losses"] = torch.zeros(2 * T + 1, device=dev)
         need = plan.workspace_bytes
         if self._workspace is None or self._workspace.numel() * 4 < need or self._workspace.device != dev:
@@ -371,7 +383,7 @@ class FCMAE(nn.Module):
         io.workspace = self._workspace.data_ptr()
         io.workspace_bytes = self._workspace.numel() * 4
         io.noise = run["noise"].data_ptr()
-        io.s2_input = run["s2"].data_ptr()
+        io.s2_input = run["s2"].data_ptr() if run["s2"] is not None else None
         for i, t in enumerate(run["targets"]):
             io.targets[i] = t.data_ptr()
         io.mask = run["mask"].data_ptr()
@@ -472,7 +484,7 @@ class FCMAE(nn.Module):
         """``models/fcmae.py:242-247``: (dense features [B, C3, G, G] with zeros at masked cells, mask)."""
         if abs(mask_ratio - self.mask_ratio) > 1e-7:
             self.mask_ratio = mask_ratio
-        run = self._prepare({"sentinel2": imgs}, with_targets=False)
+        run = self._prepare({"sentinel2": imgs}, with_targets=False, with_preds=False)
         io = self._io(run)
         stream = torch.cuda.current_stream(run["dev"]).cuda_stream
         with torch.cuda.device(run["dev"]):
@@ -480,6 +492,92 @@ class FCMAE(nn.Module):
                       "mpmae_forward_encoder")
         self.last_run = run
         return self.encoder_features(run), run["mask"]
+
+    def _stages(self, run: dict, stages: int) -> None:
+        io = self._io(run)
+        stream = torch.cuda.current_stream(run["dev"]).cuda_stream
+        with torch.cuda.device(run["dev"]):
+            nat.check(nat.lib.mpmae_forward_stages(run["plan"].handle, C.byref(io), stages, C.c_void_p(stream)),
+                      "mpmae_forward_stages")
+
+    def _check_mask(self, mask: torch.Tensor) -> None:
+        V = int(self.num_patches * (1 - self.mask_ratio))
+        kept = (mask == 0).sum(dim=1)
+        if not bool(((mask == 0) | (mask == 1)).all()) or not bool((kept == V).all()):
+            raise ValueError(f"mask must be {{0,1}} with exactly {V} visible patches per sample (mask_ratio "
+                             f"{self.mask_ratio}); got between {int(kept.min())} and {int(kept.max())}")
+
+    def _pred_dict(self, run: dict) -> Dict[str, torch.Tensor]:
+        plan, B = run["plan"], run["B"]
+        G = self.img_size // self.patch_size
+        pred = {}
+        for i, m in enumerate(self.out_modalities):
+            off = plan.col_offset(i)
+            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL):
+                n = self.patch_size ** 2 * self.out_chans[m]
+                pred[m] = run["pred_pixel"].view(B, G, G, -1)[..., off:off + n].permute(0, 3, 1, 2)
+            else:
+                pred[m] = run["pred_image"][:, off:off + self.out_chans[m]]
+        return pred
+
+    @torch.no_grad()
+    def forward_decoder(self, x: torch.Tensor, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """``models/fcmae.py:249-265``: dense encoder features ``[B, C3, G, G]`` + mask -> predictions of every output
+        modality.  Only the visible cells of ``x`` are read (the reference overwrites the masked ones with the mask
+        token).  Step-wise inference call (no autograd); training goes through ``forward``."""
+        self._device_check(x)
+        self._check_mask(mask)
+        run = self._prepare(None, with_targets=False, mask=mask)
+        B, C3 = x.shape[0], x.shape[1]
+        rows = x.float().permute(0, 2, 3, 1).reshape(B * self.num_patches, C3)[mask.reshape(-1) == 0]
+        self.tap(f"stage3.block{self.depths[3] - 1}.y", run).copy_(rows)      # [B*V, C3], ascending patch index
+        self._stages(run, nat.STAGE_MASK | nat.STAGE_DECODER)
+        self.last_run = run
+        return self._pred_dict(run)
+
+    @torch.no_grad()
+    def forward_loss(self, imgs_dict: Dict[str, torch.Tensor], preds: Dict[str, torch.Tensor], mask: torch.Tensor):
+        """``models/fcmae.py:267-412``: per-modality reconstruction losses of given predictions + their aggregate;
+        returns ``(loss, loss_dict, log_vars, normalized_loss_list)``.  Step-wise inference call (no autograd)."""
+        self._device_check(mask)
+        self._check_mask(mask)
+        for m in self.out_modalities:
+            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL) and \
+                    tuple(imgs_dict[m].shape[-2:]) != (self.img_size, self.img_size):
+                raise ValueError(f"forward_loss: target {m!r} is {tuple(imgs_dict[m].shape)}; expected img_size "
+                                 f"{self.img_size} (models/fcmae.py:419-434 crops in forward, before the loss)")
+        run = self._prepare(None, with_targets=False, mask=mask)
+        run["targets"] = self._targets(imgs_dict)
+        plan, B, T = run["plan"], run["B"], run["T"]
+        G = self.img_size // self.patch_size
+        pix = run["pred_pixel"].view(B, G, G, -1)
+        for i, m in enumerate(self.out_modalities):
+            off = plan.col_offset(i)
+            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL):
+                n = self.patch_size ** 2 * self.out_chans[m]
+                pix[..., off:off + n].copy_(preds[m].permute(0, 2, 3, 1))
+            else:
+                run["pred_image"][:, off:off + self.out_chans[m]].copy_(preds[m])
+        self._stages(run, nat.STAGE_MASK | nat.STAGE_LOSS)
+        self.last_run = run
+        losses = run["losses"]
+        loss_dict = {m: losses[i] for i, m in enumerate(self.out_modalities)}
+        if self.loss_aggr == "uncertainty":
+            return losses[2 * T], loss_dict, _LazyList(self.loss_fn.log_vars), losses[T:2 * T]
+        return losses[2 * T], loss_dict, None, None
+
+    def upsample_mask(self, mask: torch.Tensor, scale: int) -> torch.Tensor:
+        """``models/fcmae.py:233-240``."""
+        assert len(mask.shape) == 2
+        p = int(mask.shape[1] ** 0.5)
+        return mask.reshape(-1, p, p).repeat_interleave(scale, dim=1).repeat_interleave(scale, dim=2)
+
+    def unpatchify(self, x: torch.Tensor) -> torch.Tensor:
+        """``models/fcmae.py:199-212``: ``[N, L, p*p*in_chans]`` -> ``[N, in_chans, H, W]``."""
+        p = self.patch_size
+        h = w = self.img_size // p
+        x = x.reshape(x.shape[0], h, w, p, p, self.in_chans)
+        return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], self.in_chans, h * p, h * p)
 
     def encoder_features(self, run: Optional[dict] = None) -> torch.Tensor:
         run = run or self.last_run
@@ -510,16 +608,8 @@ class FCMAE(nn.Module):
         run = self._prepare(imgs_dict)
         total, losses = _StepFunction.apply(self, run, self._ddp_token, *self._param_list)
         self.last_run = run
-        plan, B, T = run["plan"], run["B"], run["T"]
-        G = self.img_size // self.patch_size
-        pred = {}
-        for i, m in enumerate(self.out_modalities):
-            off = plan.col_offset(i)
-            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL):
-                n = self.patch_size ** 2 * self.out_chans[m]
-                pred[m] = run["pred_pixel"].view(B, G, G, -1)[..., off:off + n].permute(0, 3, 1, 2)
-            else:
-                pred[m] = run["pred_image"][:, off:off + self.out_chans[m]]
+        T = run["T"]
+        pred = self._pred_dict(run)
         loss_dict = {m: losses[i] for i, m in enumerate(self.out_modalities)}
         if self.loss_aggr == "uncertainty":
             log_vars = _LazyList(self.loss_fn.log_vars)

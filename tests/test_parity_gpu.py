@@ -212,3 +212,102 @@ def test_loss_trajectory_20_steps_matches_oracle(backend):
             a, b = float(ld[m]), float(o_ld[m])
             assert abs(a - b) <= 1e-3 * abs(b) + 1e-6, (step, m, a, b)
     assert float(loss) < float(z["loss"])          # and it actually trained
+
+
+@pytest.mark.parametrize("case", ["atto_p8_all_unc", "atto_p8_pix_unw", "atto_p8_img_unw", "atto_p16_all_unc"])
+def test_stepwise_methods_match_forward_and_oracle(case):
+    """The reference's step-wise surface (models/fcmae.py:242-412): forward_encoder -> forward_decoder -> forward_loss
+    gives what forward gives, and each step matches the oracle's method of the same name on the same inputs."""
+    z, meta, orc, batch, noise = gu.inputs(case)
+    cfg = meta["cfg"]
+    model = build_native(cfg, orc, 3)
+    model.noise_override = noise
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    loss, pred, mask, loss_dict, log_vars, weighted = model(dev_batch, mask_ratio=0.6)
+    loss, pred, mask = loss.clone(), {k: v.clone() for k, v in pred.items()}, mask.clone()
+    loss_dict = {k: v.clone() for k, v in loss_dict.items()}
+
+    x, mask2 = model.forward_encoder(dev_batch["sentinel2"], 0.6)
+    assert torch.equal(mask2, mask)
+    model.noise_override = None
+    pred2 = model.forward_decoder(x, mask2)
+    for m in meta["modalities"]:
+        assert pred2[m].shape == pred[m].shape
+        assert gu.max_rel(pred2[m], pred[m]) < 1e-4, m      # the encoder ran twice: atomics order in the GRN statistics
+    pred2 = {k: v.clone() for k, v in pred2.items()}
+    loss2, ld2, lv2, w2 = model.forward_loss(dev_batch, pred2, mask2)
+    assert abs(float(loss2) - float(loss)) <= 1e-4 * abs(float(loss))
+    for m in meta["modalities"]:
+        assert abs(float(ld2[m]) - float(loss_dict[m])) <= 1e-4 * abs(float(loss_dict[m])) + 1e-7, m
+    assert (w2 is None) == (weighted is None) and (lv2 is None) == (log_vars is None)
+
+    # oracle, step by step, from the NATIVE intermediate (so every step is checked on identical inputs)
+    clean = dict(batch)
+    for m in ("sentinel2", "sentinel1", "aster", "canopy_height_eth"):
+        if m in clean:
+            clean[m] = torch.nan_to_num(clean[m], nan=0.0, posinf=0.0, neginf=0.0)       # fcmae.py:445-449
+    with torch.no_grad():
+        o_pred, _ = orc.forward_decoder(x.cpu(), mask2.cpu())
+        o_loss, o_ld, _, o_w = orc.forward_loss(clean, {k: v.cpu() for k, v in pred2.items()}, mask2.cpu())
+    for m in meta["modalities"]:
+        assert gu.max_rel(pred2[m], o_pred[m]) < 1e-3, m
+        assert abs(float(ld2[m]) - float(o_ld[m])) <= 1e-4 * abs(float(o_ld[m])) + 1e-7, m
+    assert abs(float(loss2) - float(o_loss)) <= 1e-4 * abs(float(o_loss))
+    if o_w is not None:
+        assert gu.max_rel(w2, o_w) < 1e-4
+
+    # a mask that does not have exactly V visible patches is refused, not mis-read
+    bad = mask2.clone()
+    bad[0] = 1.0
+    with pytest.raises(ValueError):
+        model.forward_decoder(x, bad)
+    assert torch.equal(model.upsample_mask(mask2, 2)[:, ::2, ::2].reshape(mask2.shape), mask2)
+    t = torch.randn(2, model.num_patches, model.patch_size ** 2 * 12, device="cuda")
+    assert torch.equal(model.patchify(model.unpatchify(t), "sentinel2"), t)
+
+
+def test_non_finite_input_is_zeroed_like_nan_to_num():
+    """models/fcmae.py:445-449 zeroes NaN/inf of the continuous pixel modalities (the stated intent for the sentinel2
+    input too: "setting to 0 also ensures that these values become sparse").  The kernels do that on load: a batch with
+    non-finite sentinel2 values gives exactly what the cleaned batch gives, and it matches the oracle on the cleaned batch."""
+    z, meta, orc, batch, noise = gu.inputs("atto_p8_all_unc")
+    model = build_native(meta["cfg"], orc, 3)
+    model.noise_override = noise
+    dirty = {k: v.clone() for k, v in batch.items()}
+    g = torch.Generator().manual_seed(77)
+    s2 = dirty["sentinel2"]
+    r = torch.rand(s2.shape, generator=g)
+    s2[r < 0.01] = float("nan")
+    s2[(r >= 0.01) & (r < 0.015)] = float("inf")
+    s2[(r >= 0.015) & (r < 0.02)] = float("-inf")
+    clean = dict(dirty)
+    clean["sentinel2"] = torch.nan_to_num(s2, nan=0.0, posinf=0.0, neginf=0.0)
+    la = model({k: v.cuda() for k, v in dirty.items()}, mask_ratio=0.6)
+    loss_a, pred_a = la[0].clone(), {k: v.clone() for k, v in la[1].items()}
+    la[0].backward()
+    ga = model.flat_grads.clone()
+    model.zero_grad(set_to_none=True)
+    lb = model({k: v.cuda() for k, v in clean.items()}, mask_ratio=0.6)
+    lb[0].backward()
+    assert torch.isfinite(loss_a) and torch.isfinite(ga).all()
+    assert abs(float(loss_a) - float(lb[0])) <= 1e-5 * abs(float(lb[0]))      # two runs: atomics order only
+    for m in meta["modalities"]:
+        assert gu.max_rel(pred_a[m], lb[1][m]) < 1e-4, m
+    assert gu.rel_err(ga, model.flat_grads) < 1e-4
+    o_loss = orc(clean, mask_ratio=0.6, noise=noise)[0]
+    assert abs(float(loss_a) - float(o_loss)) <= 1e-3 * abs(float(o_loss))
+
+
+def test_all_visible_encoder_is_the_dense_convnextv2_encoder():
+    """mask_ratio = 0: every patch is visible and the sparse encoder equals the dense ConvNeXt-V2 feature extractor with
+    the same (re-laid-out) weights -- the consumer the reference gets by remap_checkpoint_keys (helpers.py:668-707,
+    SURVEY.md 8f rank 4).  Checked against the oracle's encoder with an all-zero mask."""
+    z, meta, orc, batch, noise = gu.inputs("atto_p8_all_unc")
+    model = build_native(meta["cfg"], orc, 3)
+    s2 = batch["sentinel2"]
+    feats, mask = model.forward_encoder(s2.cuda(), 0.0)
+    assert mask.shape == (s2.shape[0], 49) and float(mask.sum()) == 0.0
+    with torch.no_grad():
+        ref = orc.encoder(s2, torch.zeros(s2.shape[0], 49))
+    assert feats.shape == ref.shape
+    assert gu.max_rel(feats, ref) < 1e-3
