@@ -311,3 +311,46 @@ def test_all_visible_encoder_is_the_dense_convnextv2_encoder():
         ref = orc.encoder(s2, torch.zeros(s2.shape[0], 49))
     assert feats.shape == ref.shape
     assert gu.max_rel(feats, ref) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["convnextv2_femto", "convnextv2_pico", "convnextv2_nano", "convnextv2_base"])
+def test_other_model_factories_match_oracle(name):
+    """models/fcmae.py:459-496: the factories beyond atto / tiny (other channel widths through every kernel's generic or
+    templated path), one sample, forward + every gradient against the oracle."""
+    cfg = dict(model=name, img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty")
+    orc = fo.build_oracle(model=name)
+    fo.init_like_reference(orc, seed=3)
+    batch = fo.synthetic_batch(1, 56, seed=5, nan_frac=0.05)
+    noise = torch.randn(1, 49, generator=torch.Generator().manual_seed(11))
+    model = build_native(cfg, orc, 3)
+    model.noise_override = noise
+    loss, pred, mask, loss_dict, _, _ = model({k: v.cuda() for k, v in batch.items()}, mask_ratio=0.6)
+    o_loss, o_pred, o_mask, o_ld, _, _ = orc(batch, mask_ratio=0.6, noise=noise)
+    assert torch.equal(mask.cpu(), o_mask)
+    assert abs(float(loss) - float(o_loss)) <= 1e-3 * abs(float(o_loss))
+    for m in o_pred:
+        assert gu.max_rel(pred[m], o_pred[m]) < 1e-3, m
+        assert abs(float(loss_dict[m]) - float(o_ld[m])) <= 1e-3 * abs(float(o_ld[m])) + 1e-6, m
+    loss.backward()
+    ograds = gu.oracle_grads(orc, o_loss)
+    named = dict(model.named_parameters())
+    total_sq = diff_sq = 0.0
+    for pname, g in ograds.items():
+        if g is None:
+            continue
+        e, gn = gu.rel_err(named[pname].grad, g), float(g.double().norm())
+        total_sq += gn ** 2
+        diff_sq += (e * gn) ** 2
+        assert e < 3e-3 or float((named[pname].grad.cpu() - g).abs().max()) < 3e-5 * max(1.0, gn), (pname, e)
+    assert (diff_sq / total_sq) ** 0.5 < 3e-3
+
+
+@pytest.mark.parametrize("name", ["convnextv2_large", "convnextv2_huge"])
+def test_unsupported_widths_are_refused_at_construction(name):
+    """dims[0] > 128 is outside what the patch-embedding kernels are instantiated for: the factory says so when it is
+    called (no silent fallback, no wrong results)."""
+    import mmearth_train_b200 as mp
+    from mmearth_train_b200._native import NativeError
+    with pytest.raises(NativeError, match="dims"):
+        getattr(mp, name)(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True, patch_size=8,
+                          img_size=56, args=fo.make_args(None, "uncertainty"), loss_fn=mp.UncertaintyWeightingStrategy(12))
