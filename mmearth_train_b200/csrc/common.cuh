@@ -3,9 +3,48 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 namespace mpmae {
 
 constexpr int kWarp = 32;
+
+// Programmatic dependent launch.  Every kernel starts with pdl_prologue(): `launch_dependents` lets the NEXT launch of the
+// stream be scheduled while this grid is still running (its CTAs become resident as ours drain), `wait` then blocks until
+// every prerequisite grid has completed and its memory is visible -- nothing of a kernel runs before that, so the stream
+// semantics are unchanged; what overlaps is launch latency, CTA scheduling and the drain of the previous grid.  Without
+// the launch attribute both instructions are no-ops.  pdl(...) is the launch side: the triple-chevron launch of `kernel`
+// with (g, b, s, st) is spelled pdl(kernel, g, b, s, st)(args); the attribute is set when MPMAE_PDL=1.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("MPMAE_PDL"); return e ? atoi(e) != 0 : false; }();
+  return on;
+}
+template <typename K>
+struct PdlLaunch {
+  K kernel;
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <typename... Args>
+  cudaError_t operator()(Args &&...args) const {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  }
+};
+template <typename K>
+inline PdlLaunch<K> pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  return PdlLaunch<K>{kernel, grid, block, smem, stream};
+}
 
 __host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

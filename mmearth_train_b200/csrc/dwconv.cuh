@@ -47,7 +47,7 @@ __device__ __forceinline__ int64_t sparse_row(const int *slot_of, const Geo &g, 
 }
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) dwconv_fwd_kernel(DwArgs p) {
+__global__ void __launch_bounds__(NW * 32) dwconv_fwd_kernel(DwArgs p) { pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   const int C = p.C, P = p.P, G = p.geo.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -169,7 +169,7 @@ inline cudaError_t launch_dwconv_fwd(DwArgs p, cudaStream_t st) {
     configured = 227 * 1024;
   }
   const unsigned grid = (p.P == 1) ? p.geo.B : p.geo.B * p.geo.V;
-  dwconv_fwd_kernel<NW><<<grid, NW * 32, sm, st>>>(p);
+  pdl(dwconv_fwd_kernel<NW>, grid, NW * 32, sm, st)(p);
   return cudaGetLastError();
 }
 
@@ -187,7 +187,7 @@ struct DwWgradArgs {
 };
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32) dwconv_wgrad_kernel(DwWgradArgs p) {
+__global__ void __launch_bounds__(NW * 32) dwconv_wgrad_kernel(DwWgradArgs p) { pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   const int C = p.C, CC = p.CC, P = p.P, G = p.geo.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -297,7 +297,7 @@ inline cudaError_t launch_dwconv_wgrad(DwWgradArgs p, cudaStream_t st) {
   int gx = (148 * 4) / chunks;
   if (gx < 1) gx = 1;
   if (gx > units) gx = units;
-  dwconv_wgrad_kernel<NW><<<dim3(gx, chunks), NW * 32, sm, st>>>(p);
+  pdl(dwconv_wgrad_kernel<NW>, dim3(gx, chunks), NW * 32, sm, st)(p);
   return cudaGetLastError();
 }
 

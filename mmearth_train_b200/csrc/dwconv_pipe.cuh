@@ -71,7 +71,7 @@ __device__ __forceinline__ void issue_window(const float *__restrict__ x, const 
 
 // ------------------------------------------------------------------------------------------------ forward / dX
 template <int P, int TR, int C>
-__global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledArgs t, int units) {
+__global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledArgs t, int units) { pdl_prologue();
   constexpr int W = P + 6, TILES = P / TR, NPIX = W * W;
   const DwArgs &p = t.a;
   extern __shared__ __align__(128) float smem[];
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_pipe_kernel(DwTiledA
 // dW[tap, c] += sum du[o, c] * x[o + off(tap), c] ; db[c] += sum du[o, c]: 49 partial sums per thread for the whole kernel
 template <int P, int TR, int C>
 __global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_wgrad_pipe_kernel(DwWgradArgs p, const int *__restrict__ vis_patch,
-                                                                             int units) {
+                                                                             int units) { pdl_prologue();
   constexpr int W = P + 6, TILES = P / TR, NPIX = W * W, NOUT = P * P;
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar[2];
@@ -255,7 +255,7 @@ inline cudaError_t launch_patch_pipe(const DwTiledArgs &t, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > units) grid = units;
-  dwconv_patch_pipe_kernel<P, TR, C><<<grid, threads, sm, st>>>(t, units);
+  pdl(dwconv_patch_pipe_kernel<P, TR, C>, grid, threads, sm, st)(t, units);
   return cudaGetLastError();
 }
 
@@ -278,7 +278,7 @@ inline cudaError_t launch_patch_wgrad_pipe(const DwWgradArgs &p, const int *vis_
   if (per_sm < 1) per_sm = 1;
   int grid = 148 * per_sm;
   if (grid > units) grid = units;
-  dwconv_patch_wgrad_pipe_kernel<P, TR, C><<<grid, threads, sm, st>>>(p, vis_patch, units);
+  pdl(dwconv_patch_wgrad_pipe_kernel<P, TR, C>, grid, threads, sm, st)(p, vis_patch, units);
   return cudaGetLastError();
 }
 
@@ -292,7 +292,7 @@ constexpr int kS2GW = 20, kS2Cells = kS2GW * kS2GW, kS2CC = 32;
 // copy ([4V][C] floats); a 20x20 table maps every padded grid cell to the byte offset of its row (masked / outside cells
 // point at a zero row), so no dense grid is filled or cleared.  Warp = (32-channel chunk, patch subset): the 49 taps of a
 // lane's channel are loaded once; a window row of 8 cells costs four uniform 8-byte table loads + 8 data loads.
-__global__ void __launch_bounds__(768) dwconv_s2_pipe_kernel(DwArgs p, const int *__restrict__ vis_patch) {
+__global__ void __launch_bounds__(768) dwconv_s2_pipe_kernel(DwArgs p, const int *__restrict__ vis_patch) { pdl_prologue();
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(16) uint32_t tab[kS2Cells];
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(768) dwconv_s2_pipe_kernel(DwArgs p, const int
 // Weight gradient: persistent CTAs over samples, warp = (32-channel chunk, patch subset) so a lane keeps its channel's 49
 // partial sums in registers for the whole kernel.  Per sample two bulk async copies (x rows, du rows), double buffered,
 // and a cell -> row-offset table computed straight from the slot table.
-__global__ void __launch_bounds__(768) dwconv_s2_wgrad_pipe_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+__global__ void __launch_bounds__(768) dwconv_s2_wgrad_pipe_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) { pdl_prologue();
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ __align__(16) uint32_t tab[2][kS2Cells];
@@ -512,7 +512,7 @@ inline cudaError_t launch_s2_pipe(const DwArgs &a, const int *vis_patch, cudaStr
   int warps = nchunks * npg;
   if (warps * 32 < rows) warps = (rows + 31) / 32;
   if (a.colsum_out && (a.do_ln || (warps * 32) % (a.C / 4) != 0)) return cudaErrorInvalidConfiguration;
-  dwconv_s2_pipe_kernel<<<a.geo.B, warps * 32, sm, st>>>(a, vis_patch);
+  pdl(dwconv_s2_pipe_kernel, a.geo.B, warps * 32, sm, st)(a, vis_patch);
   return cudaGetLastError();
 }
 inline cudaError_t launch_s2_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {
@@ -530,7 +530,7 @@ inline cudaError_t launch_s2_wgrad_pipe(const DwWgradArgs &p, const int *vis_pat
   if (npg < 1) npg = 1;
   const int warps = nchunks * npg;
   const int grid = p.geo.B < 148 ? p.geo.B : 148;
-  dwconv_s2_wgrad_pipe_kernel<<<grid, warps * 32, sm, st>>>(p, vis_patch);
+  pdl(dwconv_s2_wgrad_pipe_kernel, grid, warps * 32, sm, st)(p, vis_patch);
   return cudaGetLastError();
 }
 

@@ -108,7 +108,7 @@ __device__ __forceinline__ void load_neighbour_slots(const int *slot_of, const G
 // ------------------------------------------------------------------------------------------------ patch flavour
 // CT = channel count known at compile time (0 = run time): shared-memory addresses become immediates
 template <int P, int TR, int CT>
-__global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
+__global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) { pdl_prologue();
   constexpr int W = P + 6, TILES = P / TR;
   const DwArgs &p = t.a;
   extern __shared__ __align__(16) float smem[];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(512) dwconv_patch_kernel(DwTiledArgs t) {
 // dW[tap, c] += sum du[o, c] * x[o + off(tap), c] ; db[c] += sum du[o, c].  Persistent CTAs: every thread keeps its
 // channel's 49 partial sums in registers across all the patches it visits.
 template <int P, int TR, int CT>
-__global__ void __launch_bounds__(512) dwconv_patch_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+__global__ void __launch_bounds__(512) dwconv_patch_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) { pdl_prologue();
   constexpr int W = P + 6, TILES = P / TR;
   extern __shared__ __align__(16) float smem[];
   __shared__ int nb[25];
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(512) dwconv_patch_wgrad_kernel(DwWgradArgs p, 
 }
 
 // ------------------------------------------------------------------------------------------------ grid flavour (P = 1, G = 7)
-__global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) {
+__global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) { pdl_prologue();
   constexpr int G = 7, L = 49;
   extern __shared__ __align__(16) float smem[];   // ubuf [V][C]
   __shared__ int slot_s[L];
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(512) dwconv_grid7_kernel(DwArgs p) {
 }
 
 // weight gradient on the 7x7 maps: thread per channel, x[49] and dW[49] in registers, persistent over samples
-__global__ void __launch_bounds__(128, 2) dwconv_grid7_wgrad_kernel(DwWgradArgs p) {
+__global__ void __launch_bounds__(128, 2) dwconv_grid7_wgrad_kernel(DwWgradArgs p) { pdl_prologue();
   constexpr int G = 7, L = 49;
   __shared__ int slot_s[L];
   const int C = p.C, V = p.geo.V;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(128, 2) dwconv_grid7_wgrad_kernel(DwWgradArgs 
 // is loaded exactly once, and one thread computes a 2x2 patch of one channel from an 8x8 register window
 // (64 shared loads for 196 FMAs).  The [76, C] result tile collects all chunks, then LayerNorm + coalesced copy-out.
 template <int CC>
-__global__ void __launch_bounds__(512) dwconv_s2_kernel(DwArgs p, const int *__restrict__ vis_patch) {
+__global__ void __launch_bounds__(512) dwconv_s2_kernel(DwArgs p, const int *__restrict__ vis_patch) { pdl_prologue();
   constexpr int GW = 20, NCELL = GW * GW, CC4 = CC / 4;
   constexpr int NT = (512 / CC) * CC, NPG = NT / CC;
   extern __shared__ __align__(16) float smem[];
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(512) dwconv_s2_kernel(DwArgs p, const int *__r
 // weight gradient, same staging; blockIdx.y = channel chunk, blockIdx.x strides samples; every thread keeps its channel's
 // 49 partial sums in registers across all the patches and samples it visits
 template <int CC>
-__global__ void __launch_bounds__(512) dwconv_s2_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) {
+__global__ void __launch_bounds__(512) dwconv_s2_wgrad_kernel(DwWgradArgs p, const int *__restrict__ vis_patch) { pdl_prologue();
   constexpr int GW = 20, NCELL = GW * GW, CC4 = CC / 4;
   constexpr int NT = (512 / CC) * CC, NPG = NT / CC;
   extern __shared__ __align__(16) float smem[];
@@ -568,7 +568,7 @@ inline cudaError_t launch_s2(const DwArgs &a, const int *vis_patch, cudaStream_t
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dwconv_s2_kernel<CC><<<a.geo.B, (512 / CC) * CC, sm, st>>>(a, vis_patch);
+  pdl(dwconv_s2_kernel<CC>, a.geo.B, (512 / CC) * CC, sm, st)(a, vis_patch);
   return cudaGetLastError();
 }
 template <int CC>
@@ -587,7 +587,7 @@ inline cudaError_t launch_s2_wgrad(const DwWgradArgs &p, const int *vis_patch, c
   int gx = (148 * per_sm) / chunks;
   if (gx < 1) gx = 1;
   if (gx > p.geo.B) gx = p.geo.B;
-  dwconv_s2_wgrad_kernel<CC><<<dim3(gx, chunks), (512 / CC) * CC, sm, st>>>(p, vis_patch);
+  pdl(dwconv_s2_wgrad_kernel<CC>, dim3(gx, chunks), (512 / CC) * CC, sm, st)(p, vis_patch);
   return cudaGetLastError();
 }
 inline int s2_chunk(int C) {
@@ -611,7 +611,7 @@ inline cudaError_t launch_patch(const DwTiledArgs &t, cudaStream_t st) {
     (void)cudaFuncSetAttribute(dwconv_patch_kernel<P, TR, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
-  dwconv_patch_kernel<P, TR, CT><<<t.a.geo.B * t.a.geo.V, threads, sm, st>>>(t);
+  pdl(dwconv_patch_kernel<P, TR, CT>, t.a.geo.B * t.a.geo.V, threads, sm, st)(t);
   return cudaGetLastError();
 }
 
@@ -635,7 +635,7 @@ inline cudaError_t launch_patch_wgrad(const DwWgradArgs &p, const int *vis_patch
   int grid = 148 * per_sm;
   const int units = p.geo.B * p.geo.V;
   if (grid > units) grid = units;
-  dwconv_patch_wgrad_kernel<P, TR, CT><<<grid, threads, sm, st>>>(p, vis_patch);
+  pdl(dwconv_patch_wgrad_kernel<P, TR, CT>, grid, threads, sm, st)(p, vis_patch);
   return cudaGetLastError();
 }
 
@@ -654,7 +654,7 @@ inline cudaError_t launch_dwconv_tiled(const DwArgs &a, const int *vis_patch, cu
     }
     int threads = ((a.C + 31) / 32) * 32;
     if (threads > 512) threads = 512;
-    dwconv_grid7_kernel<<<a.geo.B, threads, sm, st>>>(a);
+    pdl(dwconv_grid7_kernel, a.geo.B, threads, sm, st)(a);
     return cudaGetLastError();
   }
   if (!vis_patch || !a.slot_of) return cudaErrorInvalidConfiguration;
@@ -693,7 +693,7 @@ inline cudaError_t launch_dwconv_wgrad_tiled(const DwWgradArgs &p, const int *vi
     int gx = (148 * 4) / cy;
     if (gx < 1) gx = 1;
     if (gx > p.geo.B) gx = p.geo.B;
-    dwconv_grid7_wgrad_kernel<<<dim3(gx, cy), threads, 0, st>>>(p);
+    pdl(dwconv_grid7_wgrad_kernel, dim3(gx, cy), threads, 0, st)(p);
     return cudaGetLastError();
   }
   if (!vis_patch || !p.slot_of) return cudaErrorInvalidConfiguration;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void colacc_add(float *colacc, int bn, int col, int g
 }
 
 template <int NT, int TN, int MODE>
-__global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) {
+__global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) { pdl_prologue();
   constexpr int BM = 128, TM = 8, BK = 8, BN = NT * TN, NTHR = 16 * NT;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -188,13 +188,13 @@ inline cudaError_t launch_gemm_rows_simt(const GemmArgs &p, cudaStream_t st) {
   if (p.M <= 0) return cudaSuccess;
   const unsigned gm = (unsigned)cdiv64(p.M, 128);
   if (p.N % 80 == 0) {
-    gemm_rows_kernel<16, 5, MODE><<<dim3(gm, p.N / 80), 256, 0, st>>>(p);
+    pdl(gemm_rows_kernel<16, 5, MODE>, dim3(gm, p.N / 80), 256, 0, st)(p);
   } else if (p.N % 64 == 0 || p.N > 64) {
-    gemm_rows_kernel<16, 4, MODE><<<dim3(gm, cdiv(p.N, 64)), 256, 0, st>>>(p);
+    pdl(gemm_rows_kernel<16, 4, MODE>, dim3(gm, cdiv(p.N, 64)), 256, 0, st)(p);
   } else if (p.N % 40 == 0 || p.N > 32) {
-    gemm_rows_kernel<8, 5, MODE><<<dim3(gm, cdiv(p.N, 40)), 128, 0, st>>>(p);
+    pdl(gemm_rows_kernel<8, 5, MODE>, dim3(gm, cdiv(p.N, 40)), 128, 0, st)(p);
   } else {
-    gemm_rows_kernel<8, 4, MODE><<<dim3(gm, cdiv(p.N, 32)), 128, 0, st>>>(p);
+    pdl(gemm_rows_kernel<8, 4, MODE>, dim3(gm, cdiv(p.N, 32)), 128, 0, st)(p);
   }
   return cudaGetLastError();
 }
@@ -230,7 +230,7 @@ __device__ __forceinline__ float4 load4_guard(const float *base, int64_t row, in
   return v;
 }
 
-__global__ void __launch_bounds__(256) gemm_wgrad_kernel(WgradArgs p) {
+__global__ void __launch_bounds__(256) gemm_wgrad_kernel(WgradArgs p) { pdl_prologue();
   constexpr int T = 64, RC = 16;
   __shared__ __align__(16) float Xs[RC][T];
   __shared__ __align__(16) float Ys[RC][T];
@@ -300,7 +300,7 @@ inline cudaError_t launch_gemm_wgrad(WgradArgs p, cudaStream_t st, int target_ct
   rps = cdiv64(rps, 16) * 16;
   splits = cdiv64(p.R, rps);
   p.rows_per_split = (int)rps;
-  gemm_wgrad_kernel<<<dim3(cdiv(p.N, 64), cdiv(p.K, 64), (unsigned)splits), 256, 0, st>>>(p);
+  pdl(gemm_wgrad_kernel, dim3(cdiv(p.N, 64), cdiv(p.K, 64), (unsigned)splits), 256, 0, st)(p);
   return cudaGetLastError();
 }
 

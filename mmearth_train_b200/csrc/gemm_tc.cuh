@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
                const __grid_constant__ CUtensorMap map_out2, const __grid_constant__ CUtensorMap map_bt,
-               const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) { pdl_prologue();
   constexpr int kEpiWarps = epi_warps(MODE, WIDE), kEpiThreads = 32 * kEpiWarps;
   constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE), kSplitThreads = 32 * kSplitWarps;
   constexpr int kThreadsNoSplit = 64 + kEpiThreads;
@@ -990,7 +990,7 @@ constexpr int kTnThreads = 192, kTnSplitThreads = 256;   // 8 splitter warps: bo
 // statistic gradient is derived from dW2f by the chain rule of the weight fold).
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) { pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
@@ -1284,7 +1284,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  gemm_tc_kernel<MODE, SPLIT, WIDE, BF16><<<grid, tc_threads(MODE, SPLIT, WIDE), smem, st>>>(ma, mb, mbl, mo, mo2, mbt, mbtl, p);
+  pdl(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16>, grid, tc_threads(MODE, SPLIT, WIDE), smem, st)(ma, mb, mbl, mo, mo2, mbt, mbtl, p);
   return cudaGetLastError();
 }
 
@@ -1378,7 +1378,7 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   }
   int grid = tiles * p.splits;
   if (grid > 148) grid = 148;
-  gemm_tn_tc_kernel<SPLIT><<<grid, SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, smem, st>>>(mm, mn, p);
+  pdl(gemm_tn_tc_kernel<SPLIT>, grid, SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, smem, st)(mm, mn, p);
   return cudaGetLastError();
 }
 

@@ -43,7 +43,7 @@ __device__ __forceinline__ void block_sum2(float &a, float &b, float *red) {
 
 // One CTA per patch cell, ONE WARP PER PIXEL MODALITY (blockDim.x = 32 * number of pixel modalities): the modalities of
 // a cell are independent, so nothing is block-synchronised and every reduction is a warp shuffle.
-__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) pixel_loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) pixel_loss_kernel(LossArgs a) { pdl_prologue();
   const int cell = blockIdx.x;               // n*L + l
   const int n = cell / a.L, l = cell - n * a.L;
   const int ph = l / a.G, pw = l - ph * a.G;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) pixel_loss_kernel(LossArgs
 }
 
 // image-level heads (fcmae.py:281-301): one CTA per sample, one warp per image modality (blockDim.x = 32 * their count)
-__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) image_loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) image_loss_kernel(LossArgs a) { pdl_prologue();
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int mi = -1;
   for (int i = 0, k = 0; i < a.n_mod; ++i)
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * MPMAE_MAX_MOD) image_loss_kernel(LossArgs
 
 // losses[0..n) = L_i ; losses[n..2n) = weighted_i ; losses[2n] = total
 __global__ void loss_finalize_kernel(const float *__restrict__ acc, const float *__restrict__ log_vars, int n_mod,
-                                     int uncertainty, float *__restrict__ losses) {
+                                     int uncertainty, float *__restrict__ losses) { pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float total = 0.f;
   for (int i = 0; i < n_mod; ++i) {
@@ -249,7 +249,7 @@ struct SeedArgs {
   int n_mod, uncertainty;
   int col_off[MPMAE_MAX_MOD], col_len[MPMAE_MAX_MOD], is_img[MPMAE_MAX_MOD];
 };
-__global__ void loss_seed_kernel(SeedArgs a) {
+__global__ void loss_seed_kernel(SeedArgs a) { pdl_prologue();
   const int i = blockIdx.x;
   const float go = a.grad_out ? a.grad_out[0] : 1.f;
   const float L = a.losses[i];

@@ -12,7 +12,7 @@ namespace mpmae {
 // M0: mask and slot tables from the noise tensor (models/fcmae.py:214-231).
 //   rank(l) = position of patch l in the ascending (stable) sort of noise; kept iff rank < V.
 __global__ void mask_kernel(const float *__restrict__ noise, float *__restrict__ mask, int *__restrict__ slot_of,
-                            int *__restrict__ vis_patch, int L, int V) {
+                            int *__restrict__ vis_patch, int L, int V) { pdl_prologue();
   extern __shared__ float sm[];
   float *nz = sm;
   int *keep = reinterpret_cast<int *>(sm + L);
@@ -43,7 +43,7 @@ __global__ void mask_kernel(const float *__restrict__ noise, float *__restrict__
 // weights of the GEMM that consumes xhat (fold_kernel).  eps = 1e-6 (sparse_norm_layers.py:61-77).
 // Generic flavour (warp per row) and the (row, part) flavour of common.cuh for C = 4 * NP * F4.
 __global__ void ln_rows_fwd_generic_kernel(const float *__restrict__ x, float *__restrict__ xhat, float *__restrict__ rstd_out,
-                                           int64_t R, int C, float eps) {
+                                           int64_t R, int C, float eps) { pdl_prologue();
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -59,7 +59,7 @@ __global__ void ln_rows_fwd_generic_kernel(const float *__restrict__ x, float *_
 }
 template <int F4>
 __global__ void __launch_bounds__(256) ln_rows_fwd_kernel(const float *__restrict__ x, float *__restrict__ xhat,
-                                                          float *__restrict__ rstd_out, int64_t R, int C, int np, float eps) {
+                                                          float *__restrict__ rstd_out, int64_t R, int C, int np, float eps) { pdl_prologue();
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r = item / np;
   const int part = (int)(item - r * np);
@@ -91,21 +91,21 @@ inline void launch_ln_rows_fwd(const float *x, float *xhat, float *rstd, int64_t
   const unsigned grid = (unsigned)cdiv64(R * np, 256);
   if ((C & 3) == 0 && f4 >= 1 && f4 <= 6) {
     switch (f4) {
-      case 1: ln_rows_fwd_kernel<1><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
-      case 2: ln_rows_fwd_kernel<2><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
-      case 3: ln_rows_fwd_kernel<3><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
-      case 4: ln_rows_fwd_kernel<4><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
-      case 5: ln_rows_fwd_kernel<5><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
-      default: ln_rows_fwd_kernel<6><<<grid, 256, 0, st>>>(x, xhat, rstd, R, C, np, eps); return;
+      case 1: pdl(ln_rows_fwd_kernel<1>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
+      case 2: pdl(ln_rows_fwd_kernel<2>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
+      case 3: pdl(ln_rows_fwd_kernel<3>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
+      case 4: pdl(ln_rows_fwd_kernel<4>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
+      case 5: pdl(ln_rows_fwd_kernel<5>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
+      default: pdl(ln_rows_fwd_kernel<6>, grid, 256, 0, st)(x, xhat, rstd, R, C, np, eps); return;
     }
   }
-  ln_rows_fwd_generic_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, st>>>(x, xhat, rstd, R, C, eps);
+  pdl(ln_rows_fwd_generic_kernel, (unsigned)cdiv64(R, 8), 256, 0, st)(x, xhat, rstd, R, C, eps);
 }
 
 // dx = rstd * (dxhat - mean_C(dxhat) - xhat * mean_C(dxhat * xhat))  (+ add)
 __global__ void ln_rows_bwd_generic_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
                                            const float *__restrict__ rstd, const float *__restrict__ add,
-                                           float *__restrict__ dx, int64_t R, int C) {
+                                           float *__restrict__ dx, int64_t R, int C) { pdl_prologue();
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -125,7 +125,7 @@ __global__ void ln_rows_bwd_generic_kernel(const float *__restrict__ dxhat, cons
 template <int F4>
 __global__ void __launch_bounds__(256) ln_rows_bwd_kernel(const float *__restrict__ dxhat, const float *__restrict__ xhat,
                                                           const float *__restrict__ rstd, const float *__restrict__ add,
-                                                          float *__restrict__ dx, int64_t R, int C, int np) {
+                                                          float *__restrict__ dx, int64_t R, int C, int np) { pdl_prologue();
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r = item / np;
   const int part = (int)(item - r * np);
@@ -162,15 +162,15 @@ inline void launch_ln_rows_bwd(const float *dxhat, const float *xhat, const floa
   const unsigned grid = (unsigned)cdiv64(R * np, 256);
   if ((C & 3) == 0 && f4 >= 1 && f4 <= 6) {
     switch (f4) {
-      case 1: ln_rows_bwd_kernel<1><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
-      case 2: ln_rows_bwd_kernel<2><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
-      case 3: ln_rows_bwd_kernel<3><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
-      case 4: ln_rows_bwd_kernel<4><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
-      case 5: ln_rows_bwd_kernel<5><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
-      default: ln_rows_bwd_kernel<6><<<grid, 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 1: pdl(ln_rows_bwd_kernel<1>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 2: pdl(ln_rows_bwd_kernel<2>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 3: pdl(ln_rows_bwd_kernel<3>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 4: pdl(ln_rows_bwd_kernel<4>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      case 5: pdl(ln_rows_bwd_kernel<5>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
+      default: pdl(ln_rows_bwd_kernel<6>, grid, 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C, np); return;
     }
   }
-  ln_rows_bwd_generic_kernel<<<(unsigned)cdiv64(R, 8), 256, 0, st>>>(dxhat, xhat, rstd, add, dx, R, C);
+  pdl(ln_rows_bwd_generic_kernel, (unsigned)cdiv64(R, 8), 256, 0, st)(dxhat, xhat, rstd, add, dx, R, C);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -179,7 +179,7 @@ inline void launch_ln_rows_bwd(const float *dxhat, const float *xhat, const floa
 //   Gx = sqrt(gsq) ; Nx = Gx / (mean_d Gx + eps) ; scale s = 1 + gamma * Nx
 __global__ void grn_scale_kernel(const float *__restrict__ gsq, const float *__restrict__ gamma,
                                  float *__restrict__ nx, float *__restrict__ scale, float *__restrict__ denom,
-                                 int D, float eps) {
+                                 int D, float eps) { pdl_prologue();
   __shared__ float red[32];
   const int g = blockIdx.x;
   float s = 0.f;
@@ -205,7 +205,7 @@ __global__ void grn_scale_kernel(const float *__restrict__ gsq, const float *__r
 // g = h * scale[group(r), d] + beta[d]
 __global__ void grn_apply_kernel(const float *__restrict__ h, const float *__restrict__ scale,
                                  const float *__restrict__ beta, float *__restrict__ g, int64_t R, int D,
-                                 int group_rows) {
+                                 int group_rows) { pdl_prologue();
   const int64_t n4 = R * (D >> 2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (D >> 2);
@@ -226,7 +226,7 @@ __global__ void grn_apply_kernel(const float *__restrict__ h, const float *__res
 //   kg[g, d] = dGx / Gx   (so that dh += kg * h)
 __global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *__restrict__ nx,
                                      const float *__restrict__ denom, const float *__restrict__ gamma,
-                                     float *__restrict__ dgamma, float *__restrict__ kg, int D) {
+                                     float *__restrict__ dgamma, float *__restrict__ kg, int D) { pdl_prologue();
   __shared__ float red[32];
   const int g = blockIdx.x;
   const float den = denom[g];
@@ -258,7 +258,7 @@ __global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *
 // da = (dg * scale[g, d] + kg[g, d] * h) * gelu'(a)   (in place over dg allowed)
 __global__ void grn_gelu_bwd_kernel(const float *dg, const float *__restrict__ h, const float *__restrict__ a,
                                     const float *__restrict__ scale, const float *__restrict__ kg, float *da,
-                                    int64_t R, int D, int group_rows) {
+                                    int64_t R, int D, int group_rows) { pdl_prologue();
   const int64_t n4 = R * (D >> 2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (D >> 2);
@@ -407,14 +407,14 @@ __device__ __forceinline__ void fold_tile(const FoldArgs &p, int bx, int by) {
     }
   }
 }
-__global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) { fold_tile(p, blockIdx.x, blockIdx.y); }
+__global__ void __launch_bounds__(256) fold_kernel(FoldArgs p) { pdl_prologue(); fold_tile(p, blockIdx.x, blockIdx.y); }
 inline void launch_fold(const FoldArgs &a, cudaStream_t st) {
-  fold_kernel<<<dim3(cdiv(a.K, 32), cdiv(a.N, 32)), dim3(32, 8), 0, st>>>(a);
+  pdl(fold_kernel, dim3(cdiv(a.K, 32), cdiv(a.N, 32)), dim3(32, 8), 0, st)(a);
 }
 // Many folds in one launch (all the parameter-only folds of a forward pass): jobs and the prefix sum of their tile
 // counts live in device memory; a CTA finds its job by scanning the (short) prefix array.
 __global__ void __launch_bounds__(256) fold_batch_kernel(const FoldArgs *__restrict__ jobs, const int *__restrict__ tile_start,
-                                                         int njobs) {
+                                                         int njobs) { pdl_prologue();
   __shared__ FoldArgs job;
   __shared__ int local;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -470,9 +470,9 @@ __device__ __forceinline__ void unfold_column(const UnfoldArgs &p, int k) {
     }
   }
 }
-__global__ void unfold_kernel(UnfoldArgs p) { unfold_column(p, blockIdx.x); }
+__global__ void unfold_kernel(UnfoldArgs p) { pdl_prologue(); unfold_column(p, blockIdx.x); }
 // Several un-folds in one launch (the deferred ones of a backward part): job table + prefix sum of the K's in device memory
-__global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const int *__restrict__ k_start, int njobs) {
+__global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const int *__restrict__ k_start, int njobs) { pdl_prologue();
   __shared__ UnfoldArgs job;
   __shared__ int local;
   if (threadIdx.x == 0) {
@@ -490,7 +490,7 @@ __global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const i
 //   xd[n*L + l, :] = slot>=0 ? z[n*V+slot, :] : token
 __global__ void scatter_token_kernel(const float *__restrict__ z, const float *__restrict__ token,
                                      const int *__restrict__ slot_of, float *__restrict__ xd, int64_t cells, int L,
-                                     int V, int C) {
+                                     int V, int C) { pdl_prologue();
   const int C4 = C >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells * C4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t cell = i / C4;
@@ -506,7 +506,7 @@ __global__ void scatter_token_kernel(const float *__restrict__ z, const float *_
 // blockDim.x = C/4: a thread owns one float4 column group for every cell its CTA visits (token sums in registers).
 __global__ void gather_token_bwd_kernel(const float *__restrict__ dxd, const int *__restrict__ slot_of,
                                         float *__restrict__ dz, float *__restrict__ dtoken, int64_t cells, int L, int V,
-                                        int C) {
+                                        int C) { pdl_prologue();
   const int C4 = C >> 2, t = threadIdx.x;
   if (t >= C4) return;
   const float4 *src = reinterpret_cast<const float4 *>(dxd);
@@ -531,7 +531,7 @@ __global__ void gather_token_bwd_kernel(const float *__restrict__ dxd, const int
 constexpr int kPoolMaxF4 = 8;
 __global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float *__restrict__ d, const float *__restrict__ w,
                                                           const float *__restrict__ b, float *__restrict__ pooled,
-                                                          float *__restrict__ rstd_out, int L, int C, float eps) {
+                                                          float *__restrict__ rstd_out, int L, int C, float eps) { pdl_prologue();
   extern __shared__ float part[];  // [nw][C]
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int f4 = C >> 7;           // float4 per lane
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(256) pool_ln_fwd_kernel(const float *__restric
 __global__ void __launch_bounds__(256) pool_ln_bwd_kernel(const float *__restrict__ d, const float *__restrict__ rstd_in,
                                                           const float *__restrict__ w, const float *__restrict__ dpooled,
                                                           float *__restrict__ ddec, float *__restrict__ dw,
-                                                          float *__restrict__ db, int L, int C, float eps) {
+                                                          float *__restrict__ db, int L, int C, float eps) { pdl_prologue();
   extern __shared__ float part[];  // [nw][C] sum_l nhat
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int f4 = C >> 7;
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256) pool_ln_bwd_kernel(const float *__restric
 // ------------------------------------------------------------------------------------------------
 // Dense encoder features [B, C, G, G] from the stage-3 rows (SparseTensor.dense(), zeros at masked cells)
 __global__ void densify_kernel(const float *__restrict__ x3, const int *__restrict__ slot_of, float *__restrict__ out,
-                               int B, int L, int V, int C) {
+                               int B, int L, int V, int C) { pdl_prologue();
   const int64_t total = (int64_t)B * C * L;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(i % L);
@@ -653,7 +653,7 @@ __global__ void densify_kernel(const float *__restrict__ x3, const int *__restri
 // read consecutive addresses whatever C is (C = 40 is 10 float4 per row), and a thread always owns the same 4 columns.
 // gridDim.y walks column chunks of 2048; gridDim.x strides row passes.
 __global__ void __launch_bounds__(512) colsum_kernel(const float *__restrict__ x, const float *__restrict__ rs,
-                                                     float *__restrict__ out, int64_t R, int C) {
+                                                     float *__restrict__ out, int64_t R, int C) { pdl_prologue();
   __shared__ float4 red[512];
   const int c4_total = C >> 2;
   const int c4_0 = blockIdx.y * 512;
@@ -693,7 +693,7 @@ inline void launch_colsum(const float *x, const float *rs, float *out, int64_t R
   int64_t gx = cdiv64(R, (int64_t)rpp * 8);            // >= 8 passes per CTA
   if (gx > 148 * 4) gx = 148 * 4;
   if (gx < 1) gx = 1;
-  colsum_kernel<<<dim3((unsigned)gx, chunks), threads, 0, st>>>(x, rs, out, R, C);
+  pdl(colsum_kernel, dim3((unsigned)gx, chunks), threads, 0, st)(x, rs, out, R, C);
 }
 
 // Small ragged products of the image-level heads (256 x 878 x 512 at cfg2; N = 878 is not a multiple of 4, so they do not
@@ -702,7 +702,7 @@ inline void launch_colsum(const float *x, const float *rs, float *out, int64_t R
 //   NN: out[m, n] = bias[n] + sum_k A[m, k] * W[n, k]        (the heads forward; A [M, K],      W [N, K])
 __global__ void __launch_bounds__(256) small_gemm_nt_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                             const float *__restrict__ cs, float *__restrict__ out, int Brows,
-                                                            int Kout, int Nred) {
+                                                            int Kout, int Nred) { pdl_prologue();
   __shared__ float As[32][33];   // [n][b]
   __shared__ float Ws[32][33];   // [n][k]
   const int b0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(256) small_gemm_nt_kernel(const float *__restr
 }
 __global__ void __launch_bounds__(256) small_gemm_nn_kernel(const float *__restrict__ A, const float *__restrict__ W,
                                                             const float *__restrict__ bias, float *__restrict__ out, int M,
-                                                            int N, int K) {
+                                                            int N, int K) { pdl_prologue();
   __shared__ float As[32][33];   // [k][m]
   __shared__ float Ws[32][33];   // [k][n]
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;

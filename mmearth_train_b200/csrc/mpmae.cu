@@ -538,7 +538,7 @@ void use_slot(Ctx &c, GemmArgs &g, const WSlot &s, bool transposed) {
 void unfold(Ctx &c, UnfoldArgs a, const char *what, bool deferrable = false) {
   if (!c.ok()) return;
   if (deferrable && c.deferred.size() < 64) { c.deferred.push_back(a); return; }
-  unfold_kernel<<<a.K, 256, 0, c.st>>>(a);
+  pdl(unfold_kernel, a.K, 256, 0, c.st)(a);
   c.post(what);
 }
 // the deferred un-folds of this call in one launch; slot selects the cached job table (0..2 = backward part)
@@ -559,7 +559,7 @@ void flush_unfolds(Ctx &c, int slot) {
     pl->unfold_njobs[slot] = n; pl->unfold_ctas[slot] = start[n];
   }
   if (c.ok()) {
-    unfold_batch_kernel<<<start[n], 256, 0, c.st>>>(d_jobs, d_start, n);
+    pdl(unfold_batch_kernel, start[n], 256, 0, c.st)(d_jobs, d_start, n);
     c.post("unfold_batch");
   }
   c.deferred.clear();
@@ -629,7 +629,7 @@ void batched_param_folds(Ctx &c, bool encoder_only) {
     pl->fold_key_params = c.P; pl->fold_key_ws = c.ws; pl->fold_njobs = n; pl->fold_tiles = start[n];
   }
   if (!c.ok()) return;
-  fold_batch_kernel<<<pl->fold_tiles, dim3(32, 8), 0, c.st>>>(d_jobs, d_start, n);
+  pdl(fold_batch_kernel, pl->fold_tiles, dim3(32, 8), 0, c.st)(d_jobs, d_start, n);
   c.post("fold_batch");
   c.folds_done = true;
 }
@@ -661,7 +661,7 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   gemm<EPI_GELU_SQ>(c, g1, "pw1");
 
   if (dense && c.ok()) {   // per-sample statistic; the batch-global one of the sparse blocks is fused into fold_pw2
-    grn_scale_kernel<<<groups, 256, 0, c.st>>>(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom),
+    pdl(grn_scale_kernel, groups, 256, 0, c.st)(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom),
                                                D4, 1e-4f);
     c.post("grn_scale");
   }
@@ -672,7 +672,7 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   if (dense) {
     if (c.ok()) {
       c.acct(4.0 * 2.0 * R * D4, 0);
-      grn_apply_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(c.w(bw.h), c.w(bw.scale), c.p(bp.beta), c.w(bw.g), R, D4,
+      pdl(grn_apply_kernel, ew_grid(R * (D4 / 4)), 256, 0, c.st)(c.w(bw.h), c.w(bw.scale), c.p(bp.beta), c.w(bw.g), R, D4,
                                                                group_rows);
       c.post("grn_apply");
     }
@@ -714,10 +714,10 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
     wg.X = dy; wg.Y = c.w(bw.g); wg.dW = c.g(bp.w2); wg.db = c.g(bp.b2); wg.R = R; wg.N = C; wg.K = D4;
     wgrad(c, wg, "dW2");
     if (c.ok()) {
-      grn_bwd_scale_kernel<<<groups, 256, 0, c.st>>>(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
+      pdl(grn_bwd_scale_kernel, groups, 256, 0, c.st)(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
       c.post("grn_bwd_scale");
       c.acct(4.0 * 4.0 * R * D4, 0);
-      grn_gelu_bwd_kernel<<<ew_grid(R * (D4 / 4)), 256, 0, c.st>>>(da, c.w(bw.h), c.w(bw.a), c.w(bw.scale), kg, da, R, D4,
+      pdl(grn_gelu_bwd_kernel, ew_grid(R * (D4 / 4)), 256, 0, c.st)(da, c.w(bw.h), c.w(bw.a), c.w(bw.scale), kg, da, R, D4,
                                                                   group_rows);
       c.post("grn_gelu_bwd");
       launch_colsum(da, nullptr, dbf1, R, D4, c.st);   // db1f = sum da
@@ -736,7 +736,7 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
     u.N = C; u.K = D4; u.SL = D4;
     unfold(c, u, "unfold_pw2");
     if (c.ok()) {
-      grn_bwd_scale_kernel<<<1, 256, 0, c.st>>>(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
+      pdl(grn_bwd_scale_kernel, 1, 256, 0, c.st)(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
       c.post("grn_bwd_scale");
     }
     // da = (dy . W2f + kg*h) * gelu'(a) ; db1f = sum da rides on the epilogue
@@ -996,7 +996,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
   c.zero(c.w(pl->o_zero_begin), pl->o_zero_end - pl->o_zero_begin, "zero_stats");
   if (stages & ST_MASK) {
     c.check(cudaMemsetAsync(io->flags, 0, 4 * sizeof(int32_t), c.st), "memset", false);
-    mask_kernel<<<geo.B, 64, (size_t)geo.L * 8, c.st>>>(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
+    pdl(mask_kernel, geo.B, 64, (size_t)geo.L * 8, c.st)(io->noise, io->mask, slot_of, vis, geo.L, geo.V);
     c.post("mask");
   }
   if (stages & (ST_ENC | ST_DEC)) batched_param_folds(c, encoder_only);
@@ -1031,16 +1031,16 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
     const int per_sm = occ_per_sm;
     int64_t grid = (int64_t)148 * per_sm;
     if (grid > units) grid = units;
-    initial_conv_fwd_kernel<<<(unsigned)grid, threads, sm, c.st>>>(a, units, s.ln0_w, s.ln0_b, s.kernel, s.bias, s.ln1_w, s.ln1_b,
+    pdl(initial_conv_fwd_kernel, (unsigned)grid, threads, sm, c.st)(a, units, s.ln0_w, s.ln0_b, s.kernel, s.bias, s.ln1_w, s.ln1_b,
                                                                   s.shat, s.rstd_s, s.x0, fuse);
     c.post("initial_conv");
     if (!fuse) {
       const unsigned sg = (unsigned)cdiv64(s.R0, 8);
       switch (cdiv(s.C0, 32)) {
-        case 1: stem_fwd_kernel<1><<<sg, 256, 0, c.st>>>(s); break;
-        case 2: stem_fwd_kernel<2><<<sg, 256, 0, c.st>>>(s); break;
-        case 3: stem_fwd_kernel<3><<<sg, 256, 0, c.st>>>(s); break;
-        default: stem_fwd_kernel<4><<<sg, 256, 0, c.st>>>(s); break;
+        case 1: pdl(stem_fwd_kernel<1>, sg, 256, 0, c.st)(s); break;
+        case 2: pdl(stem_fwd_kernel<2>, sg, 256, 0, c.st)(s); break;
+        case 3: pdl(stem_fwd_kernel<3>, sg, 256, 0, c.st)(s); break;
+        default: pdl(stem_fwd_kernel<4>, sg, 256, 0, c.st)(s); break;
       }
       c.post("stem");
     }
@@ -1074,7 +1074,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
     g.A = x; use_slot(c, g, pl->proj_slot, false); g.bias = c.p(pl->proj_b); g.out = c.w(pl->o_z);
     g.M = (int64_t)geo.B * geo.V; g.N = D; g.K = dm[3]; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "proj");
-    scatter_token_kernel<<<ew_grid(pl->cells * (D / 4)), 256, 0, c.st>>>(c.w(pl->o_z), c.p(pl->tok), slot_of, c.w(pl->o_xd),
+    pdl(scatter_token_kernel, ew_grid(pl->cells * (D / 4)), 256, 0, c.st)(c.w(pl->o_z), c.p(pl->tok), slot_of, c.w(pl->o_xd),
                                                                       pl->cells, geo.L, geo.V, D);
     c.post("scatter_token");
   }
@@ -1091,11 +1091,11 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
     gemm<EPI_STORE>(c, g, "pixel_heads");
   }
   if (pl->nimg > 0) {
-    pool_ln_fwd_kernel<<<geo.B, 256, (size_t)8 * D * 4, c.st>>>(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
+    pdl(pool_ln_fwd_kernel, geo.B, 256, (size_t)8 * D * 4, c.st)(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
                                                           c.w(pl->o_pool_rstd), geo.L, D, 1e-6f);
     c.post("pool_ln");
     if (c.ok()) {
-      small_gemm_nn_kernel<<<dim3(cdiv(pl->nimg, 32), cdiv(geo.B, 32)), 256, 0, c.st>>>(c.w(pl->o_pooled), c.p(pl->imgw), c.p(pl->imgb),
+      pdl(small_gemm_nn_kernel, dim3(cdiv(pl->nimg, 32), cdiv(geo.B, 32)), 256, 0, c.st)(c.w(pl->o_pooled), c.p(pl->imgw), c.p(pl->imgb),
                                                                                        io->pred_image, geo.B, pl->nimg, D);
       c.post("image_heads");
     }
@@ -1106,16 +1106,16 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
     if (pl->npix > 0) {
       int npm = 0;
       for (int m = 0; m < cf.n_mod; ++m) npm += pl->is_img[m] ? 0 : 1;
-      pixel_loss_kernel<<<(unsigned)pl->cells, 32 * npm, 0, c.st>>>(a);
+      pdl(pixel_loss_kernel, (unsigned)pl->cells, 32 * npm, 0, c.st)(a);
       c.post("pixel_loss");
     }
     if (pl->nimg > 0) {
       int nim = 0;
       for (int m = 0; m < cf.n_mod; ++m) nim += pl->is_img[m] ? 1 : 0;
-      image_loss_kernel<<<geo.B, 32 * nim, 0, c.st>>>(a);
+      pdl(image_loss_kernel, geo.B, 32 * nim, 0, c.st)(a);
       c.post("image_loss");
     }
-    loss_finalize_kernel<<<1, 32, 0, c.st>>>(c.w(pl->o_acc), pl->logv >= 0 ? c.p(pl->logv) : nullptr, cf.n_mod,
+    pdl(loss_finalize_kernel, 1, 32, 0, c.st)(c.w(pl->o_acc), pl->logv >= 0 ? c.p(pl->logv) : nullptr, cf.n_mod,
                                              cf.loss_aggr, io->losses);
     c.post("loss_finalize");
   }
@@ -1158,7 +1158,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     s.colscale_pix = c.w(pl->o_cs_pix); s.colscale_img = c.w(pl->o_cs_img);
     s.n_mod = cf.n_mod; s.uncertainty = cf.loss_aggr;
     for (int m = 0; m < cf.n_mod; ++m) { s.col_off[m] = pl->col_off[m]; s.col_len[m] = pl->col_len[m]; s.is_img[m] = pl->is_img[m]; }
-    loss_seed_kernel<<<cf.n_mod, 256, 0, c.st>>>(s);
+    pdl(loss_seed_kernel, cf.n_mod, 256, 0, c.st)(s);
     c.post("loss_seed");
   }
   const float *dec_out = c.w(pl->dw[cf.dec_depth - 1].y);
@@ -1179,7 +1179,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   }
   if (pl->nimg > 0) {
     if (c.ok()) {
-      small_gemm_nt_kernel<<<dim3(cdiv(D, 32), cdiv(geo.B, 32)), 256, 0, c.st>>>(
+      pdl(small_gemm_nt_kernel, dim3(cdiv(D, 32), cdiv(geo.B, 32)), 256, 0, c.st)(
           c.w(pl->o_dimg), c.p(pl->imgw), c.w(pl->o_cs_img), c.w(pl->o_dpooled), geo.B, D, pl->nimg);
       c.post("d_pooled");
     }
@@ -1188,7 +1188,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     w.R = geo.B; w.N = pl->nimg; w.K = D;
     wgrad(c, w, "dW_img");
     if (c.ok()) {
-      pool_ln_bwd_kernel<<<geo.B, 256, (size_t)8 * D * 4, c.st>>>(dec_out, c.w(pl->o_pool_rstd), c.p(pl->lnt_w), c.w(pl->o_dpooled),
+      pdl(pool_ln_bwd_kernel, geo.B, 256, (size_t)8 * D * 4, c.st)(dec_out, c.w(pl->o_pool_rstd), c.p(pl->lnt_w), c.w(pl->o_dpooled),
                                                             dd, c.g(pl->lnt_w), c.g(pl->lnt_b), geo.L, D, 1e-6f);
       c.post("pool_ln_bwd");
     }
@@ -1203,7 +1203,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   {
     float *dz = c.w(pl->o_gdv);
     if (c.ok()) {
-      gather_token_bwd_kernel<<<148 * 4, ((D / 4 + 31) / 32) * 32, 0, c.st>>>(cur, slot_of, dz, c.g(pl->tok), pl->cells, geo.L, geo.V, D);
+      pdl(gather_token_bwd_kernel, 148 * 4, ((D / 4 + 31) / 32) * 32, 0, c.st)(cur, slot_of, dz, c.g(pl->tok), pl->cells, geo.L, geo.V, D);
       c.post("gather_token_bwd");
     }
     WgradArgs w{};
@@ -1257,10 +1257,10 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     if (c.ok()) {
       const size_t ssm = (size_t)(5 + sb.f.s2) * sb.f.C0 * 4;
       switch (cdiv(sb.f.C0, 32)) {
-        case 1: stem_bwd_kernel<1><<<148 * 8, 256, ssm, c.st>>>(sb); break;
-        case 2: stem_bwd_kernel<2><<<148 * 6, 256, ssm, c.st>>>(sb); break;
-        case 3: stem_bwd_kernel<3><<<148 * 4, 256, ssm, c.st>>>(sb); break;
-        default: stem_bwd_kernel<4><<<148 * 4, 256, ssm, c.st>>>(sb); break;
+        case 1: pdl(stem_bwd_kernel<1>, 148 * 8, 256, ssm, c.st)(sb); break;
+        case 2: pdl(stem_bwd_kernel<2>, 148 * 6, 256, ssm, c.st)(sb); break;
+        case 3: pdl(stem_bwd_kernel<3>, 148 * 4, 256, ssm, c.st)(sb); break;
+        default: pdl(stem_bwd_kernel<4>, 148 * 4, 256, ssm, c.st)(sb); break;
       }
       c.post("stem_bwd");
     }
@@ -1277,7 +1277,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
       const int owners = iw.f.Cin * (iw.f.C0 / 4);
       const int parts = owners * 4 <= 512 ? 4 : (owners * 2 <= 512 ? 2 : 1);
       const int per_sm = (owners * parts <= 256) ? 4 : 2;
-      initial_conv_wgrad_kernel<<<148 * per_sm, owners * parts, sm, c.st>>>(iw);
+      pdl(initial_conv_wgrad_kernel, 148 * per_sm, owners * parts, sm, c.st)(iw);
       c.post("initial_conv_wgrad");
     }
   }
@@ -1347,7 +1347,7 @@ int mpmae_encoder_features(mpmae_plan *pl, const mpmae_io *io, float *out_nchw, 
   const int C3 = pl->cfg.dims[3];
   const float *x3 = ws + pl->bw[3][pl->cfg.depths[3] - 1].y;
   const int64_t total = (int64_t)pl->geo.B * C3 * pl->geo.L;
-  densify_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+  pdl(densify_kernel, ew_grid(total), 256, 0, static_cast<cudaStream_t>(cuda_stream))(
       x3, reinterpret_cast<const int *>(ws + pl->o_slot), out_nchw, pl->geo.B, pl->geo.L, pl->geo.V, C3);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "densify: %s", cudaGetErrorString(e));

@@ -11,7 +11,7 @@ namespace mpmae {
 
 __global__ void adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                              float *__restrict__ v, const uint8_t *__restrict__ decay, int64_t n, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float ginv) {
+                             float b2, float eps, float wd, float bc1, float bc2_sqrt, float ginv) { pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * ginv;
     float pi = p[i];
@@ -27,7 +27,7 @@ __global__ void adamw_kernel(float *__restrict__ p, const float *__restrict__ g,
 // 4 elements per thread (16-byte loads / stores); n % 4 == 0 and 16-byte aligned buffers
 __global__ void adamw_vec4_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float4 *__restrict__ m,
                                   float4 *__restrict__ v, const uchar4 *__restrict__ decay, int64_t n4, float lr, float b1,
-                                  float b2, float eps, float wd, float bc1, float bc2_sqrt, float ginv) {
+                                  float b2, float eps, float wd, float bc1, float bc2_sqrt, float ginv) { pdl_prologue();
   const float keep = 1.f - lr * wd, step = lr / bc1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 g4 = g[i];
@@ -52,7 +52,7 @@ __global__ void adamw_vec4_kernel(float4 *__restrict__ p, const float4 *__restri
 // state[2] = 1-based number of this step (bias corrections).
 __global__ void adamw_vec4_dev_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float4 *__restrict__ m,
                                       float4 *__restrict__ v, const uchar4 *__restrict__ decay, int64_t n4, float lr, float b1,
-                                      float b2, float eps, float wd, const float *__restrict__ state) {
+                                      float b2, float eps, float wd, const float *__restrict__ state) { pdl_prologue();
   const float ginv = state[0];
   if (state[1] != 0.f) return;
   const double t = (double)state[2];
@@ -82,7 +82,7 @@ inline cudaError_t launch_adamw_dev(float *p, const float *g, float *m, float *v
   if (n % 4 != 0 || (al & 15) != 0 || ((uintptr_t)decay & 3) != 0) return cudaErrorInvalidValue;
   int64_t g4 = cdiv64(n / 4, 256);
   if (g4 > 148 * 8) g4 = 148 * 8;
-  adamw_vec4_dev_kernel<<<(unsigned)g4, 256, 0, st>>>(reinterpret_cast<float4 *>(p), reinterpret_cast<const float4 *>(g),
+  pdl(adamw_vec4_dev_kernel, (unsigned)g4, 256, 0, st)(reinterpret_cast<float4 *>(p), reinterpret_cast<const float4 *>(g),
                                                      reinterpret_cast<float4 *>(m), reinterpret_cast<float4 *>(v),
                                                      reinterpret_cast<const uchar4 *>(decay), n / 4, lr, b1, b2, eps, wd, state);
   return cudaGetLastError();
@@ -98,13 +98,13 @@ inline cudaError_t launch_adamw(float *p, const float *g, float *m, float *v, co
   if (n % 4 == 0 && (al & 15) == 0 && ((uintptr_t)decay & 3) == 0) {
     int64_t g4 = cdiv64(n / 4, 256);
     if (g4 > 148 * 8) g4 = 148 * 8;
-    adamw_vec4_kernel<<<(unsigned)g4, 256, 0, st>>>(reinterpret_cast<float4 *>(p), reinterpret_cast<const float4 *>(g),
+    pdl(adamw_vec4_kernel, (unsigned)g4, 256, 0, st)(reinterpret_cast<float4 *>(p), reinterpret_cast<const float4 *>(g),
                                                    reinterpret_cast<float4 *>(m), reinterpret_cast<float4 *>(v),
                                                    reinterpret_cast<const uchar4 *>(decay), n / 4, lr, b1, b2, eps, wd, bc1,
                                                    sqrtf(bc2), ginv);
     return cudaGetLastError();
   }
-  adamw_kernel<<<(unsigned)grid, 256, 0, st>>>(p, g, m, v, decay, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), ginv);
+  pdl(adamw_kernel, (unsigned)grid, 256, 0, st)(p, g, m, v, decay, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), ginv);
   return cudaGetLastError();
 }
 

@@ -122,7 +122,7 @@ __device__ __forceinline__ void embed_ln_phase(const float *cbuf, int pitch, int
 __global__ void __launch_bounds__(512) initial_conv_fwd_kernel(InitConvArgs p, int64_t units, const float *ln0_w,
                                                                const float *ln0_b, const float *st_k, const float *st_b,
                                                                const float *ln1_w, const float *ln1_b, float *shat,
-                                                               float *rstd_s, float *x0, int fuse) {
+                                                               float *rstd_s, float *x0, int fuse) { pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   const int C0 = p.C0, Cin = p.Cin, pitch = C0 + 4;
   float *xin = smem;                       // [Cin][10][10]
@@ -211,7 +211,7 @@ struct InitConvWgradArgs {
 // the whole kernel) for one half of each tile's pixels: per pixel 9 window loads + one 16-byte dc load feed 36 FMAs.
 // Threads: Cin * (C0 / 4) owners x `parts` pixel groups (blockDim.x = owners * parts, parts in {1, 2, 4}).  One flush
 // (shared-memory atomics, then global) at the end.
-__global__ void __launch_bounds__(512) initial_conv_wgrad_kernel(InitConvWgradArgs a) {
+__global__ void __launch_bounds__(512) initial_conv_wgrad_kernel(InitConvWgradArgs a) { pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   const InitConvArgs &p = a.f;
   const int C0 = p.C0, Cin = p.Cin;
@@ -301,7 +301,7 @@ constexpr int kStemMaxPerLane = 4;  // C0 <= 128
 
 // NQ = ceil(C0 / 32) channel rounds per lane (compile time: no dead rounds)
 template <int NQ>
-__global__ void stem_fwd_kernel(StemArgs p) {
+__global__ void stem_fwd_kernel(StemArgs p) { pdl_prologue();
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= p.R0) return;
   const int lane = threadIdx.x & 31, C0 = p.C0;
@@ -346,7 +346,7 @@ struct StemBwdArgs {
 };
 // per-lane partial column sums: [0]=d_ln1_w [1]=d_ln1_b [2]=d_bias [3]=d_ln0_w [4]=d_ln0_b [5..5+s2)=d_kernel[j]
 template <int NQ>
-__global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) {
+__global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) { pdl_prologue();
   extern __shared__ float red[];  // [(5 + s2)][C0]
   const StemArgs &p = a.f;
   const int C0 = p.C0, s2 = p.s2, nvec = 5 + s2;
