@@ -96,6 +96,36 @@ def _len_or_none(it) -> Optional[int]:
         return None
 
 
+class _LaggedHostReader:
+    """``LossReader``'s interface for tensors that already live on the host (``device.type == "cpu"``: the loop run around
+    a CPU model, which is how the tests replay the reference engine's golden trajectories): same ``lag`` semantics."""
+
+    def __init__(self, depth: int):
+        self._q = deque()
+        self.depth = depth
+
+    def push(self, value: torch.Tensor):
+        self._q.append(value.detach().reshape(-1).tolist())
+        return self._q.popleft() if len(self._q) > self.depth else None
+
+    def flush(self) -> list:
+        out = list(self._q)
+        self._q.clear()
+        return out
+
+
+def _loss_vector(core, out) -> torch.Tensor:
+    """``[per-modality losses (T), weighted losses (T), total]``: the native module's loss kernels write exactly this vector
+    (``FCMAE.last_run["losses"]``); for any other module with the reference's return tuple it is assembled here."""
+    run = getattr(core, "last_run", None)
+    if isinstance(run, dict) and "losses" in run:
+        return run["losses"]
+    loss, _pred, _mask, loss_dict, _log_vars, weighted = out
+    per = torch.stack([v.detach().reshape(()) for v in loss_dict.values()])
+    w = weighted.detach().reshape(-1) if weighted is not None else torch.zeros_like(per)
+    return torch.cat([per, w, loss.detach().reshape(1)])
+
+
 def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, optimizer, device: torch.device, epoch: int,
                     use_mixed: bool, loss_scaler, log_writer=None, args=None, lag: int = 2, print_freq: int = 20,
                     quiet: bool = False):
@@ -111,6 +141,7 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
     model.train()
     core = model.module if hasattr(model, "module") else model
     device = torch.device(device)
+    on_gpu = device.type == "cuda"
     metric_logger = MetricLogger()
     metric_logger.add_meter("lr", SmoothedValue(window_size=1))
     header = "Epoch: [{}]".format(epoch)
@@ -118,14 +149,17 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
     n_iter = _len_or_none(data_loader)
     if n_iter is None:
         raise TypeError("data_loader needs __len__ (the per-iteration schedule divides by it, engine_pretrain.py:53-56)")
-    T = len(core.out_modalities)
-    names = list(core.out_modalities)
-    reader = LossReader(device, depth=max(lag, 1), width=2 * T + 1)
+    names = list(getattr(core, "out_modalities", None) or core.args.out_modalities.keys())
+    T = len(names)
+    uncertainty = getattr(core, "loss_aggr", None) or core.args.loss_aggr
+    reader = LossReader(device, depth=max(lag, 1), width=2 * T + 1) if on_gpu else _LaggedHostReader(max(lag, 1))
+    pending = deque()                      # (epoch_1000x, is an update step) of the iterations whose losses are in flight
     last = {"loss_dict": None, "weighted": None}
 
     def consume(vals: Optional[List[float]]) -> None:
         if vals is None:
             return
+        step, was_update = pending.popleft()
         loss_value = vals[2 * T]
         if not math.isfinite(loss_value):                                       # engine_pretrain.py:77-79
             print("Loss is {}, stopping training".format(loss_value))
@@ -133,10 +167,8 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
         metric_logger.update(loss=loss_value)
         last["loss_dict"] = {m: vals[i] for i, m in enumerate(names)}
         last["weighted"] = vals[T:2 * T]
-        if log_writer is not None:
-            log_writer.update(train_loss=_all_reduce_mean(loss_value, device), head="loss", step=consume.step)
-
-    consume.step = 0
+        if log_writer is not None and was_update:                               # :104-112
+            log_writer.update(train_loss=_all_reduce_mean(loss_value, device), head="loss", step=step)
 
     def as_dict(data):
         if isinstance(data, dict):
@@ -145,7 +177,10 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
             return data[1]                                                       # engine_pretrain.py:50
         return {m: data[i] for i, m in enumerate(modalities)}                    # helpers.make_modality_dict
 
-    batches = DevicePrefetcher((as_dict(d) for d in data_loader), device)
+    if on_gpu:
+        batches = DevicePrefetcher((as_dict(d) for d in data_loader), device)
+    else:
+        batches = ({k: v.to(device) for k, v in as_dict(d).items()} for d in data_loader)
     optimizer.zero_grad()
     log_var_list = None
     t0 = time.time()
@@ -154,16 +189,18 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
             lr = cosine_lr(data_iter_step / n_iter + epoch, args.lr, args.min_lr, args.warmup_epochs, args.epochs)
             for group in optimizer.param_groups:
                 group["lr"] = lr * group["lr_scale"] if "lr_scale" in group else lr
-        loss, _pred, _mask, _loss_dict, log_var_list, _norm = model(samples, mask_ratio=args.mask_ratio)
-        consume.step = int((data_iter_step / n_iter + epoch) * 1000)            # epoch_1000x, :108
-        consume(reader.push(core.last_run["losses"]))
+        out = model(samples, mask_ratio=args.mask_ratio)
+        loss, log_var_list = out[0], out[4]
         update = (data_iter_step + 1) % update_freq == 0
+        step_1000x = int((data_iter_step / n_iter + epoch) * 1000)              # epoch_1000x, :108
+        pending.append((step_1000x, update))
+        consume(reader.push(_loss_vector(core, out)))
         loss_scaler(loss / update_freq if update_freq != 1 else loss, optimizer, parameters=None, update_grad=update)
         if update:
             optimizer.zero_grad()
         metric_logger.update(lr=optimizer.param_groups[0]["lr"])
         if log_writer is not None and update:
-            log_writer.update(lr=optimizer.param_groups[0]["lr"], head="opt", step=consume.step)
+            log_writer.update(lr=optimizer.param_groups[0]["lr"], head="opt", step=step_1000x)
         if not quiet and (data_iter_step % print_freq == 0 or data_iter_step == n_iter - 1):
             print(f"{header} [{data_iter_step}/{n_iter}]  {metric_logger}  time: {(time.time() - t0) / (data_iter_step + 1):.4f}")
     for vals in reader.flush():
@@ -172,7 +209,7 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
     if not quiet:
         print("Averaged stats:", metric_logger)
     normalized = None
-    if last["weighted"] is not None and core.loss_aggr == "uncertainty":
+    if last["weighted"] is not None and uncertainty == "uncertainty":
         import numpy as np
         normalized = np.asarray(last["weighted"], dtype=np.float32)
     return ({k: m.global_avg for k, m in metric_logger.meters.items()}, last["loss_dict"],

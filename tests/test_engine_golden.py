@@ -1,0 +1,90 @@
+"""engine.train_one_epoch against golden trajectories of the UNMODIFIED reference loop (engine_pretrain.train_one_epoch
+around the unmodified reference FCMAE, AdamW as main_pretrain.py builds it, NativeScalerWithGradNormCount), made by
+oracle/make_engine_golden.py: BASELINE.json configs[0] (atto, S2 -> S2, 56/p8, bs 8, the reference's CPU-runnable case) and
+a 12-modality uncertainty-weighted run with gradient accumulation.  The loop under test is the product's host code; the model
+inside it here is the CPU oracle (the native module needs a GPU: tests/test_engine_gpu.py runs the same loop around it)."""
+import json
+import os
+
+import pytest
+import torch
+
+from mmearth_train_b200 import engine
+from oracle import make_engine_golden as meg
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 2e-5
+
+
+class _Replay(torch.nn.Module):
+    """The oracle behind the reference's call signature, drawing the fixture's noise instead of torch.randn."""
+
+    def __init__(self, orc, noises):
+        super().__init__()
+        self.orc, self.args, self.queue = orc, orc.args, list(noises)
+
+    def forward(self, samples, labels=None, mask_ratio=0.6):
+        return self.orc(samples, mask_ratio=mask_ratio, noise=self.queue.pop(0))
+
+
+class _CpuScaler:
+    """helpers.NativeScalerWithGradNormCount on CPU (GradScaler disabled, helpers.py:473): backward, step on update."""
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        loss.backward()
+        if update_grad:
+            optimizer.step()
+
+
+def _close(a, b, tol=TOL):
+    return abs(a - b) <= tol * abs(b) + 1e-9
+
+
+@pytest.mark.parametrize("case", list(meg.CASES))
+@pytest.mark.parametrize("lag", [1, 3])
+def test_loop_reproduces_reference_engine_trajectory(case, lag):
+    gold = json.load(open(os.path.join(GOLDEN_DIR, f"engine_{case}.json")))
+    cfg = gold["cfg"]
+    assert cfg == meg.CASES[case] and gold["loop_args"] == meg.LOOP_ARGS, "fixture is stale: python -m oracle.make_engine_golden"
+    orc, batches, noises = meg.case_inputs(cfg)
+    cs = gold["input_checksum"]
+    assert _close(float(sum(b["sentinel2"].double().sum() for b in batches)), cs["s2"], 1e-9), "torch CPU generator changed"
+    assert _close(float(sum(n.double().sum() for n in noises)), cs["noise"], 1e-9)
+    args = meg.loop_args(cfg)
+    model = _Replay(orc, noises)
+    optimizer = torch.optim.AdamW(meg.param_groups_weight_decay(orc, args.weight_decay), lr=args.lr, betas=(0.9, 0.95))
+    writer = meg._Writer()
+    loader = [(i, b) for i, b in enumerate(batches)]
+    stats, loss_dict, log_vars, normalized = engine.train_one_epoch(
+        model, None, loader, optimizer, torch.device("cpu"), cfg["epoch"], False, _CpuScaler(), log_writer=writer, args=args,
+        lag=lag, quiet=True)
+
+    assert _close(stats["loss"], gold["stats"]["loss"]) and _close(stats["lr"], gold["stats"]["lr"], 1e-12)
+    assert set(loss_dict) == set(gold["loss_dict"])
+    for m, v in gold["loss_dict"].items():
+        assert _close(loss_dict[m], v), m
+    if gold["log_vars"] is None:
+        assert log_vars is None and normalized is None
+    else:
+        assert all(_close(a, b) for a, b in zip(log_vars, gold["log_vars"]))
+        assert all(_close(float(a), b) for a, b in zip(normalized, gold["normalized"]))
+    # what the loop sends to the log writer: same steps, same learning rates, same per-iteration losses (engine_pretrain.py:104-112)
+    for head, key in (("loss", "train_loss"), ("opt", "lr")):
+        got = [r for r in writer.rows if r["head"] == head]
+        want = [r for r in gold["logged"] if r["head"] == head]
+        assert [r["step"] for r in got] == [r["step"] for r in want], head
+        for g, w in zip(got, want):
+            assert _close(g[key], w[key], TOL if key == "train_loss" else 1e-12), (head, g, w)
+    norm = float(torch.sqrt(sum((p.detach().double() ** 2).sum() for p in {id(p): p for p in orc.parameters()}.values())))
+    assert _close(norm, gold["final_param_norm"], 1e-6)
+    assert optimizer.param_groups[0]["lr"] == optimizer.param_groups[1]["lr"]
+
+
+@pytest.mark.skipif(not meg.ref_harness.reference_available(), reason="needs /root/reference (build container only)")
+def test_fixture_generator_still_matches_the_live_reference():
+    """Re-runs the unmodified reference loop for the small case and compares with the committed fixture."""
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "engine_cfg1.json")))
+    live = meg.run_reference_engine(meg.CASES["cfg1"])
+    assert _close(live["stats"]["loss"], gold["stats"]["loss"], 1e-6)
+    assert [r["step"] for r in live["logged"]] == [r["step"] for r in gold["logged"]]
+    assert _close(live["final_param_norm"], gold["final_param_norm"], 1e-9)
