@@ -58,3 +58,59 @@ def test_oracle_matches_live_reference_full_gradients():
         assert gu.rel_err(grads[pname], p.grad) < 5e-4, pname
         n += 1
     assert n > 150
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("model", ["convnextv2_femto", "convnextv2_pico", "convnextv2_nano", "convnextv2_base"])
+def test_oracle_matches_live_reference_other_widths(model):
+    """tests/test_parity_gpu.py::test_other_model_factories_match_oracle holds the CUDA path to the oracle for the factories
+    that have no committed fixture; this holds the oracle to the unmodified reference for the same factories (one sample)."""
+    from oracle import make_golden as mg
+    cfg = dict(model=model, img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty", B=1, nan_frac=0.05)
+    orc, ref, batch, noise, out = mg.run_reference(cfg)
+    loss, pred, mask, loss_dict, _, weighted = orc(batch, mask_ratio=0.6, noise=noise)
+    assert torch.equal(mask, out["mask"])
+    assert abs(float(loss) - float(out["loss"])) < TOL * abs(float(out["loss"]))
+    for m in pred:
+        assert gu.max_rel(pred[m], out["pred"][m]) < TOL, m
+    grads = gu.oracle_grads(orc, loss)
+    seen, total_sq, diff_sq = set(), 0.0, 0.0
+    for pname, p in ref.named_parameters():
+        if id(p) in seen or p.grad is None:
+            continue
+        seen.add(id(p))
+        gn = float(p.grad.double().norm())
+        total_sq += gn ** 2
+        diff_sq += (gu.rel_err(grads[pname], p.grad) * gn) ** 2
+    assert (diff_sq / total_sq) ** 0.5 < 1e-4
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("variant", [dict(mask_ratio=0.75), dict(norm_pix_loss=False), dict(decoder_depth=2),
+                                     dict(mask_ratio=0.5, patch_size=16, img_size=112)])
+def test_oracle_matches_live_reference_option_variants(variant):
+    """Constructor options away from the fixtures' defaults (mask ratio, norm_pix_loss, decoder depth, p16 geometry)."""
+    from oracle import fcmae_oracle as fo
+    kw = dict(model="convnextv2_atto", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty",
+              norm_pix_loss=True, mask_ratio=0.6, decoder_depth=1)
+    kw.update(variant)
+    orc = fo.build_oracle(**kw)
+    fo.init_like_reference(orc, seed=3)
+    ref, _ = ref_harness.build_reference_model(**kw)
+    ref.load_state_dict(orc.state_dict())
+    ref.train()
+    batch = fo.synthetic_batch(1, kw["img_size"], None, seed=5, nan_frac=0.05)
+    L = (kw["img_size"] // kw["patch_size"]) ** 2
+    noise = torch.randn(1, L, generator=torch.Generator().manual_seed(11))
+    real_randn = torch.randn
+    torch.randn = lambda *a, **k: noise.clone()
+    try:
+        r_loss, r_pred, r_mask, r_ld, _, _ = ref({k: v.clone() for k, v in batch.items()}, mask_ratio=kw["mask_ratio"])
+    finally:
+        torch.randn = real_randn
+    loss, pred, mask, loss_dict, _, _ = orc(batch, mask_ratio=kw["mask_ratio"], noise=noise)
+    assert torch.equal(mask, r_mask) and int(mask.sum()) == L - int(L * (1 - kw["mask_ratio"]))
+    assert abs(float(loss) - float(r_loss)) < TOL * abs(float(r_loss))
+    for m in pred:
+        assert gu.max_rel(pred[m], r_pred[m]) < TOL, m
+        assert abs(float(loss_dict[m]) - float(r_ld[m])) <= TOL * abs(float(r_ld[m])) + 1e-8, m
