@@ -151,7 +151,7 @@ def main():
     import torch.distributed as dist
     import mmearth_train_b200 as mp
     from mmearth_train_b200.optim import FlatAdamW
-    from oracle import fcmae_oracle as fo   # synthetic_batch / make_args only (data + config helpers, not compute)
+    from mmearth_train_b200 import synthetic as fo   # synthetic batches + args (the oracle is imported by the cpu_baseline / reference legs only)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

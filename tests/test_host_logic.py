@@ -89,3 +89,25 @@ def test_gen_random_mask_and_patchify_match_oracle(native_lib):
     orc = fo.build_oracle()
     t = torch.randn(2, 8, 56, 56)
     assert torch.equal(m.patchify(t, "sentinel1"), orc.patchify(t, 8))
+
+
+def test_product_synthetic_generator_equals_the_oracles_and_the_reference_modalities():
+    """bench.py and the tools draw their batches / args from mmearth_train_b200.synthetic (the product never imports the
+    oracle); same seed -> bit-identical tensors, same args fields.  With /root/reference present the band tables are also
+    checked against MODALITIES.py."""
+    from mmearth_train_b200 import synthetic as syn
+    for outs, nan_frac in ((None, 0.05), (["sentinel2"], 0.0), (["era5", "biome", "lat"], 0.1)):
+        a = syn.synthetic_batch(3, 56, outs, seed=77, nan_frac=nan_frac)
+        b = fo.synthetic_batch(3, 56, outs, seed=77, nan_frac=nan_frac)
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].dtype == b[k].dtype and torch.equal(torch.nan_to_num(a[k].double(), nan=-7.0),
+                                                            torch.nan_to_num(b[k].double(), nan=-7.0)), k
+        assert vars(syn.make_args(outs, "unweighted")) == vars(fo.make_args(outs, "unweighted"))
+    from oracle import ref_harness
+    if ref_harness.reference_available():
+        M = ref_harness.load_reference().MODALITIES
+        assert list(M.OUT_MODALITIES) == syn.ALL_OUT
+        assert M.INP_MODALITIES["sentinel2"] == syn.S2_BANDS
+        full = {k: len(v) for k, v in M.MODALITIES_FULL.items()}
+        assert {k: full[k] for k in syn.FULL_BANDS} == syn.FULL_BANDS      # (the reference also lists three S2 mask products)

@@ -54,7 +54,7 @@ def main():
     import mmearth_train_b200 as mp
     from mmearth_train_b200 import engine
     from mmearth_train_b200.optim import FlatAdamW, FlatGradScaler
-    from oracle import fcmae_oracle as fo      # synthetic batch generator only
+    from mmearth_train_b200 import synthetic as fo
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     margs = fo.make_args(None, "uncertainty")

@@ -1,6 +1,6 @@
 import torch, time, sys, os
 sys.path.insert(0, '/root/repo')
-from oracle import fcmae_oracle as fo
+from mmearth_train_b200 import synthetic as fo
 dev = torch.device('cuda', 0)
 host = [{k: v.pin_memory() for k, v in fo.synthetic_batch(256, 56, None, seed=i).items()} for i in range(4)]
 nbytes = sum(v.numel() * v.element_size() for v in host[0].values())

@@ -6,7 +6,7 @@ import torch
 import mmearth_train_b200 as mp
 from bench import CONFIGS
 from mmearth_train_b200.optim import FlatAdamW
-from oracle import fcmae_oracle as fo
+from mmearth_train_b200 import synthetic as fo
 
 cfg = CONFIGS["cfg2"]
 args = fo.make_args(cfg["out_modalities"], cfg["loss_aggr"])

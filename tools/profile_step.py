@@ -13,7 +13,7 @@ import torch  # noqa: E402
 import mmearth_train_b200 as mp  # noqa: E402
 from bench import CONFIGS  # noqa: E402
 from mmearth_train_b200.optim import FlatAdamW  # noqa: E402
-from oracle import fcmae_oracle as fo  # noqa: E402  (synthetic data + config helper only)
+from mmearth_train_b200 import synthetic as fo  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
