@@ -78,3 +78,68 @@ def load_checkpoint(path: str, model, optimizer=None, strict: bool = True) -> di
     if optimizer is not None and "optimizer" in blob and hasattr(optimizer, "load_state_dict"):
         optimizer.load_state_dict(blob["optimizer"])
     return {k: v for k, v in blob.items() if k not in ("model", "optimizer")}
+
+
+def _is_main_process() -> bool:
+    dist = torch.distributed
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
+def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler, model_ema=None, best: bool = False) -> None:
+    """``helpers.save_model`` (``helpers.py:529-565``): rank 0 writes ``<output_dir>/checkpoint-<epoch>.pth`` with the
+    reference's entries (``model``, ``optimizer``, ``epoch``, ``scaler``, ``args``) and removes the checkpoint that falls out
+    of the ``save_ckpt_num x save_ckpt_freq`` window.  Tensors are moved to the host first (the flat AdamW state is two
+    device buffers)."""
+    import os
+
+    def host(obj):
+        if torch.is_tensor(obj):
+            return obj.detach().cpu()
+        if isinstance(obj, dict):
+            return {k: host(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(host(v) for v in obj)
+        return obj
+
+    if not _is_main_process():
+        return
+    os.makedirs(args.output_dir, exist_ok=True)
+    blob = {"model": host(model_without_ddp.state_dict()), "optimizer": host(optimizer.state_dict()), "epoch": epoch,
+            "scaler": host(loss_scaler.state_dict()), "args": args}
+    if model_ema is not None:
+        blob["model_ema"] = host(model_ema.state_dict())
+    torch.save(blob, os.path.join(args.output_dir, "checkpoint-%s.pth" % str(epoch)))
+    if isinstance(epoch, int):
+        old = os.path.join(args.output_dir, "checkpoint-%s.pth" % (epoch - args.save_ckpt_num * args.save_ckpt_freq))
+        if os.path.exists(old):
+            os.remove(old)
+
+
+def auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler, model_ema=None) -> None:
+    """``helpers.auto_load_model`` (``helpers.py:568-610``): with ``args.auto_resume`` and no explicit ``args.resume`` the
+    newest ``checkpoint-<int>.pth`` of ``args.output_dir`` is taken; model, optimizer, scaler are restored and
+    ``args.start_epoch`` is set to the epoch after the checkpoint's."""
+    import glob
+    import os
+
+    if getattr(args, "auto_resume", False) and len(getattr(args, "resume", "") or "") == 0:
+        latest = -1
+        for ckpt in glob.glob(os.path.join(args.output_dir, "checkpoint-*.pth")):
+            t = ckpt.split("-")[-1].split(".")[0]
+            if t.isdigit():
+                latest = max(int(t), latest)
+        if latest >= 0:
+            args.resume = os.path.join(args.output_dir, "checkpoint-%d.pth" % latest)
+    if not getattr(args, "resume", ""):
+        return
+    if args.resume.startswith("https"):
+        blob = torch.hub.load_state_dict_from_url(args.resume, map_location="cpu", check_hash=True)
+    else:
+        blob = torch.load(args.resume, map_location="cpu", weights_only=False)
+    model_without_ddp.load_state_dict(blob["model"])
+    if "optimizer" in blob and "epoch" in blob:
+        optimizer.load_state_dict(blob["optimizer"])
+        if not isinstance(blob["epoch"], str):
+            args.start_epoch = blob["epoch"] + 1
+        if "scaler" in blob:
+            loss_scaler.load_state_dict(blob["scaler"])

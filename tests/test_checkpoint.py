@@ -72,3 +72,86 @@ def test_save_load_roundtrip(native_lib, tmp_path):
     save_checkpoint(p, a, epoch=7, extra={"args": {"model": "convnextv2_atto"}})
     rest = load_checkpoint(p, b)
     assert torch.equal(a.w, b.w) and rest["epoch"] == 7 and rest["args"]["model"] == "convnextv2_atto"
+
+
+def test_save_model_rotation_and_auto_resume(tmp_path):
+    """helpers.save_model / auto_load_model semantics (helpers.py:529-610) with stand-in objects: file naming, the rotation
+    window, newest-checkpoint pick, start_epoch, optimizer and scaler state."""
+    from argparse import Namespace
+    import os
+    from mmearth_train_b200 import checkpoint as ck
+
+    class Scaler:
+        def __init__(self):
+            self.scale = 65536.0
+
+        def state_dict(self):
+            return {"scale": self.scale}
+
+        def load_state_dict(self, sd):
+            self.scale = sd["scale"]
+
+    torch.manual_seed(0)
+    net = torch.nn.Linear(4, 3)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    scaler = Scaler()
+    args = Namespace(output_dir=str(tmp_path / "run"), save_ckpt_num=2, save_ckpt_freq=1, auto_resume=True, resume="", start_epoch=0)
+    for epoch in range(4):
+        net(torch.randn(2, 4)).sum().backward()
+        opt.step()
+        scaler.scale = 65536.0 * (epoch + 1)
+        ck.save_model(args, epoch, net, net, opt, scaler)
+    assert sorted(os.listdir(args.output_dir)) == ["checkpoint-2.pth", "checkpoint-3.pth"]      # window of 2
+    ck.save_model(args, "best", net, net, opt, scaler)                                          # non-integer tags are kept
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    step_before = opt.state_dict()["state"][0]["step"]
+
+    net2 = torch.nn.Linear(4, 3)
+    opt2 = torch.optim.AdamW(net2.parameters(), lr=1e-3)
+    scaler2 = Scaler()
+    args2 = Namespace(output_dir=args.output_dir, auto_resume=True, resume="", start_epoch=0)
+    ck.auto_load_model(args2, net2, net2, opt2, scaler2)
+    assert args2.resume.endswith("checkpoint-3.pth") and args2.start_epoch == 4
+    assert all(torch.equal(net2.state_dict()[k], v) for k, v in want.items())
+    assert opt2.state_dict()["state"][0]["step"] == step_before and scaler2.scale == 65536.0 * 4
+    blob = torch.load(args2.resume, map_location="cpu", weights_only=False)
+    assert set(blob) == {"model", "optimizer", "epoch", "scaler", "args"}                      # helpers.py:545-551
+
+    args3 = Namespace(output_dir=str(tmp_path / "empty"), auto_resume=True, resume="", start_epoch=0)
+    ck.auto_load_model(args3, net2, net2, opt2, scaler2)                                        # nothing to resume: a no-op
+    assert args3.start_epoch == 0 and args3.resume == ""
+
+
+def test_checkpoint_written_by_the_reference_resumes_here(tmp_path):
+    """A checkpoint written by the unmodified helpers.save_model is picked up by auto_load_model (build container only)."""
+    import sys
+    from argparse import Namespace
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("needs /root/reference")
+    ref_harness.load_reference()
+    if ref_harness.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_harness.REFERENCE_ROOT)
+    import helpers
+    from mmearth_train_b200 import checkpoint as ck
+    torch.manual_seed(1)
+    net = torch.nn.Linear(5, 2)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    net(torch.randn(3, 5)).sum().backward()
+    opt.step()
+    scaler = helpers.NativeScalerWithGradNormCount("cpu")
+    args = Namespace(output_dir=str(tmp_path), save_ckpt_num=3, save_ckpt_freq=1)
+    helpers.save_model(args, 7, net, net, opt, scaler)
+    ours = ck.__dict__                                                       # and ours writes the same entries
+    args_b = Namespace(output_dir=str(tmp_path / "b"), save_ckpt_num=3, save_ckpt_freq=1)
+    ours["save_model"](args_b, 7, net, net, opt, scaler)
+    a = torch.load(str(tmp_path / "checkpoint-7.pth"), map_location="cpu", weights_only=False)
+    b = torch.load(str(tmp_path / "b" / "checkpoint-7.pth"), map_location="cpu", weights_only=False)
+    assert set(a) == set(b) and a["epoch"] == b["epoch"] == 7
+    assert all(torch.equal(a["model"][k], b["model"][k]) for k in a["model"])
+
+    net2 = torch.nn.Linear(5, 2)
+    opt2 = torch.optim.AdamW(net2.parameters(), lr=1e-3)
+    args2 = Namespace(output_dir=str(tmp_path), auto_resume=True, resume="", start_epoch=0)
+    ck.auto_load_model(args2, net2, net2, opt2, helpers.NativeScalerWithGradNormCount("cpu"))
+    assert args2.start_epoch == 8 and torch.equal(net2.weight, net.weight)
