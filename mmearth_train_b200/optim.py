@@ -77,6 +77,8 @@ class FlatGradScaler:
                 "growth_interval": self.growth_interval, "_growth_tracker": int(self._growth)}
 
     def load_state_dict(self, sd):
+        if not sd:                  # a disabled torch GradScaler (CPU run) saves an empty dict
+            return
         self._scale = torch.full((), float(sd["scale"]), device=self.device)
         self._growth = torch.full((), int(sd["_growth_tracker"]), dtype=torch.int32, device=self.device)
         self.growth_factor, self.backoff_factor = sd["growth_factor"], sd["backoff_factor"]
