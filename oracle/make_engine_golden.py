@@ -16,7 +16,6 @@ import contextlib
 import io
 import json
 import os
-import sys
 from argparse import Namespace
 
 import torch
@@ -75,11 +74,8 @@ class _Writer:
 
 
 def run_reference_engine(cfg):
-    ref = ref_harness.load_reference()
-    if ref_harness.REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, ref_harness.REFERENCE_ROOT)           # engine_pretrain does `import helpers`
-    import engine_pretrain
-    import helpers
+    helpers = ref_harness.import_toplevel("helpers")             # engine_pretrain does `import helpers`
+    engine_pretrain = ref_harness.import_toplevel("engine_pretrain")
     orc, batches, noises = case_inputs(cfg)
     model, _ = ref_harness.build_reference_model(model=cfg["model"], img_size=cfg["img_size"], patch_size=cfg["patch_size"],
                                                  out_modalities=cfg["out_modalities"], loss_aggr=cfg["loss_aggr"])

@@ -97,6 +97,21 @@ def load_reference():
     return _loaded
 
 
+def import_toplevel(name: str):
+    """Import one of the reference's top-level scripts (``helpers``, ``engine_pretrain``: they import each other by bare
+    name) with the reference root on ``sys.path`` only for the duration of the import -- the root also holds a ``tests``
+    package that would otherwise shadow this repository's in spawned worker processes."""
+    load_reference()
+    import importlib
+    if name in sys.modules:
+        return sys.modules[name]
+    sys.path.append(REFERENCE_ROOT)
+    try:
+        return importlib.import_module(name)
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+
+
 def make_args(out_modalities=None, loss_aggr="uncertainty", use_orig_stem=False) -> Namespace:
     """The fields ``main_pretrain.py:175-180`` puts on ``args`` and ``FCMAE`` reads."""
     ref = load_reference()

@@ -124,15 +124,11 @@ def test_save_model_rotation_and_auto_resume(tmp_path):
 
 def test_checkpoint_written_by_the_reference_resumes_here(tmp_path):
     """A checkpoint written by the unmodified helpers.save_model is picked up by auto_load_model (build container only)."""
-    import sys
     from argparse import Namespace
     from oracle import ref_harness
     if not ref_harness.reference_available():
         pytest.skip("needs /root/reference")
-    ref_harness.load_reference()
-    if ref_harness.REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, ref_harness.REFERENCE_ROOT)
-    import helpers
+    helpers = ref_harness.import_toplevel("helpers")
     from mmearth_train_b200 import checkpoint as ck
     torch.manual_seed(1)
     net = torch.nn.Linear(5, 2)
