@@ -111,3 +111,31 @@ def test_product_synthetic_generator_equals_the_oracles_and_the_reference_modali
         assert M.INP_MODALITIES["sentinel2"] == syn.S2_BANDS
         full = {k: len(v) for k, v in M.MODALITIES_FULL.items()}
         assert {k: full[k] for k in syn.FULL_BANDS} == syn.FULL_BANDS      # (the reference also lists three S2 mask products)
+
+
+@pytest.mark.parametrize("name,patch,img", [("convnextv2_femto", 8, 56), ("convnextv2_pico", 8, 56), ("convnextv2_nano", 16, 112),
+                                            ("convnextv2_tiny", 8, 56), ("convnextv2_base", 8, 56)])
+def test_every_supported_factory_has_the_oracles_state_dict_and_decay_rule(native_lib, name, patch, img):
+    """Plan creation is host-only: parameter names / shapes of every factory the kernels accept equal the oracle's state dict
+    (whose surface is pinned to the reference's by the fixtures), and the per-parameter decay flag is timm's rule
+    (ndim <= 1 or *.bias -> no decay; main_pretrain.py:312-319)."""
+    import mmearth_train_b200 as mp
+    args = fo.make_args(None, "uncertainty")
+    m = getattr(mp, name)(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True, patch_size=patch,
+                          img_size=img, args=args, loss_fn=mp.UncertaintyWeightingStrategy(12))
+    orc = fo.build_oracle(model=name, img_size=img, patch_size=patch)
+    want = {k: tuple(v.shape) for k, v in orc.state_dict().items()}
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    mask = m.decay_mask()
+    unique = {}
+    for n, p in m.named_parameters():
+        if n != "_ddp_token":
+            unique.setdefault(p.data_ptr(), (n, p))
+    for n, p in unique.values():
+        off = (p.data_ptr() - m.flat_params.data_ptr()) // 4
+        decayed = bool(mask[off]) and bool(mask[off + p.numel() - 1])
+        assert decayed == (not (p.ndim <= 1 or n.endswith(".bias"))), n
+    assert sum(p.numel() for _, p in unique.values()) == sum(p.numel() for p in {id(q): q for q in orc.parameters()}.values())
+    plan = m._plan(64)
+    assert plan.workspace_bytes > 0 and plan.launches(False) == 0        # launch counts are filled in by the first call
