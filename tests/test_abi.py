@@ -90,3 +90,28 @@ def test_visible_patch_count_follows_python_int(native_lib):
         c = _cfg(nat)
         c.mask_ratio = mr
         assert nat.Plan(c).visible == int(49 * (1 - mr)), mr
+
+
+def test_entry_points_validate_their_arguments_before_touching_the_device(native_lib):
+    """Argument errors are reported as negative codes + a message, never as a crash or an exception (no GPU needed: every
+    check below fails before the first CUDA call)."""
+    nat = native_lib
+    plan = nat.Plan(_cfg(nat))
+    io = nat.IO()                                            # all pointers null
+    st = C.c_void_p(0)
+    for fn, args in ((nat.lib.mpmae_forward, (plan.handle, C.byref(io), st)),
+                     (nat.lib.mpmae_forward_encoder, (plan.handle, C.byref(io), st)),
+                     (nat.lib.mpmae_backward, (plan.handle, C.byref(io), st)),
+                     (nat.lib.mpmae_forward_stages, (plan.handle, C.byref(io), nat.STAGE_MASK | nat.STAGE_LOSS, st))):
+        assert fn(*args) == -1 and b"null" in nat.lib.mpmae_last_error()
+    for stages in (0, -1, 16, 255):                          # not a MPMAE_STAGE_* mask
+        assert nat.lib.mpmae_forward_stages(plan.handle, C.byref(io), stages, st) == -1
+        assert b"stages" in nat.lib.mpmae_last_error()
+    assert nat.lib.mpmae_backward_part(plan.handle, C.byref(io), 3, st) < 0
+    assert nat.lib.mpmae_adamw_step(None, None, None, None, None, 16, 1e-3, 0.9, 0.95, 1e-8, 0.05, 1, 1.0, st) == -1
+    assert nat.lib.mpmae_adamw_step_dev(None, None, None, None, None, 16, 1e-3, 0.9, 0.95, 1e-8, 0.05, None, st) == -1
+    lo, hi = C.c_int64(), C.c_int64()
+    assert nat.lib.mpmae_backward_part_range(plan.handle, 5, C.byref(lo), C.byref(hi)) < 0
+    assert nat.lib.mpmae_tap_info(plan.handle, b"no.such.tap", C.byref(lo), C.byref(hi), C.byref(C.c_int64())) < 0
+    with pytest.raises(nat.NativeError, match="no.such.tap"):
+        plan.tap("no.such.tap")
