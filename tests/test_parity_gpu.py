@@ -298,10 +298,11 @@ def test_non_finite_input_is_zeroed_like_nan_to_num():
     assert abs(float(loss_a) - float(o_loss)) <= 1e-3 * abs(float(o_loss))
 
 
-def test_all_visible_encoder_is_the_dense_convnextv2_encoder():
-    """mask_ratio = 0: every patch is visible and the sparse encoder equals the dense ConvNeXt-V2 feature extractor with
-    the same (re-laid-out) weights -- the consumer the reference gets by remap_checkpoint_keys (helpers.py:668-707,
-    SURVEY.md 8f rank 4).  Checked against the oracle's encoder with an all-zero mask."""
+def test_all_visible_mask_ratio_zero_matches_oracle():
+    """mask_ratio = 0: every patch is visible (V = L) -- the sparse encoder as a plain feature extractor, the geometry an
+    inference consumer of the pretrained encoder uses.  Checked against the oracle's encoder with an all-zero mask.  (This is
+    the SPARSE network on a full image; the reference's dense ConvNeXtV2, models/convnextv2.py:108-124, is a different
+    network: un-padded 3x3 stem convolution, per-sample GRN.)"""
     z, meta, orc, batch, noise = gu.inputs("atto_p8_all_unc")
     model = build_native(meta["cfg"], orc, 3)
     s2 = batch["sentinel2"]
