@@ -88,3 +88,56 @@ def test_fixture_generator_still_matches_the_live_reference():
     assert _close(live["stats"]["loss"], gold["stats"]["loss"], 1e-6)
     assert [r["step"] for r in live["logged"]] == [r["step"] for r in gold["logged"]]
     assert _close(live["final_param_norm"], gold["final_param_norm"], 1e-9)
+
+
+def test_loop_device_branch_with_stand_in_transport(monkeypatch):
+    """The branch the loop takes for a CUDA device (DevicePrefetcher + LossReader + the module's own loss vector), exercised
+    without a GPU: the two transport classes are replaced by host stand-ins with the same interface and the model publishes
+    ``last_run["losses"]`` like the native module.  Same golden trajectory, so the branch's bookkeeping is the checked one."""
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "engine_all_unc_accum.json")))
+    cfg = gold["cfg"]
+    orc, batches, noises = meg.case_inputs(cfg)
+    args = meg.loop_args(cfg)
+    made = {}
+
+    class Prefetch:
+        def __init__(self, src, device, depth=2):
+            made["prefetch"] = (device.type, depth)
+            self.src = src
+
+        def __iter__(self):
+            return iter(self.src)
+
+    class Reader(engine._LaggedHostReader):
+        def __init__(self, device, depth=2, width=1):
+            made["reader"] = (device.type, depth, width)
+            super().__init__(depth)
+
+        def push(self, value):
+            assert value.shape == (made["reader"][2],)
+            return super().push(value)
+
+    class Native(_Replay):
+        def forward(self, samples, labels=None, mask_ratio=0.6):
+            out = super().forward(samples, labels, mask_ratio)
+            per = torch.stack([v.detach() for v in out[3].values()])
+            self.last_run = {"losses": torch.cat([per, out[5].detach(), out[0].detach().reshape(1)])}
+            return out
+
+    monkeypatch.setattr(engine, "DevicePrefetcher", Prefetch)
+    monkeypatch.setattr(engine, "LossReader", Reader)
+    model = Native(orc, noises)
+    model.out_modalities, model.loss_aggr = list(orc.args.out_modalities), "uncertainty"
+    optimizer = torch.optim.AdamW(meg.param_groups_weight_decay(orc, args.weight_decay), lr=args.lr, betas=(0.9, 0.95))
+    writer = meg._Writer()
+    stats, loss_dict, log_vars, normalized = engine.train_one_epoch(
+        model, None, [(i, b) for i, b in enumerate(batches)], optimizer, torch.device("cuda"), cfg["epoch"], False, _CpuScaler(),
+        log_writer=writer, args=args, lag=2, quiet=True)
+    assert made == {"prefetch": ("cuda", 2), "reader": ("cuda", 2, 25)}
+    assert _close(stats["loss"], gold["stats"]["loss"]) and _close(stats["lr"], gold["stats"]["lr"], 1e-12)
+    assert all(_close(loss_dict[m], v) for m, v in gold["loss_dict"].items())
+    assert all(_close(float(a), b) for a, b in zip(normalized, gold["normalized"]))
+    got = [r for r in writer.rows if r["head"] == "loss"]
+    want = [r for r in gold["logged"] if r["head"] == "loss"]
+    assert [r["step"] for r in got] == [r["step"] for r in want]
+    assert all(_close(g["train_loss"], w["train_loss"]) for g, w in zip(got, want))
