@@ -15,6 +15,11 @@ value, and differs only in how the host learns what happened:
 * no ``empty_cache``: nothing is allocated per step.
 
 SURVEY.md section 8f ranks 1, 2 and 4.
+
+The loop itself computes nothing: it moves batches and reads losses.  With a CUDA device it uses the two transport classes above;
+with ``device.type == "cpu"`` it iterates host tensors directly -- that branch exists so the tests can replay golden trajectories
+of the unmodified reference loop through THIS loop around the CPU oracle (``tests/test_engine_golden.py``).  It is not a CPU
+fallback of the step: the native ``FCMAE`` refuses non-CUDA tensors whatever loop drives it.
 """
 from __future__ import annotations
 
