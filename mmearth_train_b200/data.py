@@ -115,3 +115,101 @@ class LossReader:
             if self._busy[slot]:
                 out.append(self._take(slot))
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Stored-dtype batches -> model-ready batches, on the device.
+#: value that marks "no data" in the stored arrays (MODALITIES.py:37-53)
+NO_DATA_VAL = {"sentinel2": 0, "sentinel1": float("-inf"), "aster": float("-inf"), "canopy_height_eth": 255, "dynamic_world": 0,
+               "esa_worldcover": 0, "lat": float("-inf"), "lon": float("-inf"), "month": float("-inf"), "era5": float("nan"),
+               "biome": 255, "eco_region": 65535}
+#: modalities whose targets are class indices (MODALITIES.py:163-180: "segmentation" / "classification")
+CLASS_TARGETS = ("esa_worldcover", "dynamic_world", "biome", "eco_region")
+_NOT_NORMALISED = ("biome", "eco_region", "dynamic_world", "esa_worldcover")
+
+
+def _label_lut(modality: str) -> torch.Tensor:
+    """256-entry table stored label -> class index (NaN = ignore), built by replaying the loader's rule on every byte value:
+    dynamic_world 0 -> no data, 1..9 -> 0..8, anything else -> ignore (``mmearth_dataset.py:88-97``); esa_worldcover 0 -> no
+    data, 10, 20, .., 90, 95, 100 -> 0..10 applied ONE AFTER THE OTHER, then anything above 10 -> ignore (``:99-108``; stored
+    values 1..9 therefore pass through as classes, exactly as in the reference).  See the note on class 0 below."""
+    v = torch.arange(256, dtype=torch.float64)
+    nan = torch.full_like(v, float("nan"))
+    v = torch.where(v == NO_DATA_VAL[modality], nan, v)
+    if modality == "dynamic_world":
+        olds, news, top = range(1, 10), range(0, 9), 8
+    else:
+        olds, news, top = (10, 20, 30, 40, 50, 60, 70, 80, 90, 95, 100), range(0, 11), 10
+    for old, new in zip(olds, news):
+        v = torch.where(v == old, torch.full_like(v, float(new)), v)
+    v = torch.where(v > top, nan, v)
+    if modality != "dynamic_world":
+        # the loader's general no-data pass runs AFTER the remap (``:110-115``) and esa_worldcover's no-data value is 0: the
+        # freshly remapped class 0 (stored 10, tree cover) becomes "ignore" as well.  Kept, because it is what the reference trains on.
+        v = torch.where(v == NO_DATA_VAL[modality], nan, v)
+    return v
+
+
+class RawBatchTransform:
+    """``MMEarthDataset.__getitem__`` (``mmearth_dataset.py:58-153``) for a whole batch, on whatever device the tensors are on.
+
+    The reference widens every sample to float32 / int64 in the loader workers (band selection, label remap, no-data -> NaN,
+    per-band z-scoring, NaN -> -1 for class targets), so a 256-sample batch crosses PCIe as 91.7 MB.  Here the loader hands
+    over the arrays as they are STORED (uint16 Sentinel-2, uint8 label maps and canopy height, float32 for the rest), they are
+    copied in that form (``DevicePrefetcher``) and this transform runs after the copy with a handful of elementwise torch
+    kernels.  Same arithmetic as the reference (float64 subtraction / division, then float32) unless ``exact=False``.
+
+    ``modalities`` / ``modalities_full`` / ``band_stats`` are the ``args`` fields of the same names
+    (``mmearth_dataset.py:36-50``); ``l2a`` says per sample which Sentinel-2 statistics apply (``tile_info[..]["S2_type"]``).
+    """
+
+    def __init__(self, modalities: Dict[str, object], modalities_full: Dict[str, list], band_stats: Dict[str, dict],
+                 exact: bool = True):
+        self.modalities, self.exact = dict(modalities), exact
+        self._idx, self._stats, self._lut = {}, {}, {}
+        for m, bands in self.modalities.items():
+            if m not in NO_DATA_VAL:
+                raise ValueError(f"unknown modality {m!r}")
+            full = list(modalities_full[m])
+            idx = list(range(len(full))) if bands == "all" else [full.index(b) for b in bands]
+            self._idx[m] = torch.tensor(idx, dtype=torch.long)
+            if m not in _NOT_NORMALISED:
+                keys = ("sentinel2_l1c", "sentinel2_l2a") if m == "sentinel2" else (m, m)
+                self._stats[m] = torch.stack([torch.tensor([band_stats[k]["mean"], band_stats[k]["std"]],
+                                                           dtype=torch.float64)[:, idx] for k in keys])      # [2 (l1c/l2a), 2, nb]
+            if m in ("dynamic_world", "esa_worldcover"):
+                self._lut[m] = _label_lut(m)
+
+    def _on(self, cache: dict, m: str, device) -> torch.Tensor:
+        t = cache[m]
+        if t.device != device:
+            t = cache[m] = t.to(device)
+        return t
+
+    def __call__(self, raw: Dict[str, torch.Tensor], l2a: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = {}
+        for m in self.modalities:
+            x = raw[m]
+            dev = x.device
+            if m in self._lut:                                   # label maps: one gather through the 256-entry table
+                x = x.index_select(1, self._on(self._idx, m, dev))
+                v = self._on(self._lut, m, dev)[x.long()]
+            else:
+                v = x.double() if self.exact else x.float()      # widen first: torch.uint16 supports little besides conversion
+                if m not in ("biome", "eco_region"):             # one-hot rows are taken whole (mmearth_dataset.py:76-79)
+                    v = v.index_select(1, self._on(self._idx, m, dev))
+                nd = NO_DATA_VAL[m]
+                if nd == nd:                                     # NaN marks nothing: `data == nan` is never true
+                    v = torch.where(v == nd, torch.full_like(v, float("nan")), v)
+            if m in self._stats:
+                st = self._on(self._stats, m, dev)[l2a.to(dev).long()]                  # [B, 2, nb]
+                shape = st.shape[:1] + st.shape[2:] + (1,) * (v.dim() - 2)
+                mean, std = st[:, 0].reshape(shape), st[:, 1].reshape(shape)
+                if not self.exact:
+                    mean, std = mean.float(), std.float()
+                v = (v - mean) / std
+            if m in CLASS_TARGETS:
+                out[m] = torch.where(torch.isnan(v), torch.full_like(v, -1.0), v).long()
+            else:
+                out[m] = v.float()
+        return out
