@@ -229,3 +229,33 @@ def _all_reduce_mean(x: float, device: torch.device) -> float:
     t = torch.tensor(x, device=device)
     dist.all_reduce(t)
     return float(t.item() / dist.get_world_size())
+
+
+def fit(model, model_without_ddp, data_loader, optimizer, loss_scaler, device, args, log_writer=None, quiet: bool = True,
+        lag: int = 2) -> List[dict]:
+    """The epoch loop of ``main_pretrain.main`` (``main_pretrain.py:322-366``): resume from the newest checkpoint when
+    ``args.auto_resume`` says so, then for every epoch from ``args.start_epoch`` run ``train_one_epoch`` and write a checkpoint
+    every ``args.save_ckpt_freq`` epochs and after the last one.  Returns the per-epoch statistics (``train_<meter>`` keys plus
+    ``epoch``, as the reference logs them)."""
+    from . import checkpoint
+
+    if not hasattr(args, "start_epoch"):
+        args.start_epoch = 0
+    if getattr(args, "output_dir", ""):
+        checkpoint.auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler)
+    history = []
+    for epoch in range(args.start_epoch, args.epochs):
+        sampler = getattr(data_loader, "sampler", None)
+        if hasattr(sampler, "set_epoch"):                                      # main_pretrain.py:337-338
+            sampler.set_epoch(epoch)
+        stats, loss_dict, log_vars, normalized = train_one_epoch(model, getattr(args, "modalities", None), data_loader, optimizer,
+                                                                 device, epoch, False, loss_scaler, log_writer=log_writer,
+                                                                 args=args, lag=lag, quiet=quiet)
+        if getattr(args, "output_dir", "") and getattr(args, "save_ckpt", True):
+            if (epoch + 1) % args.save_ckpt_freq == 0 or epoch + 1 == args.epochs:
+                checkpoint.save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler)
+        row = {f"train_{k}": v for k, v in stats.items()}
+        row.update(epoch=epoch, loss_dict=loss_dict, log_vars=log_vars,
+                   normalized=None if normalized is None else [float(v) for v in normalized])
+        history.append(row)
+    return history

@@ -141,3 +141,54 @@ def test_loop_device_branch_with_stand_in_transport(monkeypatch):
     want = [r for r in gold["logged"] if r["head"] == "loss"]
     assert [r["step"] for r in got] == [r["step"] for r in want]
     assert all(_close(g["train_loss"], w["train_loss"]) for g, w in zip(got, want))
+
+
+def test_fit_interrupted_and_resumed_equals_uninterrupted(tmp_path):
+    """Checkpoint / resume through the epoch loop (main_pretrain.py:322-366 + helpers.save_model / auto_load_model): a run that
+    dies in the middle of its third epoch and is started again with auto_resume ends with the same per-epoch statistics and
+    the same weights, bit for bit, as a run that was never interrupted."""
+    from argparse import Namespace
+    from oracle import fcmae_oracle as fo
+
+    class Scaler(_CpuScaler):
+        def state_dict(self):
+            return {}
+
+        def load_state_dict(self, sd):
+            pass
+
+    class Crash(Exception):
+        pass
+
+    def launch(out_dir, crash_at_step=None):
+        """One process lifetime: fresh objects, weights / optimizer state come from the newest checkpoint if there is one."""
+        orc = fo.build_oracle(out_modalities=["sentinel2"], loss_aggr="unweighted")
+        fo.init_like_reference(orc, seed=3)
+        batches = [fo.synthetic_batch(2, 56, ["sentinel2"], seed=60 + i) for i in range(2)]
+        opt = torch.optim.AdamW(meg.param_groups_weight_decay(orc, 0.05), lr=3e-4, betas=(0.9, 0.95))
+        args = Namespace(update_freq=1, lr=3e-4, min_lr=1e-6, warmup_epochs=1, epochs=4, mask_ratio=0.6, no_ffcv=True,
+                         output_dir=str(out_dir), auto_resume=True, resume="", save_ckpt=True, save_ckpt_freq=1, save_ckpt_num=2)
+
+        class Model(_Replay):
+            def forward(self, samples, labels=None, mask_ratio=0.6):
+                step = int(next(iter(opt.state.values()))["step"]) if len(opt.state) else 0     # restored with the optimizer
+                if crash_at_step is not None and step == crash_at_step:
+                    raise Crash()
+                g = torch.Generator().manual_seed(1000 + step)                                   # masks resumable by step
+                return self.orc(samples, mask_ratio=mask_ratio, noise=torch.randn(2, 49, generator=g))
+
+        hist = engine.fit(Model(orc, []), orc, [(i, b) for i, b in enumerate(batches)], opt, Scaler(), torch.device("cpu"), args)
+        norm = float(torch.sqrt(sum((p.detach().double() ** 2).sum() for p in {id(p): p for p in orc.parameters()}.values())))
+        return hist, norm
+
+    whole, norm_a = launch(tmp_path / "a")
+    with pytest.raises(Crash):
+        launch(tmp_path / "b", crash_at_step=5)                     # 2 iterations per epoch: dies inside epoch 2
+    assert sorted(os.listdir(tmp_path / "b")) == ["checkpoint-0.pth", "checkpoint-1.pth"]
+    rest, norm_b = launch(tmp_path / "b")
+    assert [h["epoch"] for h in whole] == [0, 1, 2, 3] and [h["epoch"] for h in rest] == [2, 3]
+    for a, b in zip(whole[2:], rest):
+        assert a["train_loss"] == b["train_loss"] and a["train_lr"] == b["train_lr"], (a["epoch"], a["train_loss"], b["train_loss"])
+    assert norm_a == norm_b
+    assert sorted(os.listdir(tmp_path / "b")) == ["checkpoint-2.pth", "checkpoint-3.pth"]
+    assert whole[-1]["train_loss"] < whole[0]["train_loss"]
