@@ -64,7 +64,9 @@ def band_stats(seed: int = 7):
     return {k: {"mean": r.uniform(-5, 2000, size=n).tolist(), "std": r.uniform(0.5, 900, size=n).tolist()} for k, n in full.items()}
 
 
-def main():
+def run_reference(mods=None):
+    """(raw arrays, band statistics, l2a flags, modality dict, {modality: stacked reference outputs}) for the given
+    ``modalities`` dict (default: the reference's INP + OUT modalities)."""
     _stub = types.ModuleType("h5py")
     _stub.File = object
     sys.modules.setdefault("h5py", _stub)
@@ -76,8 +78,9 @@ def main():
     tile_info = {n: {"S2_type": "l2a" if i % 2 else "l1c"} for i, n in enumerate(names)}
     splits = os.path.join("/tmp", "mpmae_ds_splits.json")
     json.dump({"train": list(range(N))}, open(splits, "w"))
-    mods = dict(M.INP_MODALITIES)
-    mods.update(M.OUT_MODALITIES)
+    if mods is None:
+        mods = dict(M.INP_MODALITIES)
+        mods.update(M.OUT_MODALITIES)
     args = Namespace(data_path=None, data_name="synthetic", splits_path=splits, tile_info=tile_info, modalities=mods,
                      modalities_full=dict(M.MODALITIES_FULL), band_stats=stats)
     ds = ds_mod.MMEarthDataset(args, split="train")
@@ -91,9 +94,15 @@ def main():
         for m, v in sample.items():
             if m != "id":
                 out.setdefault(m, []).append(np.asarray(v))
+    l2a = np.array([tile_info[n]["S2_type"] == "l2a" for n in names])
+    return raw, stats, l2a, mods, {k: np.stack(v) for k, v in out.items()}, dict(M.MODALITIES_FULL)
+
+
+def main():
+    raw, stats, l2a, mods, out, _full = run_reference()
     arrays = {f"raw.{k}": v for k, v in raw.items()}
-    arrays.update({f"out.{k}": np.stack(v) for k, v in out.items()})
-    arrays["l2a"] = np.array([tile_info[n]["S2_type"] == "l2a" for n in names])
+    arrays.update({f"out.{k}": v for k, v in out.items()})
+    arrays["l2a"] = l2a
     arrays["meta"] = np.frombuffer(json.dumps({"band_stats": stats, "modalities": {k: v for k, v in mods.items()},
                                                "order": list(out)}).encode(), dtype=np.uint8)
     np.savez_compressed(OUT, **arrays)

@@ -64,3 +64,23 @@ def test_label_tables():
 def test_unknown_modality_is_refused():
     with pytest.raises(ValueError):
         RawBatchTransform({"sentinel3": "all"}, {"sentinel3": ["a"]}, {})
+
+
+def test_band_subsets_against_the_live_reference_loader():
+    """Explicit band lists for several modalities (the fixture only has Sentinel-2's 12-of-13): the unmodified loader is run
+    here on the same raw arrays (build container only)."""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("needs /root/reference")
+    from oracle import make_dataset_golden as mdg
+    mods = {"sentinel2": ["B4", "B3", "B2", "B8"], "sentinel1": ["desc_VV", "asc_VH"], "era5": ["year_avg_temp", "curr_month_total_precip"],
+            "aster": ["slope"], "canopy_height_eth": "all", "esa_worldcover": "all", "dynamic_world": "all", "biome": "all",
+            "lat": ["cos"], "month": "all"}
+    raw, stats, l2a, mods, want, full = mdg.run_reference(mods)
+    got = RawBatchTransform(mods, full, stats)({k: torch.from_numpy(v) for k, v in raw.items()}, torch.from_numpy(l2a))
+    assert list(got) == list(want)
+    for m, w in want.items():
+        g = got[m].numpy()
+        assert g.dtype == w.dtype and g.shape == w.shape, m
+        assert np.array_equal(np.isnan(g.astype(np.float64)), np.isnan(w.astype(np.float64))), m
+        assert np.array_equal(np.nan_to_num(g.astype(np.float64)), np.nan_to_num(w.astype(np.float64))), m
