@@ -27,9 +27,14 @@ CONFIGS = {  # BASELINE.json configs (per-GPU batch, weak scaling)
     "cfg2": dict(model="convnextv2_atto", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty", batch=256),
     "cfg3": dict(model="convnextv2_atto", img_size=112, patch_size=16, out_modalities=None, loss_aggr="uncertainty", batch=128),
     "cfg4": dict(model="convnextv2_tiny", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty", batch=64),
+    "cfg5a": dict(model="convnextv2_atto", img_size=56, patch_size=8, loss_aggr="unweighted", batch=256,
+                  out_modalities=["sentinel2", "sentinel1", "aster", "dynamic_world", "canopy_height_eth", "esa_worldcover"]),
+    "cfg5b": dict(model="convnextv2_atto", img_size=56, patch_size=8, loss_aggr="unweighted", batch=256,
+                  out_modalities=["era5", "lat", "lon", "biome", "eco_region", "month"]),
 }
 # algorithmic work per sample (fwd+bwd): GFLOP, MB
-ALGO = {"cfg1": (2.078, 38.67), "cfg2": (2.389, 30.93), "cfg3": (3.756, 39.57), "cfg4": (11.573, 100.62)}
+ALGO = {"cfg1": (2.078, 38.67), "cfg2": (2.389, 30.93), "cfg3": (3.756, 39.57), "cfg4": (11.573, 100.62),
+        "cfg5a": (2.386, 30.90), "cfg5b": (1.965, 29.42)}
 try:
     METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
 except Exception:
@@ -134,85 +139,65 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
-    ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32, 3 tcgen05 3xBF16 = default)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    a = ap.parse_args()
-    if a.impl == "reference":
-        return run_reference(a)
+class Workload:
+    """One BASELINE.json configuration on this rank: model, optimizer, rotating synthetic batches (pinned host + resident)."""
 
-    import torch
-    import torch.distributed as dist
-    import mmearth_train_b200 as mp
-    from mmearth_train_b200.optim import FlatAdamW
-    from mmearth_train_b200 import synthetic as fo   # synthetic batches + args (the oracle is imported by the cpu_baseline / reference legs only)
+    def __init__(self, name, dev, rank, world, backend=None, nb=4):
+        import torch
+        import torch.distributed as dist
+        import mmearth_train_b200 as mp
+        from mmearth_train_b200.optim import FlatAdamW
+        from mmearth_train_b200 import synthetic as fo   # synthetic batches + args (the oracle is imported by the cpu_baseline / reference legs only)
+        self.name, self.dev, self.rank, self.world, self.nb = name, dev, rank, world, nb
+        cfg = self.cfg = CONFIGS[name]
+        B = self.B = cfg["batch"]
+        args = fo.make_args(cfg["out_modalities"], cfg["loss_aggr"])
+        torch.manual_seed(0 + rank)                                       # main_pretrain.py:202-203
+        lf = mp.UncertaintyWeightingStrategy(len(args.out_modalities)) if cfg["loss_aggr"] == "uncertainty" else None
+        self.model = getattr(mp, cfg["model"])(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True,
+                                               patch_size=cfg["patch_size"], img_size=cfg["img_size"], args=args, loss_fn=lf,
+                                               gemm_backend=backend).to(dev)
+        if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's, main_pretrain.py:306-310)
+            dist.broadcast(self.model.flat_params, 0)
+        self.opt = FlatAdamW(self.model, lr=1.5e-4 * B * world / 256, betas=(0.9, 0.95), weight_decay=0.05)
+        self.host = [self.make_host_batch(rank, i) for i in range(nb)]
+        self.resident = [{k: v.to(dev) for k, v in b.items()} for b in self.host]
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host[0].values())
+        self.net = self.model            # what is called: the module itself, or its DistributedDataParallel wrap (ddp leg)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus and world > 1:
-        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = CONFIGS[a.config]
-    B = cfg["batch"]
-    K, W = a.steps, max(a.warmup, 3)
+    def make_host_batch(self, rank, i):
+        from mmearth_train_b200 import synthetic as fo
+        b = fo.synthetic_batch(self.B, self.cfg["img_size"], self.cfg["out_modalities"], seed=1234 + rank * 100 + i)
+        return {k: v.pin_memory() for k, v in b.items()}
 
-    args = fo.make_args(cfg["out_modalities"], cfg["loss_aggr"])
-    torch.manual_seed(0 + rank)                                       # main_pretrain.py:202-203
-    lf = mp.UncertaintyWeightingStrategy(len(args.out_modalities)) if cfg["loss_aggr"] == "uncertainty" else None
-    model = getattr(mp, cfg["model"])(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True,
-                                      patch_size=cfg["patch_size"], img_size=cfg["img_size"], args=args, loss_fn=lf,
-                                      gemm_backend=a.backend).to(dev)
-    if world > 1:   # identical initial weights on every rank (DDP broadcasts rank 0's, main_pretrain.py:306-310)
-        dist.broadcast(model.flat_params, 0)
-    opt = FlatAdamW(model, lr=1.5e-4 * B * world / 256, betas=(0.9, 0.95), weight_decay=0.05)
-
-    NB = 4
-    host = [fo.synthetic_batch(B, cfg["img_size"], cfg["out_modalities"], seed=1234 + rank * 100 + i) for i in range(NB)]
-    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-
-    def step_resident(i):
-        loss = model(resident[i % NB], mask_ratio=0.6)[0]
+    def step_resident(self, i):
+        loss = self.net(self.resident[i % self.nb], mask_ratio=0.6)[0]
         loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
         return loss
 
-    from mmearth_train_b200.data import DevicePrefetcher, LossReader
-
-    def host_stream(n):                                               # what a DataLoader(pin_memory=True) would yield
-        for i in range(n):
-            yield host[i % NB]
-
-    def run_e2e(n):
+    def run_e2e(self, n):
         """n steps through the public API: pinned host batches in (copy stream, overlapped with the previous step),
         model(batch) -> loss.backward() -> optimizer.step(), and the loss read back to the host every step."""
+        from mmearth_train_b200.data import DevicePrefetcher, LossReader
         last = None
-        reader = LossReader(dev)                                      # every step's loss is read on the host, two steps late
-        for b in DevicePrefetcher(host_stream(n), dev):
-            loss = model(b, mask_ratio=0.6)[0]
+        reader = LossReader(self.dev)                                 # every step's loss is read on the host, two steps late
+        for b in DevicePrefetcher((self.host[i % self.nb] for i in range(n)), self.dev):   # what a DataLoader(pin_memory=True) yields
+            loss = self.net(b, mask_ratio=0.6)[0]
             loss.backward()
-            opt.step()
-            opt.zero_grad(set_to_none=True)
+            self.opt.step()
+            self.opt.zero_grad(set_to_none=True)
             v = reader.push(loss)                                     # D2H read of the step's result (pinned, event-tracked)
             last = v if v is not None else last
         for v in reader.flush():                                      # the reads still in flight land inside the timed region
             last = v
         return last
 
-    def timed(fn, n, whole=False):
-        if world > 1:
+    def timed(self, fn, n, whole=False):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -225,23 +210,132 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms
+
+    def measure(self, K, W):
+        for i in range(W):
+            self.step_resident(i)
+        ms = self.timed(self.step_resident, K)
+        self.run_e2e(W)
+        ms_e2e = self.timed(self.run_e2e, K, whole=True)
+        return ms, ms_e2e
+
+    def summary(self, K, ms, ms_e2e):
+        gf, mb = ALGO[self.name]
+        pk = peaks()
+        n = self.B * self.world * K
+        return {"samples_s": n / (ms / 1e3), "ms_per_step": ms / K, "per_gpu_batch": self.B, "global_batch": self.B * self.world,
+                "step_hbm_frac": (mb * 1e6 * self.B * K / (ms / 1e3)) / (pk["hbm"] * 1e9),
+                "step_tf32_frac": (gf * 1e9 * self.B * K / (ms / 1e3)) / (pk["bf16_sustained"] / 2 * 1e12),
+                "e2e": {"value": n / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": self.h2d_bytes,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K}}
+
+    # ---- multi-GPU correctness (VERDICT r1 missing #3 / next #4)
+    def replica_check(self):
+        """After the timed steps: (1) number of ranks whose parameters differ BITWISE from rank 0's (0 = the replicas stayed
+        identical); (2) one step's all-reduced gradient against the mean of the per-rank gradients computed on ONE GPU from the
+        same parameters, batches and masks (GRN statistics stay per-rank batch, like the reference under DDP)."""
+        import torch
+        import torch.distributed as dist
+        model, dev, world, rank = self.model, self.dev, self.world, self.rank
+        flat = model.flat_params
+        sig = torch.stack([flat.view(torch.int32).long().sum(), (flat.view(torch.int32).long() * 31 % 1000003).sum()])
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        differing = sum(0 if torch.equal(s, sigs[0]) else 1 for s in sigs)
+        noise_of = lambda r: torch.randn(self.B, model.num_patches, generator=torch.Generator().manual_seed(4242 + r))
+        model.noise_override = noise_of(rank)
+        model.zero_grad(set_to_none=True)
+        self.net(self.resident[0], mask_ratio=0.6)[0].backward()          # distributed: gradient = mean over ranks
+        g_dist = model.flat_grads.clone()
+        rel = None
+        dist.barrier()
+        if rank == 0:
+            model.reduce_gradients = False                                 # local backward only
+            acc = torch.zeros_like(g_dist)
+            for r in range(world):
+                b = self.resident[0] if r == 0 else {k: v.to(dev) for k, v in self.make_host_batch(r, 0).items()}
+                model.noise_override = noise_of(r)
+                model.zero_grad(set_to_none=True)
+                model(b, mask_ratio=0.6)[0].backward()
+                acc += model.flat_grads
+            model.reduce_gradients = True
+            acc /= world
+            rel = float((g_dist - acc).norm() / acc.norm())
+        model.noise_override = None
+        model.zero_grad(set_to_none=True)
+        dist.barrier()
+        return {"ranks_differing_from_rank0": differing, "grad_vs_single_gpu_mean_rel_err": rel}
+
+    def ddp_leg(self, K, W):
+        """The same steps through a real ``DistributedDataParallel(model)`` wrap (main_pretrain.py:306-310): DDP manages the
+        token parameter only, the flat gradient buffer is reduced by the module."""
+        import torch
+        self.net = torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[self.dev.index], find_unused_parameters=False)
+        for i in range(W):
+            self.step_resident(i)
+        ms = self.timed(self.step_resident, K)
+        loss = float(self.step_resident(0))
+        self.net = self.model
+        return {"ms_per_step": ms / K, "samples_s": self.B * self.world * K / (ms / 1e3), "loss": loss}
+
+    def close(self):
+        import torch
+        self.model = self.opt = self.net = self.host = self.resident = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32, 3 tcgen05 3xBF16 = default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--others", default=None, help="comma-separated configs measured briefly after the headline one "
+                    "(default: cfg3,cfg4,cfg5a,cfg5b when the headline is cfg2; 'none' to skip)")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = a.steps, max(a.warmup, 3)
+    wl = Workload(a.config, dev, rank, world, a.backend)
+    cfg, B, model = wl.cfg, wl.B, wl.model
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # started before the warm-up so that nvidia-smi is already sampling when the timed steps run
     for i in range(W):
-        step_resident(i)
-    ms = timed(step_resident, K)
+        wl.step_resident(i)
+    ms = wl.timed(wl.step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
-    run_e2e(W)
-    ms_e2e = timed(run_e2e, K, whole=True)
-    loss_val = run_e2e(1)
+    wl.run_e2e(W)
+    ms_e2e = wl.timed(wl.run_e2e, K, whole=True)
+    loss_val = wl.run_e2e(1)
     flags = model.input_flags()
+    replica = wl.replica_check() if world > 1 else None
+    ddp = wl.ddp_leg(min(K, 10), 3) if world > 1 else None
+    replica_after_ddp = wl.replica_check()["ranks_differing_from_rank0"] if world > 1 else None
 
     # ---- per-kernel device times (CUDA events on the launching stream inside the library), rank 0
     plan = model.last_run["plan"]
@@ -249,9 +343,22 @@ def main():
     torch.cuda.synchronize()
     plan.profile_begin()
     for i in range(prof_steps):
-        step_resident(i)
+        wl.step_resident(i)
     rows = plan.profile_report()
     launches_per_step = plan.launches(False) + plan.launches(True) + 1   # + fused AdamW
+    workspace_bytes, h2d_bytes, NB, backend_used = plan.workspace_bytes, wl.h2d_bytes, wl.nb, model.gemm_backend
+    wl.close()
+
+    # ---- the other BASELINE.json configurations, briefly: same protocol, 10 timed steps each
+    others = {}
+    names = a.others.split(",") if a.others not in (None, "none") else ([] if a.others == "none" else
+                                                                        (["cfg3", "cfg4", "cfg5a", "cfg5b"] if a.config == "cfg2" else []))
+    for name in names:
+        o = Workload(name, dev, rank, world, a.backend, nb=3)
+        oms, oms_e2e = o.measure(10, 3)
+        others[name] = o.summary(10, oms, oms_e2e)
+        others[name]["launches_per_step"] = o.model.last_run["plan"].launches(False) + o.model.last_run["plan"].launches(True) + 1
+        o.close()
 
     if rank == 0:
         pk = peaks()
@@ -279,6 +386,7 @@ def main():
             traffic = None
         roof.update({"traffic": traffic, "algorithmic_bytes_per_launch": top[3] / top[1], "kernel": top[0], "launches_per_step": top[1] // prof_steps,
                      "avg_launch_ms": top[2] / top[1], "share_of_step": top[2] / tot_ms, "peak_source": pk["src"],
+                     "accounting": "SURVEY.md 8(d): operands + ONE materialised [R, N] output per GEMM launch (fp32)",
                      "step_hbm_frac": (mb * 1e6 * B * K / (ms / 1e3)) / (pk["hbm"] * 1e9) / 1.0,
                      "step_tf32_frac": (gf * 1e9 * B * K / (ms / 1e3)) / (tf32_peak * 1e12),
                      "kernels": [{"name": r[0], "launches": r[1] // prof_steps, "ms_per_step": r[2] / prof_steps,
@@ -287,22 +395,31 @@ def main():
                                  for r in sorted(rows, key=lambda r: -r[2])[:40]]})
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = oracle_cpu_throughput(cfg, 12, 1, max_seconds=20.0)
+            cb["reference_leg_A"] = ("BASELINE.md section 5 leg (A), the unmodified reference dense FCMAE at 112/p16 on CPU, needs "
+                                     "/root/reference, which does not exist on the GPU box; timed in the build container: "
+                                     "profiles/r2_reference_leg_A.json")
         else:
             cb = None
         line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (GEMMs: 3xBF16 split products on tcgen05, fp32 accumulate)" if backend_used == 3 else "f32",
                 "data": "synthetic",
                 "config": {"workload": f"{a.config}: {cfg['model']} S2->{'all_mod' if cfg['out_modalities'] is None else '+'.join(cfg['out_modalities'])} "
                                        f"{cfg['img_size']}x{cfg['img_size']} patch{cfg['patch_size']} mask 0.6 {cfg['loss_aggr']} loss, "
                                        f"bs {B}/GPU, step = fwd + bwd" + (" + flat NCCL all-reduce" if world > 1 else "") + " + fused AdamW",
-                           "global_batch": B * world, "gemm_backend": model.gemm_backend,
-                           "l2": f"{NB} rotating resident batches ({h2d_bytes * NB / 1e6:.0f} MB) and a {plan.workspace_bytes / 1e9:.2f} GB "
+                           "global_batch": B * world, "gemm_backend": backend_used,
+                           "l2": f"{NB} rotating resident batches ({h2d_bytes * NB / 1e6:.0f} MB) and a {workspace_bytes / 1e9:.2f} GB "
                                  "activation workspace, both >> 126 MB L2; no explicit flush",
                            "parallelism": f"dp{world}"},
                 "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-                "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "loss": loss_val, "input_flags": flags}
+                "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "loss": loss_val, "input_flags": flags,
+                "other_configs": others}
+        if world > 1:
+            line["replica_check"] = replica["ranks_differing_from_rank0"] + replica_after_ddp
+            line["replica"] = dict(replica, ranks_differing_after_ddp_leg=replica_after_ddp)
+            line["ddp_leg"] = ddp
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -37,8 +37,17 @@ class DevicePrefetcher:
 
     def _stage(self, slot: int, host: Dict[str, torch.Tensor]) -> None:
         bufs = self._bufs[slot]
+        compute = torch.cuda.current_stream(self.device)
         if bufs is None or any(k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype for k, v in host.items()):
-            bufs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            # (re)allocation: the caching allocator may hand back a block whose last use is still queued on the compute
+            # stream (the buffers of the previous epoch / of a differently shaped batch), so the copy stream first waits
+            # for everything queued there; allocating under the copy stream makes it the blocks' owning stream, and
+            # record_stream tells the allocator that the compute stream reads them too
+            self.copy_stream.wait_stream(compute)
+            with torch.cuda.stream(self.copy_stream):
+                bufs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            for t in bufs.values():
+                t.record_stream(compute)
             self._bufs[slot] = bufs
         else:
             self.copy_stream.wait_event(self._free[slot])        # the step that used this slot has been queued behind us

@@ -157,7 +157,12 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
     names = list(getattr(core, "out_modalities", None) or core.args.out_modalities.keys())
     T = len(names)
     uncertainty = getattr(core, "loss_aggr", None) or core.args.loss_aggr
-    reader = LossReader(device, depth=max(lag, 1), width=2 * T + 1) if on_gpu else _LaggedHostReader(max(lag, 1))
+    dist = torch.distributed
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    # the loss vector carries one more entry when world > 1: the mean over ranks of this step's total loss
+    # (helpers.all_reduce_mean, engine_pretrain.py:103), reduced on the device by EVERY rank EVERY step
+    width = 2 * T + (2 if world > 1 else 1)
+    reader = LossReader(device, depth=max(lag, 1), width=width) if on_gpu else _LaggedHostReader(max(lag, 1))
     pending = deque()                      # (epoch_1000x, is an update step) of the iterations whose losses are in flight
     last = {"loss_dict": None, "weighted": None}
 
@@ -172,8 +177,9 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
         metric_logger.update(loss=loss_value)
         last["loss_dict"] = {m: vals[i] for i, m in enumerate(names)}
         last["weighted"] = vals[T:2 * T]
-        if log_writer is not None and was_update:                               # :104-112
-            log_writer.update(train_loss=_all_reduce_mean(loss_value, device), head="loss", step=step)
+        loss_value_reduce = vals[2 * T + 1] if world > 1 else loss_value        # :103, already reduced on the device
+        if log_writer is not None and was_update:                               # :104-112 (rank 0 alone has a writer)
+            log_writer.update(train_loss=loss_value_reduce, head="loss", step=step)
 
     def as_dict(data):
         if isinstance(data, dict):
@@ -199,8 +205,9 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
         update = (data_iter_step + 1) % update_freq == 0
         step_1000x = int((data_iter_step / n_iter + epoch) * 1000)              # epoch_1000x, :108
         pending.append((step_1000x, update))
-        consume(reader.push(_loss_vector(core, out)))
-        loss_scaler(loss / update_freq if update_freq != 1 else loss, optimizer, parameters=None, update_grad=update)
+        consume(reader.push(_with_rank_mean(_loss_vector(core, out), T, world)))
+        loss_scaler(loss / update_freq if update_freq != 1 else loss, optimizer, parameters=model.parameters(),
+                    update_grad=update)
         if update:
             optimizer.zero_grad()
         metric_logger.update(lr=optimizer.param_groups[0]["lr"])
@@ -221,14 +228,16 @@ def train_one_epoch(model: torch.nn.Module, modalities, data_loader: Iterable, o
             list(log_var_list) if log_var_list is not None else None, normalized)
 
 
-def _all_reduce_mean(x: float, device: torch.device) -> float:
-    """``helpers.all_reduce_mean`` (``helpers.py:393-401``)."""
-    dist = torch.distributed
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return x
-    t = torch.tensor(x, device=device)
-    dist.all_reduce(t)
-    return float(t.item() / dist.get_world_size())
+def _with_rank_mean(vec: torch.Tensor, T: int, world: int) -> torch.Tensor:
+    """``helpers.all_reduce_mean`` (``helpers.py:393-401``) without its host sync: the total loss is all-reduced on the
+    device and appended to the loss vector, so it reaches the host through the same lagged read.  The reference calls it
+    unconditionally on every rank every step (``engine_pretrain.py:103``); so does this -- a collective that only the rank
+    holding the log writer joined would pair with the other ranks' next gradient all-reduce."""
+    if world == 1:
+        return vec
+    red = vec[2 * T:2 * T + 1].detach().clone()
+    torch.distributed.all_reduce(red)
+    return torch.cat([vec.detach().reshape(-1), red / world])
 
 
 def fit(model, model_without_ddp, data_loader, optimizer, loss_scaler, device, args, log_writer=None, quiet: bool = True,

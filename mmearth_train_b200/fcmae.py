@@ -145,6 +145,7 @@ class FCMAE(nn.Module):
         self.allreduce_chunks = 4
         self.noise_override: Optional[torch.Tensor] = None
         self.backward_in_parts = False      # world_size > 1 always runs the backward in parts (overlapped all-reduce)
+        self.reduce_gradients = True        # False: the backward stays rank-local even under torch.distributed (checks)
         self.last_run: Optional[dict] = None
 
         # ---- module tree with the reference's names
@@ -404,7 +405,7 @@ class FCMAE(nn.Module):
         dev = run["dev"]
         world = 1
         dist = torch.distributed
-        if dist.is_available() and dist.is_initialized():
+        if dist.is_available() and dist.is_initialized() and self.reduce_gradients:
             world = dist.get_world_size()
         go = grad_total.detach().reshape(1).float().contiguous()
         if world > 1:

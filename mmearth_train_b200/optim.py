@@ -180,10 +180,112 @@ class FlatAdamW:
             g.mul_(torch.clamp(clip / (n + 1e-6), max=1.0))
         return n
 
+    # ------------------------------------------------------------------ checkpoint interchange
+    def _reference_groups(self):
+        """Parameters as the reference's optimizer enumerates them: ``timm.optim.param_groups_weight_decay`` over
+        ``model.named_parameters()`` gives ``[no_decay, decay]`` (``main_pretrain.py:312-320``), and
+        ``torch.optim.Optimizer.state_dict`` numbers the parameters through the groups in that order.  Returns two lists of
+        ``(name, offset, numel, shape)`` in the REFERENCE's registration order (``reference_param_order``)."""
+        model = self.model
+        by_name = {name: (off, numel, shape) for (name, _s, off, _d), (_o, numel, shape)
+                   in zip(model._layout, model._param_slices)}
+        decay_of = {name: d for name, _s, _o, d in model._layout}
+        public = {}                                    # native layout name -> the module's (reference) parameter name
+        for (name, _s, _o, _d), p in zip(model._layout, model._param_list):
+            public[id(p)] = name
+        names = []
+        for n, p in model.named_parameters():
+            if n == "_ddp_token":
+                continue
+            names.append((n, public[id(p)]))
+        order = reference_param_order([n for n, _ in names], model.out_modalities)
+        lookup = dict(names)
+        groups = ([], [])
+        for n in order:
+            native = lookup[n]
+            off, numel, shape = by_name[native]
+            groups[1 if decay_of[native] else 0].append((n, off, numel, tuple(shape)))
+        return groups
+
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "t": self.t, "lr": self.lr}
+        """The layout ``torch.optim.AdamW.state_dict()`` has for the reference's two parameter groups (``state`` /
+        ``param_groups``), so that a checkpoint written here resumes in the reference and the other way round
+        (``helpers.py:541-610``)."""
+        no_decay, decay = self._reference_groups()
+        t = self.t
+        state, idx, groups = {}, 0, []
+        for members, wd in ((no_decay, 0.0), (decay, self.weight_decay)):
+            ids = []
+            for _n, off, numel, shape in members:
+                state[idx] = {"step": torch.tensor(float(t)),
+                              "exp_avg": self.exp_avg[off:off + numel].view(shape).clone(),
+                              "exp_avg_sq": self.exp_avg_sq[off:off + numel].view(shape).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": wd, "amsgrad": False,
+                           "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                           "decoupled_weight_decay": True, "params": ids})
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.t, self.lr = sd["t"], sd["lr"]
+        if "exp_avg" in sd and "state" not in sd:               # round-1 private format (flat buffers)
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.t, self.lr = sd["t"], sd["lr"]
+            return
+        if "state" not in sd or "param_groups" not in sd:
+            raise ValueError("optimizer state is neither the torch.optim.AdamW layout (state / param_groups) nor the "
+                             "flat-buffer layout (exp_avg / exp_avg_sq / t / lr)")
+        no_decay, decay = self._reference_groups()
+        saved = sd["param_groups"]
+        if len(saved) != 2 or len(saved[0]["params"]) != len(no_decay) or len(saved[1]["params"]) != len(decay):
+            raise ValueError(f"optimizer state has groups of {[len(g['params']) for g in saved]} parameters; this model has "
+                             f"[{len(no_decay)}, {len(decay)}] (no-decay, decay: timm's rule, main_pretrain.py:312-320)")
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        step = None
+        for members, g in ((no_decay, saved[0]), (decay, saved[1])):
+            for (name, off, numel, shape), idx in zip(members, g["params"]):
+                st = sd["state"].get(idx)
+                if st is None:                                   # a parameter that never received a gradient
+                    continue
+                if tuple(st["exp_avg"].shape) != shape:
+                    raise ValueError(f"optimizer state {idx} has shape {tuple(st['exp_avg'].shape)}, parameter {name} "
+                                     f"has {shape}: the checkpoint belongs to another model")
+                self.exp_avg[off:off + numel].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + numel].copy_(st["exp_avg_sq"].reshape(-1))
+                step = int(float(st["step"])) if step is None else step
+        self.t = step or 0
+        self.lr = saved[0]["lr"]
+
+
+_SPARSE_BLOCK_LEAVES = ("dwconv.kernel", "dwconv.bias", "norm.ln.weight", "norm.ln.bias", "pwconv1.linear.weight",
+                        "pwconv1.linear.bias", "pwconv2.linear.weight", "pwconv2.linear.bias", "grn.gamma", "grn.beta")
+_DENSE_BLOCK_LEAVES = ("dwconv.weight", "dwconv.bias", "norm.weight", "norm.bias", "pwconv1.weight", "pwconv1.bias",
+                       "grn.gamma", "grn.beta", "pwconv2.weight", "pwconv2.bias")
+
+
+def reference_param_order(names, out_modalities):
+    """``names`` sorted the way the reference module's ``named_parameters()`` yields them: root parameters first
+    (``mask_token``), then the children in the order ``FCMAE.__init__`` / ``SparseConvNeXtV2.__init__`` register them
+    (``models/fcmae.py:93-155``, ``models/convnextv2_sparse.py:95-160``): ``loss_fn``, encoder (downsample layers, initial
+    conv, stem, stages), ``proj``, ``decoder_dict`` (the shared block appears once, under the first modality), ``pred_dict`` in
+    modality order, ``layer_norm_tmp``.  Pinned against the unmodified reference in ``tests/test_checkpoint.py``."""
+    top = {"mask_token": 0, "loss_fn": 1, "encoder": 2, "proj": 3, "decoder_dict": 4, "pred_dict": 5, "layer_norm_tmp": 6}
+    enc = {"downsample_layers": 0, "initial_conv": 1, "stem": 2, "stages": 3}
+    mods = {m: i for i, m in enumerate(out_modalities)}
+    wb = {"weight": 0, "kernel": 0, "bias": 1}
+
+    def key(n):
+        p = n.split(".")
+        if p[0] == "encoder":
+            if p[1] == "stages":
+                return (2, 3, int(p[2]), int(p[3]), _SPARSE_BLOCK_LEAVES.index(".".join(p[4:])))
+            return (2, enc[p[1]], int(p[2]), int(p[3]) if p[3].isdigit() else 0, wb[p[-1]], 0)
+        if p[0] == "decoder_dict":
+            return (4, mods[p[1]], int(p[2]), _DENSE_BLOCK_LEAVES.index(".".join(p[3:])), 0)
+        if p[0] == "pred_dict":
+            return (5, mods[p[1]], wb[p[-1]], 0, 0)
+        return (top[p[0]], wb.get(p[-1], 0), 0, 0, 0)
+
+    return sorted(names, key=key)

@@ -42,6 +42,17 @@ def max_rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+def elementwise(a, b, rtol=1e-3, atol_frac=1e-3):
+    """Element-wise criterion |a - b| <= rtol * |b| + atol with atol = atol_frac * rms(b) (the scale of the tensor: a pure
+    relative bound is meaningless for the entries that happen to be near zero).  Returns the worst ratio
+    |a - b| / (rtol * |b| + atol) -- the test passes when it is <= 1 -- and the largest absolute difference."""
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64) if not torch.is_tensor(a) else a.double().cpu()
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64) if not torch.is_tensor(b) else b.double().cpu()
+    atol = atol_frac * float(b.pow(2).mean().sqrt()) + 1e-30
+    d = (a - b).abs()
+    return float((d / (rtol * b.abs() + atol)).max()), float(d.max())
+
+
 def oracle_grads(orc, loss):
     orc.zero_grad(set_to_none=True)
     loss.backward()

@@ -151,3 +151,19 @@ def test_checkpoint_written_by_the_reference_resumes_here(tmp_path):
     args2 = Namespace(output_dir=str(tmp_path), auto_resume=True, resume="", start_epoch=0)
     ck.auto_load_model(args2, net2, net2, opt2, helpers.NativeScalerWithGradNormCount("cpu"))
     assert args2.start_epoch == 8 and torch.equal(net2.weight, net.weight)
+
+
+def test_reference_param_order_matches_the_reference_module(native_lib):
+    """``optim.reference_param_order`` against ``named_parameters()`` of the unmodified reference ``FCMAE`` (fixture
+    ``tests/golden/param_order.json``, made by importing the reference in the build container; the optimizer state of a
+    reference checkpoint is indexed by that order, helpers.py:541-547)."""
+    import json
+    from mmearth_train_b200.optim import reference_param_order
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "param_order.json")))
+    for tag, row in fx.items():
+        assert reference_param_order(sorted(row["names"]), row["out_modalities"]) == row["names"], tag
+    if os.path.isfile("/root/reference/models/fcmae.py"):      # and live, where the reference exists
+        from oracle import ref_harness as rh
+        ref, args = rh.build_reference_model(model="convnextv2_femto")
+        names = [n for n, _ in ref.named_parameters()]
+        assert reference_param_order(sorted(names), list(args.out_modalities.keys())) == names

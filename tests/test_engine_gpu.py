@@ -133,3 +133,43 @@ def test_train_one_epoch_matches_hand_written_loop(update_freq):
     for m in a.out_modalities:
         assert abs(loss_dict[m] - float(out[3][m])) <= 1e-3 * abs(float(out[3][m])) + 1e-6, m
     assert len(log_vars) == 12 and normalized.shape == (12,)
+
+
+def test_optimizer_state_interchanges_with_torch_adamw():
+    """a checkpoint written by the reference's ``save_model`` holds ``torch.optim.AdamW.state_dict()`` over
+    timm's two parameter groups (main_pretrain.py:312-320).  FlatAdamW reads and writes exactly that layout: a torch AdamW
+    run is resumed by FlatAdamW and the other way round, with identical parameters afterwards."""
+    from mmearth_train_b200.optim import FlatAdamW, reference_param_order
+    a, batch, noise = _model()
+    b, _, _ = _model()
+    dev = {k: v.cuda() for k, v in batch.items()}
+    a.noise_override = b.noise_override = noise
+    named = {n: p for n, p in b.named_parameters() if n != "_ddp_token"}
+    order = reference_param_order(list(named), b.out_modalities)
+    no_decay = [named[n] for n in order if named[n].ndim <= 1 or n.endswith(".bias")]
+    decay = [named[n] for n in order if not (named[n].ndim <= 1 or n.endswith(".bias"))]
+    ot = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}], lr=3e-4,
+                           betas=(0.9, 0.95))
+    oa = FlatAdamW(a, lr=3e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    for _ in range(2):                                  # torch AdamW on b, FlatAdamW on a: same trajectory
+        b(dev)[0].backward(); ot.step(); ot.zero_grad(set_to_none=False)
+        a(dev)[0].backward(); oa.step(); oa.zero_grad()
+    sd_t, sd_f = ot.state_dict(), oa.state_dict()
+    assert [len(g["params"]) for g in sd_t["param_groups"]] == [len(g["params"]) for g in sd_f["param_groups"]]
+    for i in sd_t["state"]:
+        assert sd_f["state"][i]["exp_avg"].shape == sd_t["state"][i]["exp_avg"].shape, i
+        assert gu.rel_err(sd_f["state"][i]["exp_avg"], sd_t["state"][i]["exp_avg"]) < 2e-2, i
+        assert float(sd_f["state"][i]["step"]) == float(sd_t["state"][i]["step"]) == 2.0
+    # resume the torch run with FlatAdamW and the flat run with torch AdamW
+    c, _, _ = _model()
+    c.noise_override = noise
+    c.load_state_dict(b.state_dict())
+    oc = FlatAdamW(c, lr=1.0, betas=(0.9, 0.95), weight_decay=0.05)
+    oc.load_state_dict(sd_t)
+    assert oc.t == 2 and oc.lr == 3e-4
+    ot.load_state_dict(sd_f)                            # b continues from a's moments (the same up to atomics order)
+    b(dev)[0].backward(); ot.step()
+    c(dev)[0].backward(); oc.step()
+    assert gu.rel_err(c.flat_params, b.flat_params) < 1e-5
+    with pytest.raises(ValueError):
+        oc.load_state_dict({"state": {}, "param_groups": [{"params": [0]}, {"params": [1]}]})

@@ -14,13 +14,13 @@ TOL = {0: 1e-4, 1: 1e-3, 2: 1e-3, 3: 1e-3}
 GRAD_TOL = {0: 5e-4, 1: 3e-3, 2: 3e-3, 3: 3e-3}
 
 
-def build_native(cfg, orc, backend):
+def build_native(cfg, orc, backend, mask_ratio=0.6, decoder_depth=1, norm_pix_loss=True):
     import mmearth_train_b200 as mp
     args = fo.make_args(cfg["out_modalities"], cfg["loss_aggr"])
     lf = mp.UncertaintyWeightingStrategy(len(args.out_modalities)) if cfg["loss_aggr"] == "uncertainty" else None
-    m = getattr(mp, cfg["model"])(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True,
-                                  patch_size=cfg["patch_size"], img_size=cfg["img_size"], args=args, loss_fn=lf,
-                                  gemm_backend=backend)
+    m = getattr(mp, cfg["model"])(mask_ratio=mask_ratio, decoder_depth=decoder_depth, decoder_embed_dim=512,
+                                  norm_pix_loss=norm_pix_loss, patch_size=cfg["patch_size"], img_size=cfg["img_size"],
+                                  args=args, loss_fn=lf, gemm_backend=backend)
     m.load_state_dict(orc.state_dict())
     return m.cuda()
 
@@ -355,3 +355,130 @@ def test_unsupported_widths_are_refused_at_construction(name):
     with pytest.raises(NativeError, match="dims"):
         getattr(mp, name)(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True, patch_size=8,
                           img_size=56, args=fo.make_args(None, "uncertainty"), loss_fn=mp.UncertaintyWeightingStrategy(12))
+
+
+WORST = {}     # observed worst cases of the element-wise criterion, printed at the end of the module (pytest -s / -rP)
+
+
+def _compare_with_oracle(model, orc, batch, noise, mask_ratio, tag, check_grads=True):
+    """CUDA step vs the oracle on the same inputs: mask bit-exact, loss and per-modality losses within 1e-3, every
+    prediction and the encoder features ELEMENT-WISE (|a-b| <= 1e-3 |b| + 1e-3 rms(b)), every parameter gradient
+    norm-wise within 3e-3 and the flat gradient norm within 1e-3."""
+    model.noise_override = noise
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    loss, pred, mask, loss_dict, log_vars, weighted = model(dev_batch, mask_ratio=mask_ratio)
+    taps = {}
+    o_loss, o_pred, o_mask, o_ld, _, _ = orc(batch, mask_ratio=mask_ratio, noise=noise, taps=taps)
+    assert torch.equal(mask.cpu(), o_mask), "mask indices must be bit-exact"
+    assert abs(float(loss) - float(o_loss)) <= 1e-3 * abs(float(o_loss)), (float(loss), float(o_loss))
+    worst = {"loss": abs(float(loss) - float(o_loss)) / abs(float(o_loss))}
+    for m in o_pred:
+        assert abs(float(loss_dict[m]) - float(o_ld[m])) <= 1e-3 * abs(float(o_ld[m])) + 1e-6, m
+        r, d = gu.elementwise(pred[m], o_pred[m].detach())
+        worst[f"pred.{m}"] = r
+        assert r <= 1.0, (m, r, d)
+    with torch.no_grad():
+        feats = orc.encoder(torch.nan_to_num(batch["sentinel2"], nan=0.0, posinf=0.0, neginf=0.0), o_mask)
+    r, d = gu.elementwise(model.encoder_features(), feats)
+    worst["encoder_features"] = r
+    assert r <= 1.0, ("encoder_features", r, d)
+    if check_grads:
+        loss.backward()
+        ograds = gu.oracle_grads(orc, o_loss)
+        named = dict(model.named_parameters())
+        total_sq = diff_sq = got_sq = 0.0
+        for name, g in ograds.items():
+            if g is None:
+                continue
+            e, gn = gu.rel_err(named[name].grad, g), float(g.double().norm())
+            total_sq += gn ** 2
+            diff_sq += (e * gn) ** 2
+            got_sq += float(named[name].grad.double().norm()) ** 2
+            assert e < 3e-3 or float((named[name].grad.cpu() - g).abs().max()) < 3e-5 * max(1.0, gn), (name, e)
+        worst["grad.flat"] = (diff_sq / total_sq) ** 0.5
+        assert worst["grad.flat"] < 3e-3
+        assert abs(got_sq ** 0.5 - total_sq ** 0.5) <= 1e-3 * total_sq ** 0.5          # flat gradient norm
+    WORST[tag] = worst
+    return worst
+
+
+@pytest.mark.parametrize("bs", [64, 256])
+def test_numerical_parity_at_benchmark_batch(bs):
+    """BASELINE.json configs[1] (atto, S2 -> 12 modalities, 56/p8, uncertainty) at bs 64 and at the
+    benchmarked bs 256 -- NUMBERS, not shapes.  The batch-global GRN statistic runs over 78k / 311k rows here (fp32
+    atomics), which is exactly what changes with the batch size."""
+    cfg = dict(model="convnextv2_atto", img_size=56, patch_size=8, out_modalities=None, loss_aggr="uncertainty")
+    orc = fo.build_oracle()
+    fo.init_like_reference(orc, seed=3)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    model = build_native(cfg, orc, 3)
+    batch = fo.synthetic_batch(bs, 56, seed=900 + bs, nan_frac=0.02)
+    noise = torch.randn(bs, 49, generator=torch.Generator().manual_seed(17))
+    w = _compare_with_oracle(model, orc, batch, noise, 0.6, f"cfg2_bs{bs}")
+    print("worst cases", bs, {k: round(v, 4) for k, v in w.items()})
+
+
+VARIANTS = {
+    "mask075": dict(mask_ratio=0.75),
+    "mask050": dict(mask_ratio=0.5),
+    "no_norm_pix": dict(norm_pix_loss=False),
+    "decoder_depth2": dict(decoder_depth=2),
+    "p16_mask050": dict(mask_ratio=0.5, patch_size=16, img_size=112),
+    "tiny_mask075": dict(mask_ratio=0.75, model="convnextv2_tiny"),
+}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_option_variants_match_oracle(variant):
+    """the constructor options the reference exposes (models/fcmae.py:27-60: mask_ratio,
+    norm_pix_loss, decoder_depth, patch_size / img_size), CUDA vs oracle (the oracle is pinned to the live reference for the
+    same variants in tests/test_oracle_golden.py)."""
+    kw = dict(VARIANTS[variant])
+    name = kw.pop("model", "convnextv2_atto")
+    ps, S = kw.pop("patch_size", 8), kw.pop("img_size", 56)
+    mr, dd, npl = kw.get("mask_ratio", 0.6), kw.get("decoder_depth", 1), kw.get("norm_pix_loss", True)
+    cfg = dict(model=name, img_size=S, patch_size=ps, out_modalities=None, loss_aggr="uncertainty")
+    orc = fo.build_oracle(model=name, img_size=S, patch_size=ps, mask_ratio=mr, decoder_depth=dd, norm_pix_loss=npl)
+    fo.init_like_reference(orc, seed=3)
+    model = build_native(cfg, orc, 3, mask_ratio=mr, decoder_depth=dd, norm_pix_loss=npl)
+    B = 2
+    batch = fo.synthetic_batch(B, S, seed=31, nan_frac=0.05)
+    noise = torch.randn(B, 49, generator=torch.Generator().manual_seed(5))
+    w = _compare_with_oracle(model, orc, batch, noise, mr, variant)
+    V = int(49 * (1 - mr))
+    assert model.last_run["plan"].visible_patches == V
+    print("worst cases", variant, {k: round(v, 4) for k, v in w.items()})
+
+
+def test_random_crop_same_window_for_all_pixel_modalities():
+    """models/fcmae.py:419-434: inputs larger than img_size are cropped with ONE random window per sample shared by the six
+    pixel-wise modalities; image-level modalities pass through."""
+    import mmearth_train_b200 as mp
+    S, H, B = 56, 64, 6
+    model = mp.convnextv2_atto(mask_ratio=0.6, decoder_depth=1, decoder_embed_dim=512, norm_pix_loss=True, patch_size=8,
+                               img_size=S, args=fo.make_args(None, "uncertainty"), loss_fn=mp.UncertaintyWeightingStrategy(12)).cuda()
+    big = {k: v.cuda() for k, v in fo.synthetic_batch(B, H, seed=77).items()}
+    torch.manual_seed(3)
+    out = model._random_crop(big)
+    pix = [m for m, t in big.items() if t.dim() == 4]
+    assert sorted(pix) == sorted(["sentinel2", "sentinel1", "aster", "canopy_height_eth", "dynamic_world", "esa_worldcover"])
+    windows = []
+    for n in range(B):
+        found = [(y, x) for y in range(H - S + 1) for x in range(H - S + 1)
+                 if torch.equal(out["sentinel2"][n], big["sentinel2"][n, :, y:y + S, x:x + S])]
+        assert len(found) == 1, (n, found)
+        y, x = found[0]
+        windows.append((y, x))
+        for m in pix:
+            assert out[m].shape[-2:] == (S, S) and out[m].dtype == big[m].dtype and out[m].is_contiguous()
+            assert torch.equal(out[m][n], big[m][n, :, y:y + S, x:x + S]), (m, n)
+    assert len(set(windows)) > 1                      # per-sample windows, not one for the batch
+    for m, t in big.items():
+        if t.dim() != 4:
+            assert out[m] is t
+    # forward() takes the crop path by itself when the input is larger than img_size
+    torch.manual_seed(3)
+    loss = model(big, mask_ratio=0.6)[0]
+    assert torch.isfinite(loss)
+    with pytest.raises(ValueError):
+        model._random_crop({k: (v[:, :, :40, :40] if v.dim() == 4 else v) for k, v in big.items()})
