@@ -164,6 +164,9 @@ class Workload:
         self.resident = [{k: v.to(dev) for k, v in b.items()} for b in self.host]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host[0].values())
         self.net = self.model            # what is called: the module itself, or its DistributedDataParallel wrap (ddp leg)
+        from mmearth_train_b200.data import DevicePrefetcher, LossReader
+        self.prefetcher = DevicePrefetcher(None, dev)   # persistent device buffers / pinned slots, as in a training run
+        self.reader = LossReader(dev)                   # every step's loss is read on the host, two steps late
 
     def make_host_batch(self, rank, i):
         from mmearth_train_b200 import synthetic as fo
@@ -180,10 +183,10 @@ class Workload:
     def run_e2e(self, n):
         """n steps through the public API: pinned host batches in (copy stream, overlapped with the previous step),
         model(batch) -> loss.backward() -> optimizer.step(), and the loss read back to the host every step."""
-        from mmearth_train_b200.data import DevicePrefetcher, LossReader
         last = None
-        reader = LossReader(self.dev)                                 # every step's loss is read on the host, two steps late
-        for b in DevicePrefetcher((self.host[i % self.nb] for i in range(n)), self.dev):   # what a DataLoader(pin_memory=True) yields
+        reader = self.reader
+        self.prefetcher.src = (self.host[i % self.nb] for i in range(n))   # what a DataLoader(pin_memory=True) yields
+        for b in self.prefetcher:
             loss = self.net(b, mask_ratio=0.6)[0]
             loss.backward()
             self.opt.step()
@@ -285,7 +288,7 @@ class Workload:
 
     def close(self):
         import torch
-        self.model = self.opt = self.net = self.host = self.resident = None
+        self.model = self.opt = self.net = self.host = self.resident = self.prefetcher = self.reader = None
         import gc
         gc.collect()
         torch.cuda.empty_cache()

@@ -168,6 +168,16 @@ typedef struct mpmae_gemm_desc {
   float *out, *out2, *colsum, *colsum2, *scratch;
   int64_t M;
   int32_t N, K, group_rows;
+  /* optional (zero = off).  a_gelu: the A operand is consumed as gelu(a[m,k]) * a_scale[k] (a_scale null = 1), applied by
+   * the operand-splitter warps (backends 1, 3) or on load (backend 0) -- pw2 of a sparse block reading the saved
+   * pre-activation.  acc_scale [N] (mode 3): out = (a.b^T * acc_scale[n] + kg[n] * gelu(aux2)) * gelu'(aux2).
+   * grn_*: mode 0 with a_gelu, backends 1 / 3: the A scale is the batch-global GRN scale, derived in the kernel from
+   * grn_gsq[k] = sum_rows h^2: nx = sqrt(gsq) / (mean sqrt(gsq) + grn_eps), scale = 1 + grn_gamma * nx (both written out,
+   * with the denominator, for the backward pass); a_scale is then ignored. */
+  int32_t a_gelu;
+  const float *a_scale, *acc_scale, *grn_gsq, *grn_gamma;
+  float *grn_nx, *grn_scale, *grn_denom;
+  float grn_eps;
 } mpmae_gemm_desc;
 int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void *cuda_stream);
 
@@ -175,6 +185,10 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
  * backend 0 = fp32 SIMT, 1 or 3 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 */
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
                      void *cuda_stream);
+/* the same with y consumed as gelu(y) when y_gelu != 0 (dW2f = dy^T . gelu(a) without a materialised h): applied by the
+ * splitter warps on backends 1 / 3, on load on backend 0; backend 2 has no splitter and refuses it */
+int mpmae_gemm_wgrad_act(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
+                         int32_t y_gelu, void *cuda_stream);
 
 /* Fused AdamW over flat buffers (torch.optim.AdamW semantics; the reference builds its optimizer at
  * main_pretrain.py:312-320).  decay_mask: one byte per element (null = decay everything);

@@ -39,7 +39,9 @@ class IO(C.Structure):
 class GemmDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("a", "b", "bias", "resid", "aux", "aux2", "kg", "out", "out2", "colsum", "colsum2",
                                           "scratch")] + [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32),
-                                                         ("group_rows", C.c_int32)]
+                                                         ("group_rows", C.c_int32), ("a_gelu", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("a_scale", "acc_scale", "grn_gsq", "grn_gamma", "grn_nx", "grn_scale", "grn_denom")] + \
+               [("grn_eps", C.c_float)]
 
 
 class NativeError(RuntimeError):
@@ -83,6 +85,7 @@ def _load():
         "mpmae_gemm_rows": (C.c_int, [I32, P, P, P, P, I64, I32, I32, P, P]),
         "mpmae_gemm_epi": (C.c_int, [I32, I32, C.POINTER(GemmDesc), P]),
         "mpmae_gemm_wgrad": (C.c_int, [I32, P, P, P, I64, I32, I32, P]),
+        "mpmae_gemm_wgrad_act": (C.c_int, [I32, P, P, P, I64, I32, I32, I32, P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
         "mpmae_adamw_step_dev": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, P, P]),
     }
@@ -97,7 +100,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
+           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_gemm_wgrad_act", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
 
 
 def check(rc: int, what: str = "") -> None:

@@ -11,9 +11,9 @@ namespace mpmae {
 
 enum EpiMode : int {
   EPI_STORE = 0,    // out = acc + bias (+ resid)
-  EPI_GELU_SQ = 1,  // a = acc + bias -> out ; h = gelu(a) -> out2 ; colsum[g, n] += h^2
+  EPI_GELU_SQ = 1,  // a = acc + bias -> out ; h = gelu(a) -> out2 (when given) ; colsum[g, n] += h^2
   EPI_DG = 2,       // out = acc ; colsum[g, n] += acc * aux[m, n] ; colsum2[n] += acc
-  EPI_DH_GELU = 3   // out = (acc + kg[g, n] * aux[m, n]) * gelu'(aux2[m, n]) ; colsum2[n] += out
+  EPI_DH_GELU = 3   // out = (acc * acc_scale[n] + kg[g, n] * gelu(aux2[m, n])) * gelu'(aux2[m, n]) ; colsum2[n] += out
 };
 
 constexpr int kMaxGroupsPerTile = 12;
@@ -37,6 +37,18 @@ struct GemmArgs {
   int64_t M;
   int N, K;
   int group_rows;      // rows per statistics group (>= M means one group)
+  // The A operand consumed as gelu(A[m, k]) * a_scale[k] (a_scale null = 1): pw2 of a sparse block reads the saved
+  // pre-activation `a` and applies GELU and the GRN scale on the way into the tensor core, so `h` is never materialised
+  int a_gelu;
+  const float *a_scale;    // [K] or null
+  const float *acc_scale;  // [N] or null (EPI_DH_GELU): per-column factor of the accumulator (the GRN scale of dg = dy . W2)
+  // Batch-global GRN statistic (models/sparse_norm_layers.py:24-33) computed by the a_gelu kernel itself (tcgen05 path):
+  // when grn_gsq = sum_rows h^2 [K] is given, every CTA derives nx = sqrt(gsq) / (mean sqrt(gsq) + eps) and the A-operand
+  // scale s = 1 + gamma * nx in its prologue (it overlaps the pipeline fill) and CTA 0 writes nx / scale / denom for the
+  // backward pass; a_scale is then ignored.
+  const float *grn_gsq, *grn_gamma;   // [K]
+  float *grn_nx, *grn_scale, *grn_denom;
+  float grn_eps;
 };
 
 // Column accumulation helper shared by the SIMT and tcgen05 epilogues: a thread owns `nrows`
@@ -76,6 +88,10 @@ __global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) { pdl_pr
       const int r = t >> 1, kq = (t & 1) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m0 + r < p.M) v = *reinterpret_cast<const float4 *>(p.A + (m0 + r) * p.K + k0 + kq);
+      if (p.a_gelu) {
+        const float4 sc = p.a_scale ? *reinterpret_cast<const float4 *>(p.a_scale + k0 + kq) : make_float4(1.f, 1.f, 1.f, 1.f);
+        v.x = gelu_f(v.x) * sc.x; v.y = gelu_f(v.y) * sc.y; v.z = gelu_f(v.z) * sc.z; v.w = gelu_f(v.w) * sc.w;
+      }
       As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
     }
     for (int t = tid; t < BN * 2; t += NTHR) {
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) { pdl_pr
         if (p.bias) v += p.bias[n];
         p.out[o] = v;
         const float h = gelu_f(v);
-        p.out2[o] = h;
+        if (p.out2) p.out2[o] = h;
         part[j] += h * h;
       } else if (MODE == EPI_DG) {
         p.out[o] = v;
@@ -153,7 +169,9 @@ __global__ void __launch_bounds__(16 * NT) gemm_rows_kernel(GemmArgs p) { pdl_pr
         part2[j] += v;
       } else {  // EPI_DH_GELU
         const float kgv = p.kg ? p.kg[(g_first + g) * p.N + n] : 0.f;
-        const float da = (v + kgv * p.aux[o]) * gelu_grad_f(p.aux2[o]);
+        const float hv = p.aux ? p.aux[o] : gelu_f(p.aux2[o]);
+        if (p.acc_scale) v *= p.acc_scale[n];
+        const float da = (v + kgv * hv) * gelu_grad_f(p.aux2[o]);
         p.out[o] = da;
         part2[j] += da;
       }
@@ -214,6 +232,7 @@ struct WgradArgs {
   int N, K;
   int rows_per_split;
   int exact;        // tensor-core path: 3xTF32 (the result feeds back into the data path)
+  int y_gelu;       // Y is consumed as gelu(Y): dW2f = dy^T . gelu(a) without a materialised h
 };
 
 __device__ __forceinline__ float4 load4_guard(const float *base, int64_t row, int ld, int col, int ncols, bool vec_ok) {
@@ -256,6 +275,7 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(WgradArgs p) { pdl_prol
     if (r0 + lr < r_end) {
       xv = load4_guard(p.X, r0 + lr, p.N, n0 + lc, p.N, xvec);
       yv = load4_guard(p.Y, r0 + lr, p.K, k0 + lc, p.K, yvec);
+      if (p.y_gelu) { yv.x = gelu_f(yv.x); yv.y = gelu_f(yv.y); yv.z = gelu_f(yv.z); yv.w = gelu_f(yv.w); }
     }
     *reinterpret_cast<float4 *>(&Xs[lr][lc]) = xv;
     *reinterpret_cast<float4 *>(&Ys[lr][lc]) = yv;

@@ -246,14 +246,17 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
 // 18-20 warps = 5 per scheduler keeps 96 registers per thread.
 // WIDE (K >= 256, e.g. the decoder block): measured best is 8 + 8 for the forward GELU epilogue and 12 + 4 for the backward
 // ones (same as their narrow-K setting).
-__host__ __device__ constexpr int epi_warps(int mode, bool wide) {
-  return mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 16) : 12);
+// AGELU (EPI_STORE only): the splitter warps also apply GELU and the GRN scale to every A element (pw2 of a sparse block
+// reading the saved pre-activation); that is ~3x their work per element while the epilogue covers only N = C columns, so
+// the roles become 4 epilogue + 16 splitter warps.
+__host__ __device__ constexpr int epi_warps(int mode, bool wide, bool agelu = false) {
+  return agelu ? 4 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 16) : 12));
 }
-__host__ __device__ constexpr int split_warps(int mode, bool split, bool wide) {
-  return !split ? 0 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 2) : 4));
+__host__ __device__ constexpr int split_warps(int mode, bool split, bool wide, bool agelu = false) {
+  return !split ? 0 : agelu ? 16 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 2) : 4));
 }
-__host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide) {
-  return 64 + 32 * epi_warps(mode, wide) + 32 * split_warps(mode, split, wide);
+__host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide, bool agelu = false) {
+  return 64 + 32 * epi_warps(mode, wide, agelu) + 32 * split_warps(mode, split, wide, agelu);
 }
 __host__ __device__ constexpr int out_arrays(int mode) { return mode == EPI_GELU_SQ ? 2 : 1; }
 constexpr uint32_t kStageOutBytes = 32 * 16 * 4;   // one warp's [32 rows x 16 columns] output chunk
@@ -296,14 +299,14 @@ __device__ __forceinline__ bool get_work(const TcParams &p, int it, WorkItem &w)
 // splitter warps convert them IN PLACE into a bf16 high tile and a bf16 remainder tile ([128 x 64] each, 128-byte
 // swizzle); the weight arrives pre-split as bf16 (hi, lo); D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with kind::f16 MMAs -- the
 // same stage bytes as 3xTF32 carry twice the K and the tensor pipe runs at twice the rate; |error| <= 2^-16 per product.
-template <int MODE, bool SPLIT, bool WIDE, bool BF16>
-__global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE), 1)
+template <int MODE, bool SPLIT, bool WIDE, bool BF16, bool AGELU = false>
+__global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE, AGELU), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
                const __grid_constant__ CUtensorMap map_out2, const __grid_constant__ CUtensorMap map_bt,
                const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) { pdl_prologue();
-  constexpr int kEpiWarps = epi_warps(MODE, WIDE), kEpiThreads = 32 * kEpiWarps;
-  constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE), kSplitThreads = 32 * kSplitWarps;
+  constexpr int kEpiWarps = epi_warps(MODE, WIDE, AGELU), kEpiThreads = 32 * kEpiWarps;
+  constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE, AGELU), kSplitThreads = 32 * kSplitWarps;
   constexpr int kThreadsNoSplit = 64 + kEpiThreads;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
@@ -329,6 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float *vec_kg_all = vec_bias_all + p.num_n * bn;                   // [num_n * bn] kg of group 0 (EPI_DH_GELU)
   float *statacc1 = vec_kg_all + p.num_n * bn;                       // [num_n * bn] kernel-long column sums (one group)
   float *statacc2 = statacc1 + p.num_n * bn;                         // [num_n * bn]
+  float *vec_as_all = statacc2 + p.num_n * bn;                       // [num_n * bn] accumulator scale (EPI_DH_GELU)
+  float *a_scale_s = vec_kg_all + p.num_n * bn;                      // AGELU (EPI_STORE): [32 | K] reduction scratch, A scale
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs &g = p.g;
@@ -348,7 +353,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = threadIdx.x - 64; i < (kTcGroups + 1) * bn; i += kEpiThreads) colacc[i] = 0.f;
     for (int i = threadIdx.x - 64; i < p.num_n * bn; i += kEpiThreads) {
       vec_bias_all[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
-      if (MODE == EPI_DH_GELU) vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+      if (MODE == EPI_DH_GELU) {
+        vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+        vec_as_all[i] = (g.acc_scale && i < g.N) ? __ldg(g.acc_scale + i) : 1.f;
+      }
       if (MODE != EPI_STORE) { statacc1[i] = 0.f; statacc2[i] = 0.f; }
     }
   }
@@ -462,7 +470,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t m = (int64_t)m_blk * BM + q * 32 + lane;
       const bool row_ok = m < g.M;
       const int n_base = w.n0;
-      const float *vec_bias = vec_bias_all + n_base, *vec_kg = vec_kg_all + n_base;
+      const float *vec_bias = vec_bias_all + n_base, *vec_kg = vec_kg_all + n_base, *vec_as = vec_as_all + n_base;
+      const bool has_out2 = MODE == EPI_GELU_SQ && g.out2 != nullptr;
       const int64_t g_first = ((int64_t)m_blk * BM) / g.group_rows;
       const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
       const int gw_lo = (int)(mw0 / g.group_rows - g_first);
@@ -600,12 +609,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               s2[j] = acc.x; s2[j + 1] = acc.y; s2[j + 2] = acc.z; s2[j + 3] = acc.w;
             } else {  // EPI_DH_GELU
               const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j);
+              const float4 asv = *reinterpret_cast<const float4 *>(vec_as + c0 + j);
               float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
               gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
-              r.x = fmaf(kgv.x, hx, acc.x) * dx_;
-              r.y = fmaf(kgv.y, hy, acc.y) * dy_;
-              r.z = fmaf(kgv.z, hz, acc.z) * dz_;
-              r.w = fmaf(kgv.w, hw, acc.w) * dw_;
+              r.x = fmaf(kgv.x, hx, acc.x * asv.x) * dx_;
+              r.y = fmaf(kgv.y, hy, acc.y * asv.y) * dy_;
+              r.z = fmaf(kgv.z, hz, acc.z * asv.z) * dz_;
+              r.w = fmaf(kgv.w, hw, acc.w * asv.w) * dw_;
               s2[j] = r.x; s2[j + 1] = r.y; s2[j + 2] = r.z; s2[j + 3] = r.w;
             }
             o[q4] = r; o2[q4] = r2;
@@ -616,13 +626,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               sts_v4(srow + (((uint32_t)q4 ^ sx) << 4), o[q4]);
-              if (MODE == EPI_GELU_SQ) sts_v4(srow + kStageOutBytes + (((uint32_t)q4 ^ sx) << 4), o2[q4]);
+              if (has_out2) sts_v4(srow + kStageOutBytes + (((uint32_t)q4 ^ sx) << 4), o2[q4]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
               tma_store_2d(&map_out, sbuf, n_base + c0, row0);
-              if (MODE == EPI_GELU_SQ) tma_store_2d(&map_out2, sbuf + kStageOutBytes, n_base + c0, row0);
+              if (has_out2) tma_store_2d(&map_out2, sbuf + kStageOutBytes, n_base + c0, row0);
               bulk_commit();
             }
           }
@@ -701,12 +711,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else {  // EPI_DH_GELU: h = a * Phi(a) is recomputed from a (it shares the erf with gelu')
               if (row_ok) {
                 const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j4);
+                const float4 asv = *reinterpret_cast<const float4 *>(vec_as + c0 + j4);
                 float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
                 gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
-                o.x = (acc.x + kgv.x * hx) * dx_;
-                o.y = (acc.y + kgv.y * hy) * dy_;
-                o.z = (acc.z + kgv.z * hz) * dz_;
-                o.w = (acc.w + kgv.w * hw) * dw_;
+                o.x = (acc.x * asv.x + kgv.x * hx) * dx_;
+                o.y = (acc.y * asv.y + kgv.y * hy) * dy_;
+                o.z = (acc.z * asv.z + kgv.z * hz) * dz_;
+                o.w = (acc.w * asv.w + kgv.w * hw) * dw_;
                 st2 = o;
               }
             }
@@ -725,7 +736,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int h8 = 0; h8 < 2; ++h8) {
               if (n0 + 8 * h8 < g.N) {
                 st_global_v8(g.out + m * g.N + n0 + 8 * h8, ov[2 * h8], ov[2 * h8 + 1]);
-                if (MODE == EPI_GELU_SQ) st_global_v8(g.out2 + m * g.N + n0 + 8 * h8, ov2[2 * h8], ov2[2 * h8 + 1]);
+                if (has_out2) st_global_v8(g.out2 + m * g.N + n0 + 8 * h8, ov2[2 * h8], ov2[2 * h8 + 1]);
               }
             }
           } else {
@@ -733,7 +744,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               if (n0 + 4 * j < g.N) {
                 *reinterpret_cast<float4 *>(g.out + m * g.N + n0 + 4 * j) = ov[j];
-                if (MODE == EPI_GELU_SQ) *reinterpret_cast<float4 *>(g.out2 + m * g.N + n0 + 4 * j) = ov2[j];
+                if (has_out2) *reinterpret_cast<float4 *>(g.out2 + m * g.N + n0 + 4 * j) = ov2[j];
               }
             }
           }
@@ -801,6 +812,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int stid = threadIdx.x - kThreadsNoSplit;   // 0..kSplitThreads-1
     int stage = 0;
     uint32_t phase = 0;
+    const float *a_sc = a_scale_s + 32;
+    if (AGELU) {
+      // per-column scale of the A operand in shared memory: the GRN scale derived here from the finished statistic
+      // (every CTA redundantly: K <= a few thousand floats out of L2 while the first TMA loads are in flight), or given
+      constexpr int kST = kSplitThreads > 0 ? kSplitThreads : 32;
+      float *sc_w = a_scale_s + 32;
+      if (g.grn_gsq) {
+        float part = 0.f;
+        for (int k = stid; k < g.K; k += kST) part += sqrtf(__ldg(g.grn_gsq + k));
+        part = warp_sum(part);
+        if (lane == 0) a_scale_s[stid >> 5] = part;
+        asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kST / 32; ++i) tot += a_scale_s[i];
+        const float den = tot / (float)g.K + g.grn_eps;
+        for (int k = stid; k < g.K; k += kST) {
+          const float nx = sqrtf(__ldg(g.grn_gsq + k)) / den;
+          const float sc = fmaf(__ldg(g.grn_gamma + k), nx, 1.f);
+          sc_w[k] = sc;
+          if (blockIdx.x == 0) { g.grn_nx[k] = nx; g.grn_scale[k] = sc; }
+        }
+        if (blockIdx.x == 0 && stid == 0) g.grn_denom[0] = den;
+      } else {
+        for (int k = stid; k < g.K; k += kST) sc_w[k] = g.a_scale ? __ldg(g.a_scale + k) : 1.f;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
+    }
     WorkItem w;
     for (int it = 0; get_work(p, it, w); ++it) {
       for (int kb = 0; kb < p.num_k; ++kb) {
@@ -812,24 +851,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // box 1.  A pass handles a band of rows: read both boxes' chunks of the band into registers, barrier among the
           // splitter warps, write the band of both bf16 tiles (rows are independent, so bands do not interfere).
           constexpr int kST = kSplitThreads > 0 ? kSplitThreads : 32;
-          constexpr int kPasses = 2048 / (8 * kST);              // 2 x 128 x 8 float4 in all, 8 per thread per pass
+          constexpr int kPer = (2048 / kST >= 8) ? 8 : 2048 / kST;   // 2 x 128 x 8 float4 in all, kPer per thread per pass
+          constexpr int kPasses = 2048 / (kPer * kST);
           constexpr int kBandRows = 128 / kPasses;
           uint8_t *base = smem + (size_t)stage * stage_bytes;
 #pragma unroll 1
           for (int ps = 0; ps < ((TC_DBG(p) & 64) ? 0 : kPasses); ++ps) {
-            float4 x[8];
-            int rr[8], cc[8], hh[8];
+            float4 x[kPer];
+            int rr[kPer], cc[kPer], hh[kPer];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kPer; ++i) {
               const int idx = i * kST + stid;                    // 0 .. kBandRows*16-1: (h, row in band, physical chunk)
               const int h = idx / (kBandRows * 8), rem = idx - h * (kBandRows * 8);
               const int r = ps * kBandRows + (rem >> 3), pc = rem & 7;
               hh[i] = h; rr[i] = r; cc[i] = pc ^ (r & 7);        // logical 16-byte chunk: k = 32 h + 4 c .. + 3
               x[i] = *reinterpret_cast<const float4 *>(base + h * a_bytes + r * 128 + pc * 16);
+              if (AGELU) {   // A = saved pre-activation: h = gelu(a), times the GRN scale of its column
+                const int k = kb * 64 + h * 32 + cc[i] * 4;
+                const float4 sc = k < g.K ? *reinterpret_cast<const float4 *>(a_sc + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+                x[i].x = gelu_f(x[i].x) * sc.x; x[i].y = gelu_f(x[i].y) * sc.y;
+                x[i].z = gelu_f(x[i].z) * sc.z; x[i].w = gelu_f(x[i].w) * sc.w;
+              }
             }
             asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kPer; ++i) {
               uint32_t h0, l0, h1, l1;
               split_bf16x2(x[i].x, x[i].y, h0, l0);
               split_bf16x2(x[i].z, x[i].w, h1, l1);
@@ -843,7 +889,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (!(TC_DBG(p) & 64))
 #pragma unroll
         for (int i = 0; i < (int)(a_bytes / 16) / (kSplitThreads > 0 ? kSplitThreads : 1); ++i) {
-          const float4 x = A[i * kSplitThreads + stid];
+          float4 x = A[i * kSplitThreads + stid];
+          if (AGELU) {
+            const int idx = i * kSplitThreads + stid, r = idx >> 3, k = kb * BK + (((idx & 7) ^ (r & 7)) << 2);
+            const float4 sc = k < g.K ? *reinterpret_cast<const float4 *>(a_sc + k) : make_float4(1.f, 1.f, 1.f, 1.f);
+            x.x = gelu_f(x.x) * sc.x; x.y = gelu_f(x.y) * sc.y; x.z = gelu_f(x.z) * sc.z; x.w = gelu_f(x.w) * sc.w;
+          }
           float4 hi, lo;
           hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
           hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); lo.y = x.y - hi.y;
@@ -972,6 +1023,7 @@ struct TnParams {
   int num_m, num_n, splits, chunks_per_split;   // chunk = 32 rows
   int stages;
   int vec4;          // dW 16-byte aligned and Kw % 4 == 0: vector atomics when the M side is the dW row (swap == 0)
+  int gelu_m, gelu_n;   // SPLIT only: the M- / N-side operand is consumed as gelu(operand) (dW2f = dy^T . gelu(a))
   uint32_t tmem_cols;
 };
 
@@ -983,7 +1035,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
-constexpr int kTnThreads = 192, kTnSplitThreads = 256;   // 8 splitter warps: both operand tiles are split every chunk
+constexpr int kTnThreads = 192, kTnSplitThreads = 512;   // 16 splitter warps: both operand tiles are split (one also through GELU) every chunk
 
 // SPLIT = 3xTF32: both operand tiles are split in shared memory (hi in place, remainder in a second buffer) by four
 // splitter warps; D += Mhi.Nhi + Mlo.Nhi + Mhi.Nlo.  Used where the product feeds back into the data path (the GRN
@@ -1123,9 +1175,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
     const int stid = threadIdx.x - kTnThreads;   // 0..kTnSplitThreads-1
     int stage = 0;
     uint32_t phase = 0;
-    auto split_region = [&](float4 *src, float4 *lo, int n4) {
+    auto split_region = [&](float4 *src, float4 *lo, int n4, bool act) {
       for (int i = stid; i < n4; i += kTnSplitThreads) {
-        const float4 x = src[i];
+        float4 x = src[i];
+        if (act) { x.x = gelu_f(x.x); x.y = gelu_f(x.y); x.z = gelu_f(x.z); x.w = gelu_f(x.w); }
         float4 hi, l;
         hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - hi.x;
         hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - hi.y;
@@ -1142,8 +1195,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
       for (int ch = c_begin; ch < c_end; ++ch) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t *sm = smem + (size_t)stage * stage_bytes;
-        split_region(reinterpret_cast<float4 *>(sm), reinterpret_cast<float4 *>(sm + m_bytes), m_bytes / 16);
-        split_region(reinterpret_cast<float4 *>(sm + m_span), reinterpret_cast<float4 *>(sm + m_span + n_bytes), n_bytes / 16);
+        split_region(reinterpret_cast<float4 *>(sm), reinterpret_cast<float4 *>(sm + m_bytes), m_bytes / 16, p.gelu_m != 0);
+        split_region(reinterpret_cast<float4 *>(sm + m_span), reinterpret_cast<float4 *>(sm + m_span + n_bytes), n_bytes / 16,
+                     p.gelu_n != 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[stage]);
@@ -1188,7 +1242,7 @@ inline bool tc_gemm_supported(int mode, const GemmArgs &a) {
   return tc::encode_fn() != nullptr;
 }
 
-template <int MODE, bool SPLIT, bool WIDE, bool BF16 = false>
+template <int MODE, bool SPLIT, bool WIDE, bool BF16 = false, bool AGELU = false>
 inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) {
   using namespace tc;
   TcParams p{};
@@ -1202,8 +1256,8 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     const size_t a_stage = (size_t)(SPLIT ? 2 : 1) * BM * BK * 4, b_stage = (size_t)(SPLIT ? 2 : 1) * bn * BK * 4;
     const size_t ring = b_resident(bn) ? (size_t)stages * a_stage + b_stage : (size_t)stages * (a_stage + b_stage);
     const int num_n = cdiv(a.N, bn);
-    return 1024 + ring + (size_t)epi_warps(MODE, WIDE) * out_arrays(MODE) * kStageOutBytes + 256 +
-           (size_t)(5 * bn + (MODE == EPI_STORE ? 2 : 4) * num_n * bn) * 4;
+    return 1024 + ring + (size_t)epi_warps(MODE, WIDE, AGELU) * out_arrays(MODE) * kStageOutBytes + 256 +
+           (size_t)(5 * bn + (MODE == EPI_STORE ? 2 : 5) * num_n * bn + (AGELU ? a.K + 32 : 0)) * 4;
   };
   // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget with a 2-stage ring,
   // else a ragged tail; then as many ring stages as still fit
@@ -1243,7 +1297,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   }
   p.tma_out = map_cache().get(&mo, a.out, a.M, a.N, -1) ? 1 : 0;
   mo2 = mo;
-  if (MODE == EPI_GELU_SQ && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
+  if (MODE == EPI_GELU_SQ && a.out2 && p.tma_out && !map_cache().get(&mo2, a.out2, a.M, a.N, -1)) p.tma_out = 0;
   if (!p.tma_out) mo = mo2 = ma;
   if (a.ln_rstd && (MODE != EPI_STORE || !p.tma_out || p.num_n != 1 || !tc_ln_bwd_ok(a))) return cudaErrorInvalidConfiguration;
   int grid = p.num_m * p.num_n;
@@ -1280,16 +1334,24 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16, AGELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  pdl(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16>, grid, tc_threads(MODE, SPLIT, WIDE), smem, st)(ma, mb, mbl, mo, mo2, mbt, mbtl, p);
+  pdl(gemm_tc_kernel<MODE, SPLIT, WIDE, BF16, AGELU>, grid, tc_threads(MODE, SPLIT, WIDE, AGELU), smem, st)(ma, mb, mbl, mo, mo2, mbt, mbtl, p);
   return cudaGetLastError();
 }
 
 template <int MODE>
 inline cudaError_t launch_gemm_rows_tc(const GemmArgs &a, int backend, cudaStream_t st) {
+  // GELU on the A operand is applied by the operand-splitter warps: split backends only
+  if (a.a_gelu) {
+    if constexpr (MODE == EPI_STORE) {
+      if (backend == 3 && a.b16 && a.Bw_lo) return launch_gemm_rows_tc_impl<EPI_STORE, true, true, true, true>(a, st);
+      if (backend == 1 && a.Bw_lo) return launch_gemm_rows_tc_impl<EPI_STORE, true, true, false, true>(a, st);
+    }
+    return cudaErrorInvalidConfiguration;
+  }
   const bool wide = MODE == EPI_STORE || a.K >= 256;   // WIDE only changes the roles of the statistics / GELU epilogues
   if (backend == 3 && a.b16 && a.Bw_lo)
     return wide ? launch_gemm_rows_tc_impl<MODE, true, true, true>(a, st)
@@ -1320,6 +1382,9 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   p.swap = cost(a.K, a.N) < cost(a.N, a.K) ? 1 : 0;
   p.Msz = p.swap ? a.K : a.N;
   p.Nsz = p.swap ? a.N : a.K;
+  if (a.y_gelu && !SPLIT) return cudaErrorInvalidConfiguration;   // the activation is applied by the splitter warps
+  p.gelu_m = (a.y_gelu && p.swap) ? 1 : 0;     // Y sits on the M side when swapped
+  p.gelu_n = (a.y_gelu && !p.swap) ? 1 : 0;
   int bn;
   if (p.Nsz <= 256) bn = ((p.Nsz + 31) / 32) * 32;
   else {

@@ -224,16 +224,15 @@ __global__ void grn_apply_kernel(const float *__restrict__ h, const float *__res
 // Backward of the GRN statistic.  ds[g, d] = sum_rows dg * h (from the dg epilogue).
 //   dgamma[d] += sum_g Nx * ds ; dNx = gamma * ds ; dGx = dNx/den - (sum_j dNx_j Gx_j) / (D den^2)
 //   kg[g, d] = dGx / Gx   (so that dh += kg * h)
-__global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *__restrict__ nx,
-                                     const float *__restrict__ denom, const float *__restrict__ gamma,
-                                     float *__restrict__ dgamma, float *__restrict__ kg, int D) { pdl_prologue();
+__device__ __forceinline__ void grn_bwd_scale_body(const float *ds, const float *__restrict__ nx,
+                                                   const float *__restrict__ denom, const float *__restrict__ gamma,
+                                                   float *__restrict__ dgamma, float *__restrict__ kg, int D, int g) {
   __shared__ float red[32];
-  const int g = blockIdx.x;
   const float den = denom[g];
   float s = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const int64_t i = (int64_t)g * D + d;
-    s += gamma[d] * ds[i] * (nx[i] * den);  // dNx_j * Gx_j
+    s += gamma[d] * __ldcg(ds + i) * (nx[i] * den);  // dNx_j * Gx_j
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -247,11 +246,31 @@ __global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *
   const float cross = red[0] / ((float)D * den * den);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const int64_t i = (int64_t)g * D + d;
-    const float dnx = gamma[d] * ds[i];
+    const float dsv = __ldcg(ds + i);
+    const float dnx = gamma[d] * dsv;
     const float gx = nx[i] * den;
     const float dgx = dnx / den - cross;
     kg[i] = gx > 0.f ? dgx / gx : 0.f;
-    atomicAdd(&dgamma[d], nx[i] * ds[i]);
+    atomicAdd(&dgamma[d], nx[i] * dsv);
+  }
+}
+__global__ void grn_bwd_scale_kernel(const float *__restrict__ ds, const float *__restrict__ nx,
+                                     const float *__restrict__ denom, const float *__restrict__ gamma,
+                                     float *__restrict__ dgamma, float *__restrict__ kg, int D) { pdl_prologue();
+  grn_bwd_scale_body(ds, nx, denom, gamma, dgamma, kg, D, blockIdx.x);
+}
+
+// h' = gelu(a) * scale[d]: materialises the pw2 operand for the GEMM backends without operand-splitter warps (fp32 SIMT,
+// single-pass TF32); the split backends apply it on the way into the tensor core instead (GemmArgs::a_gelu)
+__global__ void gelu_scale_rows_kernel(const float *__restrict__ a, const float *__restrict__ scale, float *__restrict__ out,
+                                       int64_t R, int D) { pdl_prologue();
+  const int64_t n4 = R * (D >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % (D >> 2)) * 4;
+    const float4 av = *reinterpret_cast<const float4 *>(a + i * 4);
+    const float4 sv = scale ? *reinterpret_cast<const float4 *>(scale + d) : make_float4(1.f, 1.f, 1.f, 1.f);
+    *reinterpret_cast<float4 *>(out + i * 4) = make_float4(gelu_f(av.x) * sv.x, gelu_f(av.y) * sv.y, gelu_f(av.z) * sv.z,
+                                                            gelu_f(av.w) * sv.w);
   }
 }
 
@@ -471,6 +490,25 @@ __device__ __forceinline__ void unfold_column(const UnfoldArgs &p, int k) {
   }
 }
 __global__ void unfold_kernel(UnfoldArgs p) { pdl_prologue(); unfold_column(p, blockIdx.x); }
+// The un-fold of a sparse block's pw2 (grid = K = 4C columns) followed, in the LAST CTA to finish, by the backward of the
+// batch-global GRN statistic, which needs the complete dscale vector (= A_c = sum_r dg * h).
+struct GrnBwdArgs {
+  const float *nx, *denom, *gamma;
+  float *dgamma, *kg;
+  unsigned int *counter;   // zero before the launch; left at zero
+};
+__global__ void unfold_grn_kernel(UnfoldArgs p, GrnBwdArgs q) { pdl_prologue();
+  __shared__ unsigned int last;
+  unfold_column(p, blockIdx.x);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(q.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  grn_bwd_scale_body(p.dscale, q.nx, q.denom, q.gamma, q.dgamma, q.kg, p.K, 0);
+  if (threadIdx.x == 0) *q.counter = 0u;
+}
 // Several un-folds in one launch (the deferred ones of a backward part): job table + prefix sum of the K's in device memory
 __global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const int *__restrict__ k_start, int njobs) { pdl_prologue();
   __shared__ UnfoldArgs job;

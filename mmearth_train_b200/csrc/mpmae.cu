@@ -10,7 +10,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,7 +57,7 @@ struct Tap { int64_t off_bytes, rows, cols; };
 // (zeroed at the start of backward) the gradient of the folded weight / bias.
 struct WSlot { int64_t wf, wf_lo, wft, wft_lo, bf, dwf, dbf; int N, K; };
 // per-block saved activations / statistics (float offsets into the workspace)
-struct BlockW { int64_t vhat, rstd, a, h, g, y, gsq, nx, scale, denom, dsv; WSlot s1, s2; };
+struct BlockW { int64_t vhat, rstd, a, h, g, y, gsq, nx, scale, denom, dsv, cnt_b; WSlot s1, s2; };
 
 }  // namespace
 
@@ -106,7 +108,32 @@ struct mpmae_plan {
 
 namespace {
 
+// The fold / un-fold job tables live INSIDE the caller's workspace (the library owns no device memory) and are uploaded
+// only when their cache key changes.  A workspace may be shared by several plans (one per batch size); their layouts
+// differ, so a call of another plan overwrites this plan's tables with activations.  The registry remembers which plan
+// last ran on a workspace: a plan that finds another owner forgets its keys and uploads again.
+std::mutex g_ws_mu;
+std::map<const void *, const mpmae_plan *> g_ws_owner;
+void claim_workspace(mpmae_plan *pl, const void *ws) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  const mpmae_plan *&owner = g_ws_owner[ws];
+  if (owner != pl) {
+    owner = pl;
+    pl->fold_key_params = pl->fold_key_ws = nullptr;
+    pl->fold_njobs = 0;
+    for (int i = 0; i < 3; ++i) {
+      pl->unfold_njobs[i] = 0;
+      for (int j = 0; j < 3; ++j) pl->unfold_key[i][j] = nullptr;
+    }
+  }
+}
+void release_workspaces(const mpmae_plan *pl) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  for (auto it = g_ws_owner.begin(); it != g_ws_owner.end();) it = (it->second == pl) ? g_ws_owner.erase(it) : std::next(it);
+}
+
 int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+constexpr int kMaxFoldJobs = 192;   // base: 36 blocks x (pw1, pw2) + downsamples + decoder + heads = 79
 
 int64_t add_param(mpmae_plan *pl, const std::string &name, std::initializer_list<int64_t> shape) {
   ParamRef r;
@@ -288,7 +315,7 @@ void build_workspace(mpmae_plan *pl) {
       w.vhat = ws_alloc(pl, N("vhat"), R, C);
       w.rstd = ws_alloc(pl, N("rstd"), R, 1);
       w.a = ws_alloc(pl, N("a"), R, 4 * C);
-      w.h = ws_alloc(pl, N("h"), R, 4 * C);
+      w.h = -1;   // never materialised: pw2 / dW2f apply GELU (and the GRN scale) to `a` on the way into the tensor core
       w.g = -1;
       w.y = ws_alloc(pl, N("y"), R, C);
       w.nx = ws_alloc(pl, N("nx"), 1, 4 * C);
@@ -352,6 +379,7 @@ void build_workspace(mpmae_plan *pl) {
       alloc_slot_grads(pl, pl->bw[i][j].s1);
       alloc_slot_grads(pl, pl->bw[i][j].s2);
       pl->bw[i][j].dsv = ws_alloc(pl, nullptr, 1, 4 * dm[i]);
+      pl->bw[i][j].cnt_b = ws_alloc(pl, nullptr, 1, 1);   // ticket counter of the GRN backward in the pw2 un-fold
     }
   for (int k = 0; k < c.dec_depth; ++k) {
     alloc_slot_grads(pl, pl->dw[k].s1);
@@ -369,7 +397,7 @@ void build_workspace(mpmae_plan *pl) {
   pl->o_dbf = ws_alloc(pl, nullptr, 1, pl->max_n);
   pl->o_dsv = ws_alloc(pl, nullptr, B, pl->max_n);
   pl->o_kg = ws_alloc(pl, nullptr, B, pl->max_n);
-  pl->o_foldjobs = ws_alloc(pl, nullptr, 1, (int64_t)(64 * sizeof(FoldArgs) + 65 * sizeof(int) + 3) / 4);
+  pl->o_foldjobs = ws_alloc(pl, nullptr, 1, (int64_t)(kMaxFoldJobs * sizeof(FoldArgs) + (kMaxFoldJobs + 1) * sizeof(int) + 3) / 4);
   for (int i = 0; i < 3; ++i) pl->o_unfoldjobs[i] = ws_alloc(pl, nullptr, 1, (int64_t)(64 * sizeof(UnfoldArgs) + 65 * sizeof(int) + 3) / 4);
   pl->o_g0 = ws_alloc(pl, nullptr, 1, pl->max_rc);
   pl->o_g1 = ws_alloc(pl, nullptr, 1, pl->max_rc);
@@ -458,6 +486,8 @@ cudaError_t dw_wgrad_launch(const DwWgradArgs &d, const int *vis, cudaStream_t s
 }
 
 void fold(Ctx &c, FoldArgs a, const char *what);
+int ew_grid(int64_t n4);
+bool splitter_backend(Ctx &c);
 
 template <int MODE>
 void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
@@ -478,8 +508,11 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
     }
   }
   {
-    const double mn = (double)a.M * a.N, io_mn = (MODE == EPI_STORE ? 1 + (a.resid ? 1 : 0) : MODE == EPI_GELU_SQ ? 2
-                                                  : MODE == EPI_DG ? 2 : 3);
+    // SURVEY.md 8(d) accounting: the operands and the tensors this launch materialises / re-reads, each once:
+    //   EPI_STORE   A + W + out (+ residual)          EPI_GELU_SQ  A + W + one [M, N] output (a; h only if it is stored)
+    //   EPI_DG      A + W + out + h                   EPI_DH_GELU  A + W + out (da) + a
+    const double mn = (double)a.M * a.N;
+    const double io_mn = MODE == EPI_STORE ? 1 + (a.resid ? 1 : 0) : MODE == EPI_GELU_SQ ? (a.out2 ? 2 : 1) : 2;
     c.acct(4.0 * ((double)a.M * a.K + (double)a.N * a.K + mn * io_mn), 2.0 * mn * a.K);
   }
   if (use_tc) {
@@ -488,11 +521,26 @@ void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
     c.check(launch_gemm_rows_simt<MODE>(a, c.st), what);
   }
 }
-void wgrad(Ctx &c, const WgradArgs &a, const char *what) {
+// does gemm<MODE>() take the tcgen05 path for these arguments (the callers that rely on splitter / tail features ask first)
+template <int MODE>
+bool gemm_uses_tc(Ctx &c, const GemmArgs &a) { return c.pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a); }
+bool splitter_backend(Ctx &c) { return c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3; }
+void wgrad(Ctx &c, const WgradArgs &a_in, const char *what) {
   if (!c.ok()) return;
+  WgradArgs a = a_in;
+  const bool use_tc = c.pl->cfg.gemm_backend != 0 && tc_wgrad_supported(a);
+  const bool exact = a.exact != 0 && splitter_backend(c);
+  if (a.y_gelu && use_tc && !exact) {
+    // tensor-core weight gradient without splitter warps: materialise gelu(Y) in the (still unused) da scratch
+    float *h = c.w(c.pl->o_gda);
+    c.acct(4.0 * 2.0 * (double)a.R * a.K, 0);
+    pdl(gelu_scale_rows_kernel, ew_grid(a.R * (a.K / 4)), 256, 0, c.st)(a.Y, (const float *)nullptr, h, a.R, a.K);
+    c.post("gelu_rows");
+    a.Y = h; a.y_gelu = 0;
+  }
   c.acct(4.0 * ((double)a.R * a.N + (double)a.R * a.K + (double)a.N * a.K), 2.0 * (double)a.R * a.N * a.K);
-  if (c.pl->cfg.gemm_backend != 0 && tc_wgrad_supported(a)) {
-    c.check(launch_gemm_wgrad_tc(a, a.exact != 0 && (c.pl->cfg.gemm_backend == 1 || c.pl->cfg.gemm_backend == 3), c.st), what);
+  if (use_tc) {
+    c.check(launch_gemm_wgrad_tc(a, exact, c.st), what);
     if (a.db && c.ok()) {   // bias gradient = column sums of X (the tensor-core kernel produces dW only)
       c.acct(4.0 * (double)a.R * a.N, 0);
       launch_colsum(a.X, a.rs, a.db, a.R, a.N, c.st);
@@ -576,6 +624,13 @@ FoldArgs pw1_fold_args(Ctx &c, const BlockP &bp, int C) {
   f.bias = c.p(bp.b1); f.SL = C;
   return f;
 }
+// sparse pw2: the raw weight (split for the tensor core) and b2f = b2 + W2 . beta; the GRN scale is NOT folded into the
+// weight any more (it would make the fold depend on this step's statistic): it multiplies the A operand instead
+FoldArgs sparse_pw2_fold_args(Ctx &c, const BlockP &bp, int D4) {
+  FoldArgs f{};
+  f.W = c.p(bp.w2); f.s_n = D4; f.s_k = 1; f.SL = D4; f.shift_k = c.p(bp.beta); f.bias = c.p(bp.b2);
+  return f;
+}
 FoldArgs dense_pw2_fold_args(Ctx &c, const BlockP &bp, int D4) {   // per-sample GRN cannot be folded: plain (split) copy
   FoldArgs f{};
   f.W = c.p(bp.w2); f.s_n = D4; f.s_k = 1; f.SL = D4;
@@ -606,7 +661,10 @@ void batched_param_folds(Ctx &c, bool encoder_only) {
   c.collect = &jobs;
   for (int i = 0; i < 4; ++i) {
     if (i > 0) fold_slot(c, ds_fold_args(c, i - 1, cf.dims[i - 1], cf.dims[i]), pl->ds_slot[i - 1], "fold_ds");
-    for (int j = 0; j < cf.depths[i]; ++j) fold_slot(c, pw1_fold_args(c, pl->blk[i][j], cf.dims[i]), pl->bw[i][j].s1, "fold_pw1");
+    for (int j = 0; j < cf.depths[i]; ++j) {
+      fold_slot(c, pw1_fold_args(c, pl->blk[i][j], cf.dims[i]), pl->bw[i][j].s1, "fold_pw1");
+      fold_slot(c, sparse_pw2_fold_args(c, pl->blk[i][j], 4 * cf.dims[i]), pl->bw[i][j].s2, "split_pw2");
+    }
   }
   if (!encoder_only) {
     fold_slot(c, proj_fold_args(c), pl->proj_slot, "split_proj");
@@ -618,11 +676,11 @@ void batched_param_folds(Ctx &c, bool encoder_only) {
   }
   c.collect = nullptr;
   const int n = (int)jobs.size();
-  if (n == 0 || n > 64 || !c.ok()) return;
+  if (n == 0 || n > kMaxFoldJobs || !c.ok()) return;
   std::vector<int> start(n + 1, 0);
   for (int j = 0; j < n; ++j) start[j + 1] = start[j] + cdiv(jobs[j].K, 32) * cdiv(jobs[j].N, 32);
   FoldArgs *d_jobs = reinterpret_cast<FoldArgs *>(c.w(pl->o_foldjobs));
-  int *d_start = reinterpret_cast<int *>(d_jobs + 64);
+  int *d_start = reinterpret_cast<int *>(d_jobs + kMaxFoldJobs);
   if (pl->fold_key_params != (const void *)c.P || pl->fold_key_ws != (const void *)c.ws || pl->fold_njobs != n) {
     c.check(cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(FoldArgs), cudaMemcpyHostToDevice, c.st), "memcpy", false);
     c.check(cudaMemcpyAsync(d_start, start.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st), "memcpy", false);
@@ -656,19 +714,17 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
   const int groups = dense ? pl->geo.B : 1;
   GemmArgs g1{};
   g1.A = c.w(bw.vhat); use_slot(c, g1, bw.s1, false); g1.bias = c.w(bw.s1.bf);
-  g1.out = c.w(bw.a); g1.out2 = c.w(bw.h); g1.colsum = c.w(bw.gsq);
+  g1.out = c.w(bw.a); g1.out2 = dense ? c.w(bw.h) : nullptr; g1.colsum = c.w(bw.gsq);
   g1.M = R; g1.N = D4; g1.K = C; g1.group_rows = group_rows;
   gemm<EPI_GELU_SQ>(c, g1, "pw1");
 
-  if (dense && c.ok()) {   // per-sample statistic; the batch-global one of the sparse blocks is fused into fold_pw2
+  if (dense && c.ok()) {   // per-sample statistic; the batch-global one of the sparse blocks is derived inside pw2
     pdl(grn_scale_kernel, groups, 256, 0, c.st)(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom),
                                                D4, 1e-4f);
     c.post("grn_scale");
   }
   GemmArgs g2{};
   g2.out = c.w(bw.y); g2.resid = x; g2.M = R; g2.N = C; g2.K = D4; g2.group_rows = group_rows;
-  FoldArgs f2{};
-  f2.W = c.p(bp.w2); f2.s_n = D4; f2.s_k = 1; f2.SL = D4;
   if (dense) {
     if (c.ok()) {
       c.acct(4.0 * 2.0 * R * D4, 0);
@@ -679,12 +735,28 @@ void block_forward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, i
     fold_slot(c, dense_pw2_fold_args(c, bp, D4), bw.s2, "split_pw2");
     g2.A = c.w(bw.g); g2.bias = c.p(bp.b2);
   } else {
-    // GRN is affine in h per channel: fold s = 1 + gamma*Nx into W2's columns and beta into the bias
-    f2.shift_k = c.p(bp.beta); f2.bias = c.p(bp.b2);
-    f2.gsq = c.w(bw.gsq); f2.gamma = c.p(bp.gamma); f2.nx_out = c.w(bw.nx); f2.scale_out = c.w(bw.scale);
-    f2.denom_out = c.w(bw.denom); f2.grn_eps = 1e-6f;
-    fold_slot(c, f2, bw.s2, "fold_pw2");
-    g2.A = c.w(bw.h); g2.bias = c.w(bw.s2.bf);
+    // GRN is affine in h per channel: y = x + (gelu(a) * s) . W2^T + (b2 + W2 . beta) with s = 1 + gamma * Nx.  The weight
+    // split and the bias are parameter-only (batched fold); gelu and s are applied to the A operand by the splitter warps.
+    fold_slot(c, sparse_pw2_fold_args(c, bp, D4), bw.s2, "split_pw2");
+    g2.bias = c.w(bw.s2.bf);
+    g2.A = c.w(bw.a); g2.a_gelu = 1;
+    if (gemm_uses_tc<EPI_STORE>(c, g2) && splitter_backend(c)) {
+      // the kernel derives the batch-global GRN scale from the finished statistic in its prologue (no launch, no pass)
+      g2.grn_gsq = c.w(bw.gsq); g2.grn_gamma = c.p(bp.gamma); g2.grn_nx = c.w(bw.nx); g2.grn_scale = c.w(bw.scale);
+      g2.grn_denom = c.w(bw.denom); g2.grn_eps = 1e-6f;
+    } else {
+      // no operand-splitter warps on this path: GRN scale by its own kernel, then gelu(a) * s materialised in the backward
+      // scratch (unused in forward)
+      float *hs = c.w(pl->o_gda);
+      if (c.ok()) {
+        pdl(grn_scale_kernel, 1, 256, 0, c.st)(c.w(bw.gsq), c.p(bp.gamma), c.w(bw.nx), c.w(bw.scale), c.w(bw.denom), D4, 1e-6f);
+        c.post("grn_scale");
+        c.acct(4.0 * 2.0 * R * D4, 0);
+        pdl(gelu_scale_rows_kernel, ew_grid(R * (D4 / 4)), 256, 0, c.st)(c.w(bw.a), c.w(bw.scale), hs, R, D4);
+        c.post("gelu_scale");
+      }
+      g2.A = hs; g2.a_gelu = 0;
+    }
   }
   use_slot(c, g2, bw.s2, false);
   gemm<EPI_STORE>(c, g2, "pw2");
@@ -724,24 +796,26 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
       c.post("colsum");
     }
   } else {
-    // folded pw2:  dW2f = dy^T . h, db2f = sum dy  ->  dW2, ds (= A), dbeta, db2 by the chain rule of the fold
+    // pw2 with h' = gelu(a) * s:  dW2f = dy^T . gelu(a), db2f = sum dy  ->  dW2 = dW2f * s + db2f (x) beta, ds (= A) =
+    // sum_n dW2f . W2, dbeta = W2^T db2f, db2 = db2f: the chain rule of (scale, shift) in front of a linear map
     float *dwf2 = c.w(bw.s2.dwf), *dbf2 = c.w(bw.s2.dbf);
     WgradArgs wg{};
-    wg.X = dy; wg.Y = c.w(bw.h); wg.dW = dwf2; wg.db = dy_colsum_done ? nullptr : dbf2; wg.R = R; wg.N = C; wg.K = D4;
+    wg.X = dy; wg.Y = c.w(bw.a); wg.y_gelu = 1; wg.dW = dwf2; wg.db = dy_colsum_done ? nullptr : dbf2; wg.R = R; wg.N = C; wg.K = D4;
     wg.exact = 1;   // ds (GRN statistic gradient) is derived from dW2f and feeds every row's gradient
     wgrad(c, wg, "dW2f");
     UnfoldArgs u{};
     u.W = c.p(bp.w2); u.s_n = D4; u.s_k = 1; u.scale_k = c.w(bw.scale); u.shift_k = c.p(bp.beta);
     u.dWf = dwf2; u.dbf = dbf2; u.dW = c.g(bp.w2); u.dscale = dsv; u.dshift = c.g(bp.beta); u.dbias = c.g(bp.b2);
     u.N = C; u.K = D4; u.SL = D4;
-    unfold(c, u, "unfold_pw2");
-    if (c.ok()) {
-      pdl(grn_bwd_scale_kernel, 1, 256, 0, c.st)(dsv, c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, D4);
-      c.post("grn_bwd_scale");
+    if (c.ok()) {   // un-fold + (last CTA) backward of the GRN statistic: dgamma, kg
+      GrnBwdArgs q{c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, reinterpret_cast<unsigned int *>(c.w(bw.cnt_b))};
+      pdl(unfold_grn_kernel, u.K, 256, 0, c.st)(u, q);
+      c.post("unfold_pw2");
     }
-    // da = (dy . W2f + kg*h) * gelu'(a) ; db1f = sum da rides on the epilogue
+    // da = ((dy . W2) * s + kg * gelu(a)) * gelu'(a) ; db1f = sum da rides on the epilogue
     GemmArgs gd{};
-    gd.A = dy; use_slot(c, gd, bw.s2, true); gd.out = da; gd.aux = c.w(bw.h); gd.aux2 = c.w(bw.a); gd.kg = kg;
+    gd.A = dy; use_slot(c, gd, bw.s2, true); gd.out = da; gd.aux = nullptr; gd.aux2 = c.w(bw.a); gd.kg = kg;
+    gd.acc_scale = c.w(bw.scale);
     gd.colsum2 = dbf1;
     gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
     gemm<EPI_DH_GELU>(c, gd, "da");
@@ -927,7 +1001,10 @@ int mpmae_plan_create(const mpmae_cfg *cfg, mpmae_plan **out) {
   return MPMAE_OK;
 }
 
-void mpmae_plan_destroy(mpmae_plan *plan) { delete plan; }
+void mpmae_plan_destroy(mpmae_plan *plan) {
+  if (plan) release_workspaces(plan);
+  delete plan;
+}
 
 int64_t mpmae_param_total(const mpmae_plan *plan) { return plan ? plan->n_params : 0; }
 int32_t mpmae_param_count(const mpmae_plan *plan) { return plan ? (int32_t)plan->params.size() : 0; }
@@ -985,6 +1062,7 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
   int rc = check_io(pl, io, false, stages);
   if (rc) return rc;
   const bool encoder_only = !(stages & ST_DEC);
+  claim_workspace(pl, io->workspace);
   Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
   c.mark("start");
   const mpmae_cfg &cf = pl->cfg;
@@ -1137,6 +1215,7 @@ int mpmae_forward_stages(mpmae_plan *pl, const mpmae_io *io, int32_t stages, voi
 static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, int parts) {
   int rc = check_io(pl, io, true);
   if (rc) return rc;
+  claim_workspace(pl, io->workspace);
   Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
   c.mark("start");
   const mpmae_cfg &cf = pl->cfg;
@@ -1387,6 +1466,12 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
   g.A = d->a; g.Bw = d->b; g.bias = d->bias; g.resid = d->resid; g.out = d->out; g.out2 = d->out2; g.aux = d->aux;
   g.aux2 = d->aux2; g.kg = d->kg; g.colsum = d->colsum; g.colsum2 = d->colsum2; g.M = d->M; g.N = d->N; g.K = d->K;
   g.group_rows = d->group_rows > 0 ? d->group_rows : 0x7fffffff;
+  g.a_gelu = d->a_gelu; g.a_scale = d->a_scale; g.acc_scale = d->acc_scale;
+  g.grn_gsq = d->grn_gsq; g.grn_gamma = d->grn_gamma; g.grn_nx = d->grn_nx; g.grn_scale = d->grn_scale; g.grn_denom = d->grn_denom;
+  g.grn_eps = d->grn_eps;
+  if (g.grn_gsq && (!(backend == 1 || backend == 3) || mode != 0 || !g.a_gelu || !g.grn_gamma || !g.grn_nx || !g.grn_scale || !g.grn_denom))
+    return fail(MPMAE_ERR_UNSUPPORTED, "the in-kernel GRN scale needs mode 0 with a_gelu on backend 1 or 3 and all grn_* pointers");
+  if (g.a_gelu && backend == 2) return fail(MPMAE_ERR_UNSUPPORTED, "a_gelu needs operand-splitter warps (backends 1, 3) or backend 0");
   const bool tc_ok = backend != 0 && tc_gemm_supported(mode, g);
   if (backend != 0 && !tc_ok) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");
   if (backend == 1 || backend == 3) {
@@ -1411,10 +1496,16 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
 
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
                      void *cuda_stream) {
+  return mpmae_gemm_wgrad_act(backend, x, y, dw, R, N, K, 0, cuda_stream);
+}
+
+int mpmae_gemm_wgrad_act(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
+                         int32_t y_gelu, void *cuda_stream) {
   if (!x || !y || !dw || R <= 0 || N <= 0 || K <= 0) return fail(MPMAE_ERR_INVALID, "wgrad args");
+  if (y_gelu && backend == 2) return fail(MPMAE_ERR_UNSUPPORTED, "y_gelu needs the splitter warps of backends 1 / 3 (or backend 0)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   WgradArgs w{};
-  w.X = x; w.Y = y; w.dW = dw; w.R = R; w.N = N; w.K = K;
+  w.X = x; w.Y = y; w.dW = dw; w.R = R; w.N = N; w.K = K; w.y_gelu = y_gelu ? 1 : 0;
   cudaError_t e;
   if (backend != 0) {
     if (!tc_wgrad_supported(w)) return fail(MPMAE_ERR_UNSUPPORTED, "shape not taken by the tcgen05 path");

@@ -133,3 +133,112 @@ def test_gemm_epilogues(native_lib, shape, backend, tol):
     ref3 = (a.double() @ b.double().t() + kg.double() * _gelu_ref(x2)) * _gelu_grad_ref(x2)
     assert float((out3.double() - ref3).abs().max() / ref3.abs().max()) < tol
     assert float((cs2.double() - ref3.sum(0)).norm() / ref3.sum(0).norm()) < 20 * tol   # sums of sign-mixed terms
+
+
+@pytest.mark.parametrize("backend,tol", [(0, 2e-5), (1, 1e-4), (3, 2e-4)])
+@pytest.mark.parametrize("shape", [(38912, 40, 160, 0), (9728, 80, 320, 0), (2500, 160, 640, 0), (4864, 320, 1280, 0), (700, 96, 384, 0)])
+def test_gemm_gelu_on_operand_and_acc_scale(native_lib, shape, backend, tol):
+    """Round 2: `h` is never materialised.  (1) mode 0 with a_gelu: out = (gelu(a) * a_scale) . b^T + bias + resid, GELU and the
+    GRN scale applied to the A operand on its way into the tensor core (pw2 of a sparse block, K = 4C incl. a K tail);
+    (2) mode 3 with acc_scale: out = (a . b^T * acc_scale + kg * gelu(aux2)) * gelu'(aux2), aux (h) absent."""
+    nat = native_lib
+    M, N, K, _ = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    b = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    a_scale = (1.0 + 0.3 * torch.randn(K, generator=g)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    scratch = torch.empty(2 * N * K, device="cuda")
+
+    def call(mode, **kw):
+        d = nat.GemmDesc()
+        for k, v in kw.items():
+            setattr(d, k, v.data_ptr() if torch.is_tensor(v) else v)
+        d.M, d.N, d.K, d.group_rows = M, N, K, 0
+        nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(d), C.c_void_p(st)), "gemm_epi")
+        torch.cuda.synchronize()
+
+    out = torch.full((M, N), float("nan"), device="cuda")
+    call(0, a=a, b=b, bias=bias, resid=resid, out=out, scratch=scratch, a_gelu=1, a_scale=a_scale)
+    ref = (_gelu_ref(a.double()) * a_scale.double()) @ b.double().t() + bias.double() + resid.double()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
+    out = torch.full((M, N), float("nan"), device="cuda")
+    call(0, a=a, b=b, out=out, scratch=scratch, a_gelu=1)                      # no scale, no bias
+    ref = _gelu_ref(a.double()) @ b.double().t()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
+    # mode 3 (the roles of N and K swap: da [M, K'] = dy [M, N'] . W): reuse the shapes transposed
+    M3, N3, K3 = M, K, N
+    dy = torch.randn(M3, K3, generator=g).cuda()
+    w = (torch.randn(N3, K3, generator=g) * K3 ** -0.5).cuda()
+    aux2 = torch.randn(M3, N3, generator=g).cuda()
+    kg = torch.randn(1, N3, generator=g).cuda() * 0.1
+    acc_scale = (1.0 + 0.3 * torch.randn(N3, generator=g)).cuda()
+    out3, cs2 = torch.full((M3, N3), float("nan"), device="cuda"), torch.zeros(N3, device="cuda")
+    d = nat.GemmDesc()
+    for k, v in dict(a=dy, b=w, aux2=aux2, kg=kg, out=out3, colsum2=cs2, scratch=torch.empty(2 * N3 * K3, device="cuda"),
+                     acc_scale=acc_scale).items():
+        setattr(d, k, v.data_ptr())
+    d.M, d.N, d.K, d.group_rows = M3, N3, K3, 0
+    nat.check(nat.lib.mpmae_gemm_epi(3, backend, C.byref(d), C.c_void_p(st)), "gemm_epi")
+    torch.cuda.synchronize()
+    x2 = aux2.double()
+    ref3 = (dy.double() @ w.double().t() * acc_scale.double() + kg.double() * _gelu_ref(x2)) * _gelu_grad_ref(x2)
+    assert float((out3.double() - ref3).abs().max() / ref3.abs().max()) < tol
+    assert float((cs2.double() - ref3.sum(0)).norm() / ref3.sum(0).norm()) < 20 * tol
+
+
+@pytest.mark.parametrize("backend,tol", [(1, 1e-4), (3, 2e-4)])
+@pytest.mark.parametrize("shape", [(38912, 40, 160), (19456, 160, 640), (4864, 320, 1280), (2500, 96, 384)])
+def test_gemm_in_kernel_grn_scale(native_lib, shape, backend, tol):
+    """pw2 of a sparse block: A = saved pre-activation, consumed as gelu(a) * s with the batch-global GRN scale
+    s = 1 + gamma * nx, nx = G / (mean G + eps), G = sqrt(gsq) (models/sparse_norm_layers.py:24-33) derived in the kernel's
+    prologue from gsq = sum_rows gelu(a)^2; nx / scale / denom are written out for the backward pass."""
+    nat = native_lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    b = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    gamma = torch.randn(K, generator=g).cuda()
+    h = _gelu_ref(a.double())
+    gsq = (h ** 2).sum(0)
+    G = gsq.sqrt()
+    den = G.mean() + 1e-6
+    sc = 1 + gamma.double() * G / den
+    ref = (h * sc) @ b.double().t() + bias.double() + resid.double()
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.full((M, N), float("nan"), device="cuda")
+    nx, scale = torch.full((K,), float("nan"), device="cuda"), torch.full((K,), float("nan"), device="cuda")
+    denom = torch.full((1,), float("nan"), device="cuda")
+    d = nat.GemmDesc()
+    for k, v in dict(a=a, b=b, bias=bias, resid=resid, out=out, scratch=torch.empty(2 * N * K, device="cuda"), grn_gsq=gsq.float(),
+                     grn_gamma=gamma, grn_nx=nx, grn_scale=scale, grn_denom=denom).items():
+        setattr(d, k, v.data_ptr())
+    d.M, d.N, d.K, d.group_rows, d.a_gelu, d.grn_eps = M, N, K, 0, 1, 1e-6
+    nat.check(nat.lib.mpmae_gemm_epi(0, backend, C.byref(d), C.c_void_p(st)), "gemm_epi")
+    torch.cuda.synchronize()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
+    assert abs(float(denom) - float(den)) < 1e-5 * float(den)
+    assert float((nx.double() - G / den).abs().max()) < 1e-5 * float((G / den).abs().max())
+    assert float((scale.double() - sc).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("backend,tol", [(0, 2e-6), (1, 2e-5)])
+@pytest.mark.parametrize("shape", [(2432, 40, 160), (608, 80, 320), (4864, 320, 1280), (9999, 160, 640)])
+def test_gemm_wgrad_gelu_operand(native_lib, shape, backend, tol):
+    """dW2f = dy^T . gelu(a): the activation is applied to the Y operand inside the kernel (splitter warps / on load)."""
+    nat = native_lib
+    R, N, K = shape
+    g = torch.Generator().manual_seed(R + N + K)
+    x = torch.randn(R, N, generator=g).cuda()
+    y = torch.randn(R, K, generator=g).cuda()
+    dw = torch.zeros(N, K, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    nat.check(nat.lib.mpmae_gemm_wgrad_act(backend, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                           R, N, K, 1, C.c_void_p(st)), "gemm_wgrad_act")
+    torch.cuda.synchronize()
+    ref = x.double().t() @ _gelu_ref(y.double())
+    assert float((dw.double() - ref).norm() / ref.norm()) < tol
