@@ -164,6 +164,7 @@ class Workload:
         self.resident = [{k: v.to(dev) for k, v in b.items()} for b in self.host]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host[0].values())
         self.net = self.model            # what is called: the module itself, or its DistributedDataParallel wrap (ddp leg)
+        self.graphed, self.graph_error = None, None
         from mmearth_train_b200.data import DevicePrefetcher, LossReader
         self.prefetcher = DevicePrefetcher(None, dev)   # persistent device buffers / pinned slots, as in a training run
         self.reader = LossReader(dev)                   # every step's loss is read on the host, two steps late
@@ -173,12 +174,31 @@ class Workload:
         b = fo.synthetic_batch(self.B, self.cfg["img_size"], self.cfg["out_modalities"], seed=1234 + rank * 100 + i)
         return {k: v.pin_memory() for k, v in b.items()}
 
-    def step_resident(self, i):
-        loss = self.net(self.resident[i % self.nb], mask_ratio=0.6)[0]
+    def eager_step(self, batch):
+        loss = self.net(batch, mask_ratio=0.6)[0]
         loss.backward()
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
         return loss
+
+    def enable_graph(self):
+        """Capture the iteration once (mmearth_train_b200.GraphedStep: fwd + bwd (+ NCCL all-reduce) + AdamW as one CUDA
+        graph); the step then is a copy of the batch into the graph's static inputs and one cudaGraphLaunch."""
+        import mmearth_train_b200 as mp
+        try:
+            self.graphed = mp.GraphedStep(self.model, self.opt, self.resident[0], mask_ratio=0.6)
+        except Exception as e:                     # capture refused (e.g. an NCCL build without stream-capture support)
+            self.graphed, self.graph_error = None, repr(e)[:200]
+        return self.graphed is not None
+
+    def step(self, batch):
+        return self.graphed(batch) if self.graphed is not None else self.eager_step(batch)
+
+    def step_resident(self, i):
+        return self.step(self.resident[i % self.nb])
+
+    def eager_resident(self, i):
+        return self.eager_step(self.resident[i % self.nb])
 
     def run_e2e(self, n):
         """n steps through the public API: pinned host batches in (copy stream, overlapped with the previous step),
@@ -187,10 +207,7 @@ class Workload:
         reader = self.reader
         self.prefetcher.src = (self.host[i % self.nb] for i in range(n))   # what a DataLoader(pin_memory=True) yields
         for b in self.prefetcher:
-            loss = self.net(b, mask_ratio=0.6)[0]
-            loss.backward()
-            self.opt.step()
-            self.opt.zero_grad(set_to_none=True)
+            loss = self.step(b)
             v = reader.push(loss)                                     # D2H read of the step's result (pinned, event-tracked)
             last = v if v is not None else last
         for v in reader.flush():                                      # the reads still in flight land inside the timed region
@@ -221,6 +238,10 @@ class Workload:
 
     def measure(self, K, W):
         for i in range(W):
+            self.eager_resident(i)
+        self.ms_eager = self.timed(self.eager_resident, K)
+        self.enable_graph()
+        for i in range(W):
             self.step_resident(i)
         ms = self.timed(self.step_resident, K)
         self.run_e2e(W)
@@ -232,6 +253,7 @@ class Workload:
         pk = peaks()
         n = self.B * self.world * K
         return {"samples_s": n / (ms / 1e3), "ms_per_step": ms / K, "per_gpu_batch": self.B, "global_batch": self.B * self.world,
+                "cuda_graph": self.graphed is not None, "eager_ms_per_step": self.ms_eager / K,
                 "step_hbm_frac": (mb * 1e6 * self.B * K / (ms / 1e3)) / (pk["hbm"] * 1e9),
                 "step_tf32_frac": (gf * 1e9 * self.B * K / (ms / 1e3)) / (pk["bf16_sustained"] / 2 * 1e12),
                 "e2e": {"value": n / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": self.h2d_bytes,
@@ -253,7 +275,7 @@ class Workload:
         noise_of = lambda r: torch.randn(self.B, model.num_patches, generator=torch.Generator().manual_seed(4242 + r))
         model.noise_override = noise_of(rank)
         model.zero_grad(set_to_none=True)
-        self.net(self.resident[0], mask_ratio=0.6)[0].backward()          # distributed: gradient = mean over ranks
+        self.net(self.resident[0], mask_ratio=0.6)[0].backward()          # distributed (eager): gradient = mean over ranks
         g_dist = model.flat_grads.clone()
         rel = None
         dist.barrier()
@@ -280,9 +302,9 @@ class Workload:
         import torch
         self.net = torch.nn.parallel.DistributedDataParallel(self.model, device_ids=[self.dev.index], find_unused_parameters=False)
         for i in range(W):
-            self.step_resident(i)
-        ms = self.timed(self.step_resident, K)
-        loss = float(self.step_resident(0))
+            self.eager_resident(i)
+        ms = self.timed(self.eager_resident, K)
+        loss = float(self.eager_resident(0).detach())
         self.net = self.model
         return {"ms_per_step": ms / K, "samples_s": self.B * self.world * K / (ms / 1e3), "loss": loss}
 
@@ -329,6 +351,10 @@ def main():
     if rank == 0:
         sampler.start()          # started before the warm-up so that nvidia-smi is already sampling when the timed steps run
     for i in range(W):
+        wl.eager_resident(i)
+    ms_eager = wl.timed(wl.eager_resident, K)
+    wl.enable_graph()
+    for i in range(W):
         wl.step_resident(i)
     ms = wl.timed(wl.step_resident, K)
     clocks = sampler.stop() if rank == 0 else None
@@ -346,16 +372,17 @@ def main():
     torch.cuda.synchronize()
     plan.profile_begin()
     for i in range(prof_steps):
-        wl.step_resident(i)
+        wl.eager_resident(i)                 # the per-launch events are recorded by the library on eager launches
     rows = plan.profile_report()
     launches_per_step = plan.launches(False) + plan.launches(True) + 1   # + fused AdamW
     workspace_bytes, h2d_bytes, NB, backend_used = plan.workspace_bytes, wl.h2d_bytes, wl.nb, model.gemm_backend
+    graphed, graph_error = wl.graphed is not None, wl.graph_error
     wl.close()
 
     # ---- the other BASELINE.json configurations, briefly: same protocol, 10 timed steps each
     others = {}
     names = a.others.split(",") if a.others not in (None, "none") else ([] if a.others == "none" else
-                                                                        (["cfg3", "cfg4", "cfg5a", "cfg5b"] if a.config == "cfg2" else []))
+                                                                        (["cfg1", "cfg3", "cfg4", "cfg5a", "cfg5b"] if a.config == "cfg2" else []))
     for name in names:
         o = Workload(name, dev, rank, world, a.backend, nb=3)
         oms, oms_e2e = o.measure(10, 3)
@@ -418,6 +445,9 @@ def main():
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "loss": loss_val, "input_flags": flags,
+                "step_api": ("mmearth_train_b200.GraphedStep: fwd + bwd" + (" + NCCL all-reduce" if world > 1 else "") + " + AdamW captured once, "
+                             "replayed as one CUDA graph") if graphed else "eager: model(batch) -> loss.backward() -> optimizer.step()",
+                "eager": {"ms_per_step": ms_eager / K, "samples_s": B * world * K / (ms_eager / 1e3), "graph_error": graph_error},
                 "other_configs": others}
         if world > 1:
             line["replica_check"] = replica["ranks_differing_from_rank0"] + replica_after_ddp

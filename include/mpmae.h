@@ -200,7 +200,8 @@ int mpmae_adamw_step(float *params, const float *grads, float *exp_avg, float *e
 /* The same step with its per-step scalars in DEVICE memory, for a loss-scaler loop without the host sync of
  * torch.cuda.amp.GradScaler.step (helpers.py:470-506): dev_state[0] = factor applied to the gradient (1 / loss scale,
  * times a clipping coefficient), dev_state[1] != 0 = a non-finite gradient was found: parameters and moments are left
- * untouched (the step is skipped), dev_state[2] = 1-based number of this step.  n % 4 == 0, 16-byte aligned buffers. */
+ * untouched (the step is skipped), dev_state[2] = 1-based number of this step; lr < 0 = read the learning rate from
+ * dev_state[3] (a step captured in a CUDA graph).  n % 4 == 0, 16-byte aligned buffers. */
 int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                          const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
                          float weight_decay, const float *dev_state, void *cuda_stream);

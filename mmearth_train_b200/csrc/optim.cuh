@@ -49,12 +49,14 @@ __global__ void adamw_vec4_kernel(float4 *__restrict__ p, const float4 *__restri
 // The same update with the per-step scalars read from DEVICE memory, so a GradScaler-style loop (helpers.py:470-506) needs no
 // host sync: state[0] = factor applied to the gradient (1 / loss scale, times the clipping coefficient), state[1] != 0 =
 // non-finite gradient found -> the launch leaves parameters and moments untouched (GradScaler.step skips the step),
-// state[2] = 1-based number of this step (bias corrections).
+// state[2] = 1-based number of this step (bias corrections); a NEGATIVE host lr means "read the learning rate from state[3]"
+// (a step captured in a CUDA graph cannot take per-iteration host scalars).
 __global__ void adamw_vec4_dev_kernel(float4 *__restrict__ p, const float4 *__restrict__ g, float4 *__restrict__ m,
-                                      float4 *__restrict__ v, const uchar4 *__restrict__ decay, int64_t n4, float lr, float b1,
+                                      float4 *__restrict__ v, const uchar4 *__restrict__ decay, int64_t n4, float lr_host, float b1,
                                       float b2, float eps, float wd, const float *__restrict__ state) { pdl_prologue();
   const float ginv = state[0];
   if (state[1] != 0.f) return;
+  const float lr = lr_host < 0.f ? state[3] : lr_host;
   const double t = (double)state[2];
   const float bc1 = 1.f - (float)pow((double)b1, t);
   const float bc2_sqrt = sqrtf(1.f - (float)pow((double)b2, t));

@@ -146,26 +146,32 @@ class FlatAdamW:
                 self.betas[0], self.betas[1], self.eps, self.weight_decay, step, grad_scale_inv,
                 C.c_void_p(stream)), "mpmae_adamw_step")
 
-    def step_dev(self, grad_factor: torch.Tensor, found_inf: torch.Tensor) -> None:
+    def _ensure_dev_state(self) -> torch.Tensor:
+        if self._dev_state is None:
+            self._dev_state = torch.tensor([1.0, 0.0, float(self._t + 1), float(self.lr)], device=self.model.flat_params.device)
+        return self._dev_state
+
+    def step_dev(self, grad_factor=None, found_inf=None, lr_on_device: bool = False) -> None:
         """One step whose gradient factor (1 / loss scale x clipping coefficient) and skip flag are 0-d DEVICE tensors:
         nothing is read back, a step with ``found_inf != 0`` changes nothing and is not counted (what
-        ``GradScaler.step`` does after a host sync, ``helpers.py:498``)."""
+        ``GradScaler.step`` does after a host sync, ``helpers.py:498``).  ``None`` leaves the stored factor / flag as they are.
+        ``lr_on_device``: the learning rate is read from ``dev_state[3]`` instead of ``param_groups`` (CUDA-graph replay)."""
         g = self.model.flat_grads
         if g is None:
             raise RuntimeError("no gradients: call loss.backward() first")
         p = self.model.flat_params
-        if self._dev_state is None:
-            self._dev_state = torch.tensor([1.0, 0.0, float(self._t + 1)], device=p.device)
-        st = self._dev_state
-        st[0] = grad_factor
-        st[1] = found_inf
+        st = self._ensure_dev_state()
+        if grad_factor is not None:
+            st[0] = grad_factor
+        if found_inf is not None:
+            st[1] = found_inf
         stream = torch.cuda.current_stream(p.device).cuda_stream
         with torch.cuda.device(p.device):
             nat.check(nat.lib.mpmae_adamw_step_dev(
                 C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(self.exp_avg.data_ptr()),
-                C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_void_p(self.decay.data_ptr()), p.numel(), self.lr,
-                self.betas[0], self.betas[1], self.eps, self.weight_decay, C.c_void_p(st.data_ptr()),
-                C.c_void_p(stream)), "mpmae_adamw_step_dev")
+                C.c_void_p(self.exp_avg_sq.data_ptr()), C.c_void_p(self.decay.data_ptr()), p.numel(),
+                -1.0 if lr_on_device else self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                C.c_void_p(st.data_ptr()), C.c_void_p(stream)), "mpmae_adamw_step_dev")
         st[2] += (st[1] == 0).to(st.dtype)
 
     def grad_norm(self, clip: float = None) -> torch.Tensor:
