@@ -49,6 +49,12 @@ struct GemmArgs {
   const float *grn_gsq, *grn_gamma;   // [K]
   float *grn_nx, *grn_scale, *grn_denom;
   float grn_eps;
+  // Backward of the batch-global GRN statistic in the prologue of the EPI_DH_GELU kernel (tcgen05 path; replaces kg): from
+  // ds[n] = sum_rows dg * h (complete before the launch), nx, the denominator and gamma every CTA derives
+  //   dNx = gamma * ds ; dGx = dNx / den - (sum_j dNx_j Gx_j) / (N den^2) ; kg[n] = dGx / Gx   
+  // and CTA 0 accumulates dgamma[n] += nx * ds.
+  const float *grnb_ds, *grnb_nx, *grnb_denom, *grnb_gamma;
+  float *grnb_dgamma;
 };
 
 // Column accumulation helper shared by the SIMT and tcgen05 epilogues: a thread owns `nrows`

@@ -69,6 +69,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if ((uint64_t)(clock64() - t0) > kSpinLimit) __trap();
   }
 }
+// Wait of a role that runs AHEAD of its consumer (the TMA producer on a full ring, the MMA issuer on a busy accumulator
+// stage): its wake-up latency is off the critical path, so it sleeps between polls instead of spinning.  The ncu source page
+// of round 1's pw1 kernel showed 15 % of all issued instructions in the spin loops of these two warps (try_wait + clock read
+// + branch), issue slots taken from the epilogue warps that bound the kernel.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -349,12 +361,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
   if (warp >= 2 && warp < 2 + kEpiWarps) {
+    float grnb_cross = 0.f, grnb_den = 1.f;
+    if (MODE == EPI_DH_GELU && g.grnb_ds) {   // backward of the batch-global GRN statistic: the cross term is a sum over all N
+      grnb_den = __ldg(g.grnb_denom);
+      float part = 0.f;
+      for (int i = threadIdx.x - 64; i < g.N; i += kEpiThreads)
+        part += __ldg(g.grnb_gamma + i) * __ldg(g.grnb_ds + i) * (__ldg(g.grnb_nx + i) * grnb_den);
+      part = warp_sum(part);
+      if (lane == 0) colacc[warp - 2] = part;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      float tot = 0.f;
+      for (int i = 0; i < kEpiWarps; ++i) tot += colacc[i];
+      grnb_cross = tot / ((float)g.N * grnb_den * grnb_den);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
     if (MODE != EPI_STORE)
       for (int i = threadIdx.x - 64; i < (kTcGroups + 1) * bn; i += kEpiThreads) colacc[i] = 0.f;
     for (int i = threadIdx.x - 64; i < p.num_n * bn; i += kEpiThreads) {
       vec_bias_all[i] = (g.bias && i < g.N) ? __ldg(g.bias + i) : 0.f;
       if (MODE == EPI_DH_GELU) {
-        vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+        if (g.grnb_ds) {
+          float kgv = 0.f;
+          if (i < g.N) {
+            const float dsv = __ldg(g.grnb_ds + i), nx = __ldg(g.grnb_nx + i), gx = nx * grnb_den;
+            const float dgx = __ldg(g.grnb_gamma + i) * dsv / grnb_den - grnb_cross;
+            kgv = gx > 0.f ? dgx / gx : 0.f;
+            if (blockIdx.x == 0) atomicAdd(g.grnb_dgamma + i, nx * dsv);
+          }
+          vec_kg_all[i] = kgv;
+        } else {
+          vec_kg_all[i] = (g.kg && i < g.N) ? __ldg(g.kg + i) : 0.f;
+        }
         vec_as_all[i] = (g.acc_scale && i < g.N) ? __ldg(g.acc_scale + i) : 1.f;
       }
       if (MODE != EPI_STORE) { statacc1[i] = 0.f; statacc2[i] = 0.f; }
@@ -382,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool tail = w.wn != bn;
         const uint32_t wb_bytes = (uint32_t)w.wn * BK * 4;   // bytes of one weight box of this item
         for (int kb = 0; kb < p.num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           uint8_t *sa = smem + (size_t)stage * stage_bytes;
           if (BF16) {
             mbar_expect_tx(&full_bar[stage], 2 * a_bytes + (b_res ? 0 : 2 * wb_bytes));
@@ -411,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       WorkItem w;
       for (int it = 0; get_work(p, it, w); ++it) {
         const uint32_t idesc = BF16 ? make_idesc_bf16(w.wn) : make_idesc(w.wn);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         for (int kb = 0; kb < p.num_k; ++kb) {
@@ -1083,7 +1120,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
         const int c_begin = sp * p.chunks_per_split;
         const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
         for (int ch = c_begin; ch < c_end; ++ch) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           uint8_t *sm = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], m_bytes + n_bytes);
 #pragma unroll
@@ -1103,7 +1140,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
         const int sp = item / (p.num_m * p.num_n);
         const int c_begin = sp * p.chunks_per_split;
         const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         for (int ch = c_begin; ch < c_end; ++ch) {

@@ -701,10 +701,23 @@ __global__ void __launch_bounds__(512) colsum_kernel(const float *__restrict__ x
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tr < rpp) {
     const float4 *xp = reinterpret_cast<const float4 *>(x) + c4_0 + tc;
-    for (int64_t r = (int64_t)blockIdx.x * rpp + tr; r < R; r += (int64_t)gridDim.x * rpp) {
+    const int64_t step = (int64_t)gridDim.x * rpp;
+    int64_t r = (int64_t)blockIdx.x * rpp + tr;
+    float4 acc1 = acc, acc2 = acc, acc3 = acc;
+    for (; r + 3 * step < R; r += 4 * step) {   // four independent loads in flight per thread: the pass is latency bound
+      const float4 v0 = __ldg(xp + r * c4_total), v1 = __ldg(xp + (r + step) * c4_total);
+      const float4 v2 = __ldg(xp + (r + 2 * step) * c4_total), v3 = __ldg(xp + (r + 3 * step) * c4_total);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
+      acc2.x += v2.x; acc2.y += v2.y; acc2.z += v2.z; acc2.w += v2.w;
+      acc3.x += v3.x; acc3.y += v3.y; acc3.z += v3.z; acc3.w += v3.w;
+    }
+    for (; r < R; r += step) {
       const float4 v = __ldg(xp + r * c4_total);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+    acc.x += (acc1.x + acc2.x) + acc3.x; acc.y += (acc1.y + acc2.y) + acc3.y;
+    acc.z += (acc1.z + acc2.z) + acc3.z; acc.w += (acc1.w + acc2.w) + acc3.w;
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -729,7 +742,7 @@ inline void launch_colsum(const float *x, const float *rs, float *out, int64_t R
   if (threads > 512) threads = 512;
   const int rpp = threads / c4n > 0 ? threads / c4n : 1;
   int64_t gx = cdiv64(R, (int64_t)rpp * 8);            // >= 8 passes per CTA
-  if (gx > 148 * 4) gx = 148 * 4;
+  if (gx > 148 * 4 / chunks) gx = chunks >= 4 ? 148 : 148 * 4 / chunks;
   if (gx < 1) gx = 1;
   pdl(colsum_kernel, dim3((unsigned)gx, chunks), threads, 0, st)(x, rs, out, R, C);
 }

@@ -807,17 +807,23 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
     u.W = c.p(bp.w2); u.s_n = D4; u.s_k = 1; u.scale_k = c.w(bw.scale); u.shift_k = c.p(bp.beta);
     u.dWf = dwf2; u.dbf = dbf2; u.dW = c.g(bp.w2); u.dscale = dsv; u.dshift = c.g(bp.beta); u.dbias = c.g(bp.b2);
     u.N = C; u.K = D4; u.SL = D4;
-    if (c.ok()) {   // un-fold + (last CTA) backward of the GRN statistic: dgamma, kg
-      GrnBwdArgs q{c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, reinterpret_cast<unsigned int *>(c.w(bw.cnt_b))};
-      pdl(unfold_grn_kernel, u.K, 256, 0, c.st)(u, q);
-      c.post("unfold_pw2");
-    }
     // da = ((dy . W2) * s + kg * gelu(a)) * gelu'(a) ; db1f = sum da rides on the epilogue
     GemmArgs gd{};
     gd.A = dy; use_slot(c, gd, bw.s2, true); gd.out = da; gd.aux = nullptr; gd.aux2 = c.w(bw.a); gd.kg = kg;
     gd.acc_scale = c.w(bw.scale);
     gd.colsum2 = dbf1;
     gd.M = R; gd.N = D4; gd.K = C; gd.group_rows = group_rows;
+    if (gemm_uses_tc<EPI_DH_GELU>(c, gd)) {
+      // plain un-fold; the backward of the GRN statistic (dgamma, kg) happens in the prologue of the da kernel
+      unfold(c, u, "unfold_pw2");
+      gd.kg = nullptr;
+      gd.grnb_ds = dsv; gd.grnb_nx = c.w(bw.nx); gd.grnb_denom = c.w(bw.denom); gd.grnb_gamma = c.p(bp.gamma);
+      gd.grnb_dgamma = c.g(bp.gamma);
+    } else if (c.ok()) {   // un-fold + (last CTA) backward of the GRN statistic: dgamma, kg
+      GrnBwdArgs q{c.w(bw.nx), c.w(bw.denom), c.p(bp.gamma), c.g(bp.gamma), kg, reinterpret_cast<unsigned int *>(c.w(bw.cnt_b))};
+      pdl(unfold_grn_kernel, u.K, 256, 0, c.st)(u, q);
+      c.post("unfold_pw2");
+    }
     gemm<EPI_DH_GELU>(c, gd, "da");
   }
   // pw1 (LN affine folded): dW1f = da^T . vhat
@@ -1335,11 +1341,15 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     sb.d_ln1_w = c.g(pl->st_lnw); sb.d_ln1_b = c.g(pl->st_lnb);
     if (c.ok()) {
       const size_t ssm = (size_t)(5 + sb.f.s2) * sb.f.C0 * 4;
-      switch (cdiv(sb.f.C0, 32)) {
-        case 1: pdl(stem_bwd_kernel<1>, 148 * 8, 256, ssm, c.st)(sb); break;
-        case 2: pdl(stem_bwd_kernel<2>, 148 * 6, 256, ssm, c.st)(sb); break;
-        case 3: pdl(stem_bwd_kernel<3>, 148 * 4, 256, ssm, c.st)(sb); break;
-        default: pdl(stem_bwd_kernel<4>, 148 * 4, 256, ssm, c.st)(sb); break;
+      c.acct(4.0 * ((2.0 + 2.0 * sb.f.s2) * sb.f.R0 * sb.f.C0), 0);
+      static const bool no_vec = getenv("MPMAE_NO_STEMVEC") != nullptr;
+      if (no_vec || !launch_stem_bwd_vec(sb, c.st)) {
+        switch (cdiv(sb.f.C0, 32)) {
+          case 1: pdl(stem_bwd_kernel<1>, 148 * 8, 256, ssm, c.st)(sb); break;
+          case 2: pdl(stem_bwd_kernel<2>, 148 * 6, 256, ssm, c.st)(sb); break;
+          case 3: pdl(stem_bwd_kernel<3>, 148 * 4, 256, ssm, c.st)(sb); break;
+          default: pdl(stem_bwd_kernel<4>, 148 * 4, 256, ssm, c.st)(sb); break;
+        }
       }
       c.post("stem_bwd");
     }

@@ -433,4 +433,118 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(StemBwdArgs a) { pdl_prol
   }
 }
 
+// The same backward with the (row, part) mapping of the LayerNorm kernels: LPR adjacent lanes (a power of two >= C0 / 4)
+// share one row and every lane owns one float4 column, so a warp handles 32 / LPR rows per iteration with 16-byte loads and
+// log2(LPR)-step row reductions.  The warp-per-row kernel above leaves 24 of 64 lane slots idle at C0 = 40 and issues four
+// times as many instructions (226 us of the 7.8 ms cfg2 step in round 1).  C0 % 4 == 0, C0 <= 128, s2 <= 4.
+template <int LPR>
+__global__ void __launch_bounds__(256) stem_bwd_vec_kernel(StemBwdArgs a) { pdl_prologue();
+  extern __shared__ float red[];  // [(5 + s2)][C0]
+  const StemArgs &p = a.f;
+  const int C0 = p.C0, s2 = p.s2, nvec = 5 + s2;
+  for (int i = threadIdx.x; i < nvec * C0; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane % LPR, rsub = lane / LPR, c = sub * 4;
+  const bool colok = c < C0;
+  const float inv_c = 1.f / (float)C0;
+  auto ld4 = [](const float *ptr) { return __ldg(reinterpret_cast<const float4 *>(ptr)); };
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 w1 = colok ? ld4(p.ln1_w + c) : z4, w0 = colok ? ld4(p.ln0_w + c) : z4, b0 = colok ? ld4(p.ln0_b + c) : z4;
+  float4 kj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) kj[j] = (colok && j < s2) ? ld4(p.kernel + j * C0 + c) : z4;
+  float4 part[9];
+#pragma unroll
+  for (int v = 0; v < 9; ++v) part[v] = z4;
+  auto fma4 = [](float4 &acc, const float4 &x, const float4 &y) {
+    acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y); acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+  };
+  auto add4 = [](float4 &acc, const float4 &x) { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; };
+  auto sum4 = [](const float4 &x) { return (x.x + x.y) + (x.z + x.w); };
+  auto dot4 = [](const float4 &x, const float4 &y) { return (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w); };
+  // two row groups per iteration, every global load issued before the first reduction: the loop is bound by the latency of
+  // its dependent load -> shuffle -> store chain, so the loads of both groups (and of all children) are put in flight at once
+  const int64_t stride = (int64_t)gridDim.x * nw;
+  for (int64_t rg0 = (int64_t)blockIdx.x * nw + warp; rg0 * RPW < p.R0; rg0 += 2 * stride) {
+    int64_t r[2];
+    bool ok[2];
+    float4 g[2], nh[2], ch[2][4];
+    float rs[2], rcs[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      r[u] = (rg0 + u * stride) * RPW + rsub;
+      ok[u] = colok && r[u] < p.R0;
+      g[u] = ok[u] ? ld4(a.dx0 + r[u] * C0 + c) : z4;
+      nh[u] = ok[u] ? ld4(p.shat + r[u] * C0 + c) : z4;
+      rs[u] = ok[u] ? __ldg(p.rstd_s + r[u]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool okj = ok[u] && j < s2;
+        ch[u][j] = okj ? ld4(p.chat + (r[u] * s2 + j) * C0 + c) : z4;
+        rcs[u][j] = okj ? __ldg(p.rstd_c + r[u] * s2 + j) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      // LN1 backward
+      fma4(part[0], g[u], nh[u]);
+      add4(part[1], g[u]);
+      const float4 dsh = make_float4(g[u].x * w1.x, g[u].y * w1.y, g[u].z * w1.z, g[u].w * w1.w);
+      const float s1 = group_sum(sum4(dsh), LPR) * inv_c, s2s = group_sum(dot4(dsh, nh[u]), LPR) * inv_c;
+      const float4 ds = make_float4(rs[u] * (dsh.x - s1 - nh[u].x * s2s), rs[u] * (dsh.y - s1 - nh[u].y * s2s),
+                                    rs[u] * (dsh.z - s1 - nh[u].z * s2s), rs[u] * (dsh.w - s1 - nh[u].w * s2s));
+      add4(part[2], ds);
+      // children
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= s2) break;
+        const float4 cj = ch[u][j];
+        float4 gj, dgj;
+        gelu_both_f(fmaf(cj.x, w0.x, b0.x), gj.x, dgj.x); gelu_both_f(fmaf(cj.y, w0.y, b0.y), gj.y, dgj.y);
+        gelu_both_f(fmaf(cj.z, w0.z, b0.z), gj.z, dgj.z); gelu_both_f(fmaf(cj.w, w0.w, b0.w), gj.w, dgj.w);
+        fma4(part[5 + j], ds, gj);                       // d_kernel[j]
+        const float4 dt = make_float4(ds.x * kj[j].x * dgj.x, ds.y * kj[j].y * dgj.y, ds.z * kj[j].z * dgj.z, ds.w * kj[j].w * dgj.w);
+        fma4(part[3], dt, cj);
+        add4(part[4], dt);
+        const float4 dch = make_float4(dt.x * w0.x, dt.y * w0.y, dt.z * w0.z, dt.w * w0.w);
+        const float t1 = group_sum(sum4(dch), LPR) * inv_c, t2 = group_sum(dot4(dch, cj), LPR) * inv_c;
+        if (ok[u]) {
+          const float rc_std = rcs[u][j];
+          *reinterpret_cast<float4 *>(a.dc + (r[u] * s2 + j) * C0 + c) =
+              make_float4(rc_std * (dch.x - t1 - cj.x * t2), rc_std * (dch.y - t1 - cj.y * t2), rc_std * (dch.z - t1 - cj.z * t2),
+                          rc_std * (dch.w - t1 - cj.w * t2));
+        }
+      }
+    }
+  }
+  if (colok) {
+#pragma unroll
+    for (int v = 0; v < 9; ++v)
+      if (v < nvec) {
+        atomicAdd(&red[v * C0 + c], part[v].x); atomicAdd(&red[v * C0 + c + 1], part[v].y);
+        atomicAdd(&red[v * C0 + c + 2], part[v].z); atomicAdd(&red[v * C0 + c + 3], part[v].w);
+      }
+  }
+  __syncthreads();
+  float *dst[5] = {a.d_ln1_w, a.d_ln1_b, a.d_bias, a.d_ln0_w, a.d_ln0_b};
+  for (int i = threadIdx.x; i < nvec * C0; i += blockDim.x) {
+    const int v = i / C0, cc = i - v * C0;
+    if (v < 5) atomicAdd(&dst[v][cc], red[i]);
+    else atomicAdd(&a.d_kernel[(v - 5) * C0 + cc], red[i]);
+  }
+}
+inline bool launch_stem_bwd_vec(const StemBwdArgs &sb, cudaStream_t st) {
+  const int C0 = sb.f.C0, c4 = C0 / 4;
+  if (C0 % 4 != 0 || c4 > 32 || sb.f.s2 > 4) return false;
+  if ((((uintptr_t)sb.dx0 | (uintptr_t)sb.dc | (uintptr_t)sb.f.shat | (uintptr_t)sb.f.chat) & 15) != 0) return false;
+  const size_t ssm = (size_t)(5 + sb.f.s2) * C0 * 4;
+  const int grid = 148 * 8;
+  if (c4 <= 8) pdl(stem_bwd_vec_kernel<8>, grid, 256, ssm, st)(sb);
+  else if (c4 <= 16) pdl(stem_bwd_vec_kernel<16>, grid, 256, ssm, st)(sb);
+  else pdl(stem_bwd_vec_kernel<32>, grid, 256, ssm, st)(sb);
+  return true;
+}
+
 }  // namespace mpmae
