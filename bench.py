@@ -214,6 +214,39 @@ class Workload:
             last = v
         return last
 
+    def setup_raw(self):
+        """Stored-dtype host batches + the loader's transform on the device (data.RawBatchTransform): what crosses PCIe is
+        the uint16 / uint8 / float32 arrays of the HDF5 files, not the widened float32 / int64 tensors (VERDICT r1 weak #12)."""
+        from mmearth_train_b200 import synthetic as fo
+        from mmearth_train_b200.data import DevicePrefetcher, RawBatchTransform
+        import torch
+        mods = {"sentinel2": fo.S2_BANDS}
+        mods.update({m: (fo.S2_BANDS if m == "sentinel2" else "all") for m in self.model.out_modalities})
+        self.raw_tf = RawBatchTransform(mods, fo.raw_modalities_full(), fo.synthetic_band_stats(), exact=True)
+        self.raw_host = []
+        for i in range(self.nb):
+            b = fo.synthetic_raw_batch(self.B, self.cfg["img_size"], seed=4321 + self.rank * 100 + i)
+            self.raw_host.append({k: v.pin_memory() for k, v in b.items() if k in mods})
+        self.raw_l2a = (torch.arange(self.B) % 2 == 1).to(self.dev)
+        self.raw_prefetcher = DevicePrefetcher(None, self.dev)
+        self.raw_bytes = sum(v.numel() * v.element_size() for v in self.raw_host[0].values())
+
+    def run_e2e_raw(self, n):
+        last = None
+        reader = self.reader
+        self.raw_prefetcher.src = (self.raw_host[i % self.nb] for i in range(n))
+        for b in self.raw_prefetcher:
+            if self.graphed is not None:   # the transform writes straight into the graph's static inputs
+                self.raw_tf(b, self.raw_l2a, into=self.graphed.static)
+                loss = self.graphed(None)
+            else:
+                loss = self.step(self.raw_tf(b, self.raw_l2a))
+            v = reader.push(loss)
+            last = v if v is not None else last
+        for v in reader.flush():
+            last = v
+        return last
+
     def timed(self, fn, n, whole=False):
         import torch
         import torch.distributed as dist
@@ -311,6 +344,7 @@ class Workload:
     def close(self):
         import torch
         self.model = self.opt = self.net = self.host = self.resident = self.prefetcher = self.reader = None
+        self.raw_host = self.raw_prefetcher = self.raw_tf = None
         import gc
         gc.collect()
         torch.cuda.empty_cache()
@@ -362,6 +396,10 @@ def main():
     ms_e2e = wl.timed(wl.run_e2e, K, whole=True)
     loss_val = wl.run_e2e(1)
     flags = model.input_flags()
+    wl.setup_raw()
+    wl.run_e2e_raw(W)
+    ms_e2e_raw = wl.timed(wl.run_e2e_raw, K, whole=True)
+    raw_bytes = wl.raw_bytes
     replica = wl.replica_check() if world > 1 else None
     ddp = wl.ddp_leg(min(K, 10), 3) if world > 1 else None
     replica_after_ddp = wl.replica_check()["ranks_differing_from_rank0"] if world > 1 else None
@@ -443,6 +481,11 @@ def main():
                            "parallelism": f"dp{world}"},
                 "e2e": {"value": sps_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
+                "e2e_raw": {"value": B * world * K / (ms_e2e_raw / 1e3), "unit": "samples/s", "h2d_bytes_per_step": raw_bytes,
+                            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_raw / K,
+                            "what": "host batches in the STORED dtypes of the MMEarth files (uint16 / uint8 / float32); the loader's "
+                                    "per-sample transform (mmearth_dataset.py:58-153) runs on the device behind the copy "
+                                    "(data.RawBatchTransform, bit-exact against the reference loader)"},
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "loss": loss_val, "input_flags": flags,
                 "step_api": ("mmearth_train_b200.GraphedStep: fwd + bwd" + (" + NCCL all-reduce" if world > 1 else "") + " + AdamW captured once, "

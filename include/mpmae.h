@@ -206,6 +206,26 @@ int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, floa
                          const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
                          float weight_decay, const float *dev_state, void *cuda_stream);
 
+/* The loader's per-sample transform (mmearth_dataset.py:58-153) for a whole batch of arrays in their STORED dtypes, on the
+ * device, bit-identical to MMEarthDataset.__getitem__ (float64 arithmetic, one rounding to float32):
+ *   v = src[n, band[b], j]  ->  lut[v] (label maps; NaN = ignore)  |  NaN where v == nodata
+ *   ->  (v - mean[set][b]) / std[set][b] with set = l2a[n] (normalize != 0)
+ *   ->  out float32, or int64 with NaN -> -1 (out_int64 != 0).
+ * src_type: 0 uint8, 1 uint16, 2 float32.  inner = elements per (sample, band).  All pointers are device pointers. */
+#define MPMAE_RAW_MAX_BANDS 16
+typedef struct mpmae_raw_desc {
+  const void *src;
+  void *out;
+  const uint8_t *l2a;      /* [B] or null */
+  const double *lut;       /* [256] or null */
+  int64_t inner;
+  int32_t B, src_bands, n_bands, src_type, out_int64, has_nodata, normalize;
+  double nodata;
+  int32_t band[MPMAE_RAW_MAX_BANDS];
+  double mean[2][MPMAE_RAW_MAX_BANDS], std[2][MPMAE_RAW_MAX_BANDS];
+} mpmae_raw_desc;
+int mpmae_raw_transform(const mpmae_raw_desc *d, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,17 @@ class GemmDesc(C.Structure):
                [("grn_eps", C.c_float)]
 
 
+RAW_MAX_BANDS = 16
+
+
+class RawDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("out", C.c_void_p), ("l2a", C.c_void_p), ("lut", C.c_void_p), ("inner", C.c_int64),
+                ("B", C.c_int32), ("src_bands", C.c_int32), ("n_bands", C.c_int32), ("src_type", C.c_int32),
+                ("out_int64", C.c_int32), ("has_nodata", C.c_int32), ("normalize", C.c_int32), ("nodata", C.c_double),
+                ("band", C.c_int32 * RAW_MAX_BANDS), ("mean", (C.c_double * RAW_MAX_BANDS) * 2),
+                ("std", (C.c_double * RAW_MAX_BANDS) * 2)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -86,6 +97,7 @@ def _load():
         "mpmae_gemm_epi": (C.c_int, [I32, I32, C.POINTER(GemmDesc), P]),
         "mpmae_gemm_wgrad": (C.c_int, [I32, P, P, P, I64, I32, I32, P]),
         "mpmae_gemm_wgrad_act": (C.c_int, [I32, P, P, P, I64, I32, I32, I32, P]),
+        "mpmae_raw_transform": (C.c_int, [C.POINTER(RawDesc), P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
         "mpmae_adamw_step_dev": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, P, P]),
     }
@@ -100,7 +112,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_gemm_wgrad_act", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
+           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_gemm_wgrad_act", "mpmae_raw_transform", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
 
 
 def check(rc: int, what: str = "") -> None:

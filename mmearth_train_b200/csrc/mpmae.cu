@@ -26,6 +26,7 @@
 #include "loss.cuh"
 #include "misc_kernels.cuh"
 #include "optim.cuh"
+#include "raw_transform.cuh"
 #include "stem.cuh"
 
 using namespace mpmae;
@@ -1524,6 +1525,30 @@ int mpmae_gemm_wgrad_act(int32_t backend, const float *x, const float *y, float 
     e = launch_gemm_wgrad(w, st);
   }
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "wgrad: %s", cudaGetErrorString(e));
+  return MPMAE_OK;
+}
+
+int mpmae_raw_transform(const mpmae_raw_desc *d, void *cuda_stream) {
+  if (!d || !d->src || !d->out || d->B <= 0 || d->inner <= 0 || d->n_bands <= 0 || d->src_bands <= 0 || d->src_type < 0 || d->src_type > 2)
+    return fail(MPMAE_ERR_INVALID, "raw_transform args");
+  if (d->n_bands > MPMAE_RAW_MAX_BANDS && d->inner != 1)
+    return fail(MPMAE_ERR_UNSUPPORTED, "raw_transform: at most %d selected bands", MPMAE_RAW_MAX_BANDS);
+  RawArgs a{};
+  a.src = d->src; a.out = d->out; a.l2a = d->l2a; a.lut = d->lut; a.inner = d->inner; a.B = d->B; a.src_bands = d->src_bands;
+  a.n_bands = d->n_bands; a.src_type = d->src_type; a.out_int64 = d->out_int64; a.has_nodata = d->has_nodata;
+  a.normalize = d->normalize; a.nodata = d->nodata;
+  if (d->n_bands > MPMAE_RAW_MAX_BANDS) {   // a long vector taken whole (one-hot rows): one band of n_bands elements
+    if (d->normalize || d->src_bands != d->n_bands) return fail(MPMAE_ERR_UNSUPPORTED, "raw_transform: long rows are taken whole");
+    a.inner = d->n_bands; a.n_bands = 1; a.src_bands = 1; a.band[0] = 0;
+  } else {
+    for (int b = 0; b < d->n_bands; ++b) {
+      if (d->band[b] < 0 || d->band[b] >= d->src_bands) return fail(MPMAE_ERR_INVALID, "raw_transform: band index");
+      a.band[b] = d->band[b];
+      for (int s = 0; s < 2; ++s) { a.mean[s][b] = d->mean[s][b]; a.stdv[s][b] = d->std[s][b]; }
+    }
+  }
+  cudaError_t e = launch_raw_transform(a, static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "raw_transform: %s", cudaGetErrorString(e));
   return MPMAE_OK;
 }
 

@@ -175,7 +175,7 @@ class RawBatchTransform:
     def __init__(self, modalities: Dict[str, object], modalities_full: Dict[str, list], band_stats: Dict[str, dict],
                  exact: bool = True):
         self.modalities, self.exact = dict(modalities), exact
-        self._idx, self._stats, self._lut = {}, {}, {}
+        self._idx, self._stats, self._lut, self._stats_host = {}, {}, {}, {}
         for m, bands in self.modalities.items():
             if m not in NO_DATA_VAL:
                 raise ValueError(f"unknown modality {m!r}")
@@ -186,6 +186,7 @@ class RawBatchTransform:
                 keys = ("sentinel2_l1c", "sentinel2_l2a") if m == "sentinel2" else (m, m)
                 self._stats[m] = torch.stack([torch.tensor([band_stats[k]["mean"], band_stats[k]["std"]],
                                                            dtype=torch.float64)[:, idx] for k in keys])      # [2 (l1c/l2a), 2, nb]
+                self._stats_host[m] = self._stats[m].clone()
             if m in ("dynamic_world", "esa_worldcover"):
                 self._lut[m] = _label_lut(m)
 
@@ -195,7 +196,62 @@ class RawBatchTransform:
             t = cache[m] = t.to(device)
         return t
 
-    def __call__(self, raw: Dict[str, torch.Tensor], l2a: torch.Tensor) -> Dict[str, torch.Tensor]:
+    # ---- device path: one fused kernel per modality (csrc/raw_transform.cuh) through the C ABI
+    _SRC_TYPE = {torch.uint8: 0, torch.uint16: 1, torch.float32: 2}
+
+    def _native(self, raw: Dict[str, torch.Tensor], l2a: torch.Tensor, into: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        import ctypes as C
+
+        from . import _native as nat
+        out = {}
+        dev = next(iter(raw.values())).device
+        flags = l2a.to(device=dev, dtype=torch.uint8).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            for m in self.modalities:
+                x = raw[m].contiguous()
+                if x.dtype not in self._SRC_TYPE:
+                    raise TypeError(f"{m}: stored dtype {x.dtype} (expected uint8, uint16 or float32)")
+                B, src_bands = x.shape[0], x.shape[1]
+                inner = 1
+                for d in x.shape[2:]:
+                    inner *= d
+                idx = self._idx[m].tolist()
+                whole = m in ("biome", "eco_region")                   # one-hot rows are taken whole
+                n_bands = src_bands if whole else len(idx)
+                is_class = m in CLASS_TARGETS
+                shape, dtype = (B, n_bands) + tuple(x.shape[2:]), torch.int64 if is_class else torch.float32
+                o = into[m] if into is not None else torch.empty(shape, dtype=dtype, device=dev)
+                if tuple(o.shape) != shape or o.dtype != dtype or not o.is_contiguous() or o.device != dev:
+                    raise ValueError(f"{m}: output buffer {tuple(o.shape)} {o.dtype}, expected contiguous {shape} {dtype} on {dev}")
+                d = nat.RawDesc()
+                d.src, d.out, d.l2a = x.data_ptr(), o.data_ptr(), flags.data_ptr()
+                d.lut = self._on(self._lut, m, dev).data_ptr() if m in self._lut else None
+                d.inner, d.B, d.src_bands, d.n_bands = inner, B, src_bands, n_bands
+                d.src_type, d.out_int64 = self._SRC_TYPE[x.dtype], 1 if is_class else 0
+                nd = NO_DATA_VAL[m]
+                d.has_nodata, d.nodata = (1, float(nd)) if nd == nd else (0, 0.0)
+                d.normalize = 1 if m in self._stats else 0
+                if n_bands <= nat.RAW_MAX_BANDS:
+                    for b in range(n_bands):
+                        d.band[b] = b if whole else idx[b]
+                    if m in self._stats:
+                        st = self._stats_host[m]                           # [2 (l1c / l2a), 2 (mean / std), nb] float64, host
+                        for s_ in range(2):
+                            for b in range(n_bands):
+                                d.mean[s_][b], d.std[s_][b] = float(st[s_, 0, b]), float(st[s_, 1, b])
+                nat.check(nat.lib.mpmae_raw_transform(C.byref(d), C.c_void_p(stream)), "mpmae_raw_transform")
+                out[m] = o
+        return out
+
+    def __call__(self, raw: Dict[str, torch.Tensor], l2a: torch.Tensor,
+                 into: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """``into`` (device path only): write the model-ready tensors into these buffers, e.g. the static inputs of a
+        ``GraphedStep``, instead of allocating new ones."""
+        if self.exact and all(v.is_cuda for v in raw.values()):
+            return self._native(raw, l2a, into)
+        if into is not None:
+            raise ValueError("`into` needs CUDA inputs and exact=True (the fused device kernel)")
         out = {}
         for m in self.modalities:
             x = raw[m]

@@ -63,3 +63,45 @@ def synthetic_batch(B: int, img_size: int, out_modalities: Optional[List[str]] =
                 t[torch.rand(t.shape, generator=g) < nan_frac / 2] = float("nan")
             d[m] = t
     return d
+
+
+# ------------------------------------------------------------------------------------------------ stored-dtype batches
+#: Sentinel-2 band names as stored (MODALITIES.py: MODALITIES_FULL): 13 bands, of which pretraining reads the 12 in S2_BANDS
+S2_FULL = ["B1", "B2", "B3", "B4", "B5", "B6", "B7", "B8A", "B8", "B9", "B10", "B11", "B12"]
+
+
+def raw_modalities_full() -> Dict[str, List[str]]:
+    full = {m: [f"{m}_{i}" for i in range(n)] for m, n in FULL_BANDS.items()}
+    full["sentinel2"] = list(S2_FULL)
+    return full
+
+
+def synthetic_band_stats() -> Dict[str, dict]:
+    """Per-band mean / std in the layout of the reference's ``band_stats`` json (``mmearth_dataset.py:36-50``), matched to
+    the distributions of :func:`synthetic_raw_batch` so that the z-scored bands come out ~N(0, 1) like real data."""
+    spec = {"sentinel2_l1c": (13, 6000.0, 3464.0), "sentinel2_l2a": (13, 5900.0, 3400.0), "sentinel1": (8, -3.0, 7.0),
+            "aster": (2, -3.0, 7.0), "canopy_height_eth": (2, 29.5, 17.3), "lat": (2, 0.0, 0.577), "lon": (2, 0.0, 0.577),
+            "month": (2, 0.0, 0.577), "era5": (12, 280.0, 30.0)}
+    return {k: {"mean": [m + 0.01 * i for i in range(n)], "std": [sd * (1.0 + 0.01 * i) for i in range(n)]}
+            for k, (n, m, sd) in spec.items()}
+
+
+def synthetic_raw_batch(B: int, img_size: int, seed: int = 1234) -> Dict[str, torch.Tensor]:
+    """One host batch AS STORED in the MMEarth HDF5 files (``mmearth_dataset.py:58-153`` reads these and widens them):
+    16-bit Sentinel-2 digital numbers (13 bands, 0 = no data), float32 Sentinel-1 / ASTER / ERA5 / lat / lon / month, one byte per
+    pixel for canopy height and the two label maps, one-hot uint8 / uint16 rows for biome / eco-region.  56.7 MB for 256 samples
+    of 56 x 56 against 91.7 MB for the widened float32 / int64 tensors the reference loader hands to the training loop."""
+    g = torch.Generator().manual_seed(seed)
+    S = img_size
+    d = {"sentinel2": torch.randint(1, 12000, (B, 13, S, S), generator=g, dtype=torch.int32).to(torch.uint16),
+         "sentinel1": torch.randn(B, 8, S, S, generator=g) * 7 - 3,
+         "aster": torch.randn(B, 2, S, S, generator=g) * 7 - 3,
+         "canopy_height_eth": torch.randint(0, 60, (B, 2, S, S), generator=g, dtype=torch.int32).to(torch.uint8),
+         "dynamic_world": torch.randint(0, 10, (B, 1, S, S), generator=g, dtype=torch.int32).to(torch.uint8),
+         "esa_worldcover": (torch.randint(0, 10, (B, 1, S, S), generator=g, dtype=torch.int32) * 10).to(torch.uint8),
+         "era5": torch.randn(B, 12, generator=g) * 30 + 280}
+    for m in ("lat", "lon", "month"):
+        d[m] = torch.rand(B, 2, generator=g) * 2 - 1
+    d["biome"] = F.one_hot(torch.randint(0, 14, (B,), generator=g), 14).to(torch.uint8)
+    d["eco_region"] = F.one_hot(torch.randint(0, 846, (B,), generator=g), 846).to(torch.int32).to(torch.uint16)
+    return d
