@@ -206,6 +206,17 @@ int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, floa
                          const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
                          float weight_decay, const float *dev_state, void *cuda_stream);
 
+/* Step-wise backward for the reference's step-wise surface (models/fcmae.py:242-412: forward_encoder -> forward_decoder ->
+ * forward_loss, each autograd-connected there).  The activations of the matching forward stages must be in the workspace.
+ *   MPMAE_BWD_LOSS     io->losses, io->grad_out (d total)  ->  dpred_pixel [B*L, npix], dpred_image [B, nimg] (OUT: gradient of
+ *                      the total loss wrt the predictions); d log_vars accumulates into io->grads
+ *   MPMAE_BWD_DECODER  dpred_pixel, dpred_image (IN)  ->  head / decoder / proj / mask-token gradients accumulate into io->grads,
+ *                      d_x3 [B*V, dims[3]] (OUT: gradient wrt the encoder output rows, visible cells in ascending patch order)
+ *   MPMAE_BWD_ENCODER  d_x3 (IN)  ->  encoder gradients accumulate into io->grads */
+enum { MPMAE_BWD_LOSS = 0, MPMAE_BWD_DECODER = 1, MPMAE_BWD_ENCODER = 2 };
+int mpmae_backward_step(mpmae_plan *plan, const mpmae_io *io, int32_t which, float *dpred_pixel, float *dpred_image,
+                        float *d_x3, void *cuda_stream);
+
 /* The loader's per-sample transform (mmearth_dataset.py:58-153) for a whole batch of arrays in their STORED dtypes, on the
  * device, bit-identical to MMEarthDataset.__getitem__ (float64 arithmetic, one rounding to float32):
  *   v = src[n, band[b], j]  ->  lut[v] (label maps; NaN = ignore)  |  NaN where v == nodata

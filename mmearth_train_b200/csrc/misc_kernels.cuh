@@ -523,6 +523,17 @@ __global__ void unfold_batch_kernel(const UnfoldArgs *__restrict__ jobs, const i
   unfold_column(job, local);
 }
 
+// out[r, c] = x[r, c] * cs[c] (the per-column loss seeds applied to the raw prediction gradient); fill: v everywhere
+__global__ void scale_cols_kernel(const float *__restrict__ x, const float *__restrict__ cs, float *__restrict__ out, int64_t R,
+                                  int C) { pdl_prologue();
+  const int64_t n = R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = x[i] * cs[i % C];
+}
+__global__ void fill_kernel(float *__restrict__ x, float v, int64_t n) { pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Decoder entry (models/fcmae.py:251-255): dense cell rows from projected visible rows + mask token.
 //   xd[n*L + l, :] = slot>=0 ? z[n*V+slot, :] : token

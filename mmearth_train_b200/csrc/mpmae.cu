@@ -1219,8 +1219,12 @@ int mpmae_forward_stages(mpmae_plan *pl, const mpmae_io *io, int32_t stages, voi
 
 // -------------------------------------------------------------------------------------------------
 // parts: bit 0 = seeds + heads + decoder + proj ; bit 1 = stages 3, 2 ; bit 2 = stages 1, 0 + patch embedding
-static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, int parts) {
-  int rc = check_io(pl, io, true);
+// ext: step-wise backward (mpmae_backward_step).  which = 1: the decoder part starts from GIVEN prediction gradients
+// (dpred_pixel / dpred_image, unit loss seeds) and hands the encoder-output gradient rows out through d_x3; which = 2: the
+// encoder parts start from d_x3.
+struct StepBwd { int which; const float *dpred_pixel, *dpred_image; float *d_x3; };
+static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, int parts, const StepBwd *ext = nullptr) {
+  int rc = check_io(pl, io, true, ext ? (ext->which == 2 ? ST_ENC : 0) : ST_ALL);
   if (rc) return rc;
   claim_workspace(pl, io->workspace);
   Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
@@ -1237,7 +1241,7 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
   if (parts & 1) {
   cur = g0; nxt = g1;
   c.zero(c.w(pl->o_bzero_begin), pl->o_bzero_end - pl->o_bzero_begin, "zero_bwd");
-  {  // seeds: d total / d L_i / denominator_i per prediction column ; d total / d log_vars
+  if (!ext) {  // seeds: d total / d L_i / denominator_i per prediction column ; d total / d log_vars
     SeedArgs s{};
     s.acc = c.w(pl->o_acc); s.log_vars = pl->logv >= 0 ? c.p(pl->logv) : nullptr; s.losses = io->losses;
     s.grad_out = io->grad_out; s.d_log_vars = pl->logv >= 0 ? c.g(pl->logv) : nullptr;
@@ -1246,6 +1250,17 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     for (int m = 0; m < cf.n_mod; ++m) { s.col_off[m] = pl->col_off[m]; s.col_len[m] = pl->col_len[m]; s.is_img[m] = pl->is_img[m]; }
     pdl(loss_seed_kernel, cf.n_mod, 256, 0, c.st)(s);
     c.post("loss_seed");
+  } else {     // given prediction gradients: unit seeds
+    if (pl->npix > 0) {
+      pdl(fill_kernel, 8, 256, 0, c.st)(c.w(pl->o_cs_pix), 1.f, (int64_t)pl->npix);
+      c.post("fill");
+      c.check(cudaMemcpyAsync(c.w(pl->o_dpix), ext->dpred_pixel, (size_t)pl->cells * pl->npix * 4, cudaMemcpyDeviceToDevice, c.st), "memcpy", false);
+    }
+    if (pl->nimg > 0) {
+      pdl(fill_kernel, 8, 256, 0, c.st)(c.w(pl->o_cs_img), 1.f, (int64_t)pl->nimg);
+      c.post("fill");
+      c.check(cudaMemcpyAsync(c.w(pl->o_dimg), ext->dpred_image, (size_t)geo.B * pl->nimg * 4, cudaMemcpyDeviceToDevice, c.st), "memcpy", false);
+    }
   }
   const float *dec_out = c.w(pl->dw[cf.dec_depth - 1].y);
   float *dd = g0;  // gradient at the decoder output [cells, D]
@@ -1299,8 +1314,15 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     g.A = dz; use_slot(c, g, pl->proj_slot, true); g.out = nxt; g.M = BV; g.N = dm[3]; g.K = D; g.group_rows = 0x7fffffff;
     gemm<EPI_STORE>(c, g, "d_x3");
     std::swap(cur, nxt);
+    if (ext && ext->d_x3)
+      c.check(cudaMemcpyAsync(ext->d_x3, cur, (size_t)BV * dm[3] * 4, cudaMemcpyDeviceToDevice, c.st), "memcpy", false);
   }
   }  // part 0
+  if (ext && ext->which == 2) {   // the encoder parts start from the given gradient of the encoder output rows
+    cur = g0; nxt = g1;
+    c.zero(c.w(pl->o_bzero_begin), pl->o_bzero_end - pl->o_bzero_begin, "zero_bwd");
+    c.check(cudaMemcpyAsync(cur, ext->d_x3, (size_t)BV * dm[3] * 4, cudaMemcpyDeviceToDevice, c.st), "memcpy", false);
+  }
   for (int i = 3; i >= 0; --i) {
     if (!(parts & (i >= 2 ? 2 : 4))) continue;
     for (int j = cf.depths[i] - 1; j >= 0; --j) {
@@ -1384,6 +1406,47 @@ int mpmae_backward(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream) { retu
 int mpmae_backward_part(mpmae_plan *pl, const mpmae_io *io, int32_t part, void *cuda_stream) {
   if (part < 0 || part > 2) return fail(MPMAE_ERR_INVALID, "backward part %d", part);
   return backward_impl(pl, io, cuda_stream, 1 << part);
+}
+
+int mpmae_backward_step(mpmae_plan *pl, const mpmae_io *io, int32_t which, float *dpred_pixel, float *dpred_image, float *d_x3,
+                        void *cuda_stream) {
+  if (!pl || !io) return fail(MPMAE_ERR_INVALID, "null plan/io");
+  if (which == MPMAE_BWD_LOSS) {
+    if (!io->workspace || !io->params || !io->grads || !io->losses) return fail(MPMAE_ERR_INVALID, "backward_step(loss): null pointer in mpmae_io");
+    if ((pl->npix > 0 && !dpred_pixel) || (pl->nimg > 0 && !dpred_image)) return fail(MPMAE_ERR_INVALID, "backward_step(loss): null output");
+    claim_workspace(pl, io->workspace);
+    Ctx c{pl, io, static_cast<cudaStream_t>(cuda_stream), static_cast<float *>(io->workspace), io->params, io->grads};
+    const mpmae_cfg &cf = pl->cfg;
+    SeedArgs s{};
+    s.acc = c.w(pl->o_acc); s.log_vars = pl->logv >= 0 ? c.p(pl->logv) : nullptr; s.losses = io->losses;
+    s.grad_out = io->grad_out; s.d_log_vars = pl->logv >= 0 ? c.g(pl->logv) : nullptr;
+    s.colscale_pix = c.w(pl->o_cs_pix); s.colscale_img = c.w(pl->o_cs_img);
+    s.n_mod = cf.n_mod; s.uncertainty = cf.loss_aggr;
+    for (int m = 0; m < cf.n_mod; ++m) { s.col_off[m] = pl->col_off[m]; s.col_len[m] = pl->col_len[m]; s.is_img[m] = pl->is_img[m]; }
+    pdl(loss_seed_kernel, cf.n_mod, 256, 0, c.st)(s);
+    c.post("loss_seed");
+    if (pl->npix > 0 && c.ok()) {
+      pdl(scale_cols_kernel, ew_grid(pl->cells * pl->npix / 4), 256, 0, c.st)(c.w(pl->o_dpix), c.w(pl->o_cs_pix), dpred_pixel, pl->cells, pl->npix);
+      c.post("scale_cols");
+    }
+    if (pl->nimg > 0 && c.ok()) {
+      pdl(scale_cols_kernel, ew_grid((int64_t)pl->geo.B * pl->nimg / 4 + 1), 256, 0, c.st)(c.w(pl->o_dimg), c.w(pl->o_cs_img), dpred_image, pl->geo.B, pl->nimg);
+      c.post("scale_cols");
+    }
+    int n = 0;
+    return finish(c, &n);
+  }
+  if (which == MPMAE_BWD_DECODER) {
+    if ((pl->npix > 0 && !dpred_pixel) || (pl->nimg > 0 && !dpred_image) || !d_x3) return fail(MPMAE_ERR_INVALID, "backward_step(decoder): null pointer");
+    StepBwd e{1, dpred_pixel, dpred_image, d_x3};
+    return backward_impl(pl, io, cuda_stream, 1, &e);
+  }
+  if (which == MPMAE_BWD_ENCODER) {
+    if (!d_x3) return fail(MPMAE_ERR_INVALID, "backward_step(encoder): d_x3 is null");
+    StepBwd e{2, nullptr, nullptr, d_x3};
+    return backward_impl(pl, io, cuda_stream, 6, &e);
+  }
+  return fail(MPMAE_ERR_INVALID, "backward_step: which = %d", which);
 }
 
 // [lo, hi) of the flat gradient buffer that is final once backward part `part` has run (reverse layer order)

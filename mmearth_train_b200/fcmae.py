@@ -87,6 +87,74 @@ class _StepFunction(torch.autograd.Function):
         return (None, None, grad_total.new_zeros(1)) + (None,) * len(ctx.model._param_list)
 
 
+class _EncoderFunction(torch.autograd.Function):
+    """``forward_encoder`` with autograd (``models/fcmae.py:242-247``): features = f(parameters)."""
+
+    @staticmethod
+    def forward(ctx, model, run, token, *params):
+        ctx.model, ctx.run = model, run
+        model._native_forward_encoder(run)
+        feats = model.encoder_features(run)
+        ctx.mark_non_differentiable(run["mask"])
+        return feats, run["mask"]
+
+    @staticmethod
+    def backward(ctx, dfeats, _dmask):
+        model, run = ctx.model, ctx.run
+        B, C3 = dfeats.shape[0], dfeats.shape[1]
+        rows = dfeats.float().permute(0, 2, 3, 1).reshape(B * model.num_patches, C3)[run["mask"].reshape(-1) == 0].contiguous()
+        model._stepwise_backward(run, nat.BWD_ENCODER, d_x3=rows)
+        return (None, None, dfeats.new_zeros(1)) + (None,) * len(model._param_list)
+
+
+class _DecoderFunction(torch.autograd.Function):
+    """``forward_decoder`` with autograd (``models/fcmae.py:249-265``): predictions = f(encoder features, parameters)."""
+
+    @staticmethod
+    def forward(ctx, model, run, x, token, *params):
+        ctx.model, ctx.run = model, run
+        B, C3 = x.shape[0], x.shape[1]
+        rows = x.detach().float().permute(0, 2, 3, 1).reshape(B * model.num_patches, C3)[run["mask"].reshape(-1) == 0]
+        model.tap(f"stage3.block{model.depths[3] - 1}.y", run).copy_(rows)      # [B*V, C3], ascending patch index
+        model._stages(run, nat.STAGE_MASK | nat.STAGE_DECODER)
+        return run["pred_pixel"], run["pred_image"]
+
+    @staticmethod
+    def backward(ctx, dpix, dimg):
+        model, run = ctx.model, ctx.run
+        B, L, C3 = run["B"], model.num_patches, model.dims[3]
+        dpix = torch.zeros_like(run["pred_pixel"]) if dpix is None else dpix.float().contiguous()
+        dimg = torch.zeros_like(run["pred_image"]) if dimg is None else dimg.float().contiguous()
+        vis = run["mask"].reshape(-1) == 0
+        d_x3 = torch.empty(int(vis.sum()), C3, device=dpix.device)
+        model._stepwise_backward(run, nat.BWD_DECODER, dpred_pixel=dpix, dpred_image=dimg, d_x3=d_x3)
+        dx = torch.zeros(B * L, C3, device=dpix.device)
+        dx[vis] = d_x3
+        G = model.img_size // model.patch_size
+        return (None, None, dx.view(B, G, G, C3).permute(0, 3, 1, 2), dpix.new_zeros(1)) + (None,) * len(model._param_list)
+
+
+class _LossFunction(torch.autograd.Function):
+    """``forward_loss`` with autograd (``models/fcmae.py:267-412``): total loss = f(predictions, log_vars)."""
+
+    @staticmethod
+    def forward(ctx, model, run, token, *preds):
+        ctx.model, ctx.run = model, run
+        model._pack_preds(run, preds)
+        model._stages(run, nat.STAGE_MASK | nat.STAGE_LOSS)
+        losses = run["losses"]
+        ctx.mark_non_differentiable(losses)
+        return losses[2 * run["T"]].clone(), losses
+
+    @staticmethod
+    def backward(ctx, grad_total, _grad_losses):
+        model, run = ctx.model, ctx.run
+        dpp, dpi = torch.empty_like(run["pred_pixel"]), torch.empty_like(run["pred_image"])
+        model._stepwise_backward(run, nat.BWD_LOSS, dpred_pixel=dpp, dpred_image=dpi, grad_out=grad_total)
+        grads = model._pred_dict({"plan": run["plan"], "B": run["B"], "pred_pixel": dpp, "pred_image": dpi})
+        return (None, None, grad_total.new_zeros(1)) + tuple(grads[m] for m in model.out_modalities)
+
+
 class FCMAE(nn.Module):
     """Fully convolutional multi-pretext masked autoencoder, native B200 step (``models/fcmae.py:27``)."""
 
@@ -440,6 +508,55 @@ class FCMAE(nn.Module):
             self._gacc.add_(self._gstep)
         self._bind_grads()
 
+    def _native_forward_encoder(self, run: dict) -> None:
+        io = self._io(run)
+        stream = torch.cuda.current_stream(run["dev"]).cuda_stream
+        with torch.cuda.device(run["dev"]):
+            nat.check(nat.lib.mpmae_forward_encoder(run["plan"].handle, C.byref(io), C.c_void_p(stream)), "mpmae_forward_encoder")
+
+    def _stepwise_backward(self, run: dict, which: int, dpred_pixel=None, dpred_image=None, d_x3=None, grad_out=None) -> None:
+        """One of the three step-wise backward calls (``mpmae_backward_step``).  Each accumulates its parameter gradients
+        into a scratch flat buffer that is then added to (first call after ``zero_grad``: copied into) the flat gradient
+        buffer, all-reduced first under ``torch.distributed`` (mean over ranks, DDP semantics)."""
+        dev = run["dev"]
+        if self._gstep is None or self._gstep.device != dev:
+            self._gstep = torch.empty(self._n_flat, device=dev)
+        tmp = self._gstep
+        tmp.zero_()
+        go = grad_out.detach().reshape(1).float().contiguous() if grad_out is not None else None
+        io = self._io(run, grads=tmp, grad_out=go)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.mpmae_backward_step(run["plan"].handle, C.byref(io), which, ptr(dpred_pixel), ptr(dpred_image),
+                                                  ptr(d_x3), C.c_void_p(stream)), "mpmae_backward_step")
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and self.reduce_gradients:
+            dist.all_reduce(tmp)
+            tmp /= dist.get_world_size()
+        fresh = self._grad_views_fresh()
+        if self._gacc is None or self._gacc.device != dev:
+            self._gacc = torch.zeros(self._n_flat, device=dev)
+            fresh = True
+        if fresh:
+            self._gacc.copy_(tmp)
+        else:
+            self._gacc.add_(tmp)
+        self._bind_grads()
+
+    def _pack_preds(self, run: dict, preds) -> None:
+        """Per-modality prediction tensors (``out_modalities`` order) into the packed buffers the loss kernels read."""
+        plan, B = run["plan"], run["B"]
+        G = self.img_size // self.patch_size
+        pix = run["pred_pixel"].view(B, G, G, -1)
+        for i, (m, t) in enumerate(zip(self.out_modalities, preds)):
+            off = plan.col_offset(i)
+            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL):
+                n = self.patch_size ** 2 * self.out_chans[m]
+                pix[..., off:off + n].copy_(t.detach().permute(0, 2, 3, 1))
+            else:
+                run["pred_image"][:, off:off + self.out_chans[m]].copy_(t.detach())
+
     def _random_crop(self, imgs_dict):
         """Same random window per sample for all pixel-wise modalities (``models/fcmae.py:419-434``)."""
         S = self.img_size
@@ -480,18 +597,18 @@ class FCMAE(nn.Module):
         x = imgs.reshape(imgs.shape[0], channels, h, p, w, p)
         return torch.einsum("nchpwq->nhwpqc", x).reshape(imgs.shape[0], h * w, p * p * channels)
 
-    @torch.no_grad()
     def forward_encoder(self, imgs: torch.Tensor, mask_ratio: float) -> Tuple[torch.Tensor, torch.Tensor]:
-        """``models/fcmae.py:242-247``: (dense features [B, C3, G, G] with zeros at masked cells, mask)."""
+        """``models/fcmae.py:242-247``: (dense features [B, C3, G, G] with zeros at masked cells, mask).  Autograd-connected
+        like the reference's when gradients are enabled: ``forward_encoder -> forward_decoder -> forward_loss`` composes into
+        the same training step as ``forward`` (which stays the fast path: one native call each way)."""
         if abs(mask_ratio - self.mask_ratio) > 1e-7:
             self.mask_ratio = mask_ratio
         run = self._prepare({"sentinel2": imgs}, with_targets=False, with_preds=False)
-        io = self._io(run)
-        stream = torch.cuda.current_stream(run["dev"]).cuda_stream
-        with torch.cuda.device(run["dev"]):
-            nat.check(nat.lib.mpmae_forward_encoder(run["plan"].handle, C.byref(io), C.c_void_p(stream)),
-                      "mpmae_forward_encoder")
         self.last_run = run
+        if torch.is_grad_enabled():
+            feats, mask = _EncoderFunction.apply(self, run, self._ddp_token, *self._param_list)
+            return feats, mask
+        self._native_forward_encoder(run)
         return self.encoder_features(run), run["mask"]
 
     def _stages(self, run: dict, stages: int) -> None:
@@ -521,25 +638,28 @@ class FCMAE(nn.Module):
                 pred[m] = run["pred_image"][:, off:off + self.out_chans[m]]
         return pred
 
-    @torch.no_grad()
     def forward_decoder(self, x: torch.Tensor, mask: torch.Tensor) -> Dict[str, torch.Tensor]:
         """``models/fcmae.py:249-265``: dense encoder features ``[B, C3, G, G]`` + mask -> predictions of every output
         modality.  Only the visible cells of ``x`` are read (the reference overwrites the masked ones with the mask
-        token).  Step-wise inference call (no autograd); training goes through ``forward``."""
+        token).  Autograd-connected (gradients flow to ``x`` and to the decoder / head parameters) when gradients are enabled."""
         self._device_check(x)
         self._check_mask(mask)
         run = self._prepare(None, with_targets=False, mask=mask)
+        run["mask"] = mask.detach().to(run["dev"]).float().clone()         # the mask kernel reproduces it; needed before that
+        self.last_run = run
+        if torch.is_grad_enabled():
+            pp, pi = _DecoderFunction.apply(self, run, x, self._ddp_token, *self._param_list)
+            return self._pred_dict({"plan": run["plan"], "B": run["B"], "pred_pixel": pp, "pred_image": pi})
         B, C3 = x.shape[0], x.shape[1]
         rows = x.float().permute(0, 2, 3, 1).reshape(B * self.num_patches, C3)[mask.reshape(-1) == 0]
         self.tap(f"stage3.block{self.depths[3] - 1}.y", run).copy_(rows)      # [B*V, C3], ascending patch index
         self._stages(run, nat.STAGE_MASK | nat.STAGE_DECODER)
-        self.last_run = run
         return self._pred_dict(run)
 
-    @torch.no_grad()
     def forward_loss(self, imgs_dict: Dict[str, torch.Tensor], preds: Dict[str, torch.Tensor], mask: torch.Tensor):
         """``models/fcmae.py:267-412``: per-modality reconstruction losses of given predictions + their aggregate;
-        returns ``(loss, loss_dict, log_vars, normalized_loss_list)``.  Step-wise inference call (no autograd)."""
+        returns ``(loss, loss_dict, log_vars, normalized_loss_list)``.  Autograd-connected (gradients flow to ``preds`` and to
+        ``loss_fn.log_vars``) when gradients are enabled."""
         self._device_check(mask)
         self._check_mask(mask)
         for m in self.out_modalities:
@@ -549,18 +669,17 @@ class FCMAE(nn.Module):
                                  f"{self.img_size} (models/fcmae.py:419-434 crops in forward, before the loss)")
         run = self._prepare(None, with_targets=False, mask=mask)
         run["targets"] = self._targets(imgs_dict)
-        plan, B, T = run["plan"], run["B"], run["T"]
-        G = self.img_size // self.patch_size
-        pix = run["pred_pixel"].view(B, G, G, -1)
-        for i, m in enumerate(self.out_modalities):
-            off = plan.col_offset(i)
-            if modality_kind(m) in (nat.PIXEL_CONTINUOUS, nat.PIXEL_CATEGORICAL):
-                n = self.patch_size ** 2 * self.out_chans[m]
-                pix[..., off:off + n].copy_(preds[m].permute(0, 2, 3, 1))
-            else:
-                run["pred_image"][:, off:off + self.out_chans[m]].copy_(preds[m])
-        self._stages(run, nat.STAGE_MASK | nat.STAGE_LOSS)
+        T = run["T"]
         self.last_run = run
+        plist = [preds[m] for m in self.out_modalities]
+        if torch.is_grad_enabled():
+            total, losses = _LossFunction.apply(self, run, self._ddp_token, *plist)
+            loss_dict = {m: losses[i] for i, m in enumerate(self.out_modalities)}
+            if self.loss_aggr == "uncertainty":
+                return total, loss_dict, _LazyList(self.loss_fn.log_vars), losses[T:2 * T]
+            return total, loss_dict, None, None
+        self._pack_preds(run, plist)
+        self._stages(run, nat.STAGE_MASK | nat.STAGE_LOSS)
         losses = run["losses"]
         loss_dict = {m: losses[i] for i, m in enumerate(self.out_modalities)}
         if self.loss_aggr == "uncertainty":
