@@ -206,6 +206,25 @@ int mpmae_adamw_step_dev(float *params, const float *grads, float *exp_avg, floa
                          const uint8_t *decay_mask, int64_t n, float lr, float beta1, float beta2, float eps,
                          float weight_decay, const float *dev_state, void *cuda_stream);
 
+/* Dense operators for the reference's dense ConvNeXt-V2 (models/convnextv2.py:59-207, the finetuning / linear-probe network;
+ * inference forward).  Activations are channels-last rows [B*H*W, C]; the pointwise / strided convolutions are
+ * mpmae_gemm_epi products on these rows.
+ *   dense_im2col: out[r, ci*k*k + kh*k + kw] = x[n, ci, oy*s+kh, ox*s+kw], r = (n*Ho+oy)*Wo+ox, columns >= C*k*k zero
+ *                 (kpad % 8 == 0; torch weight.reshape(Cout, -1) column order); nchw != 0: x is [B, C, H, W], else [B, H, W, C]
+ *   ln_rows:      out = LayerNorm_C(x) (* w + b when w is given), then GELU when gelu != 0
+ *   dense_dwconv: depthwise k x k, stride s, zero padding p, torch weight [C, 1, k, k], on [B, H, W, C]; ln != 0: LayerNorm
+ *                 (no affine) over the channels of every output pixel
+ *   grn_apply:    per-sample GRN (models/norm_layers.py:33-44, eps 1e-4) of h [R, D] given gsq[g, d] = sum_rows h^2 of every
+ *                 group of group_rows rows: out = gamma * (h * Nx) + beta + h;  scratch: (2*groups*D + groups) floats */
+int mpmae_dense_im2col(const float *x, float *out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s,
+                       int32_t kpad, int32_t nchw, void *cuda_stream);
+int mpmae_ln_rows(const float *x, const float *w, const float *b, float *out, int64_t R, int32_t C, float eps, int32_t gelu,
+                  void *cuda_stream);
+int mpmae_dense_dwconv(const float *x, const float *w, const float *bias, float *out, int32_t B, int32_t H, int32_t W, int32_t C,
+                       int32_t k, int32_t s, int32_t p, int32_t ln, float eps, void *cuda_stream);
+int mpmae_grn_apply(const float *h, const float *gsq, const float *gamma, const float *beta, float *out, int64_t R, int32_t D,
+                    int32_t group_rows, float eps, float *scratch, void *cuda_stream);
+
 /* Step-wise backward for the reference's step-wise surface (models/fcmae.py:242-412: forward_encoder -> forward_decoder ->
  * forward_loss, each autograd-connected there).  The activations of the matching forward stages must be in the workspace.
  *   MPMAE_BWD_LOSS     io->losses, io->grad_out (d total)  ->  dpred_pixel [B*L, npix], dpred_image [B, nimg] (OUT: gradient of

@@ -5,7 +5,7 @@ Host-side mirror of the reference's ``models.fcmae`` surface over the C-ABI libr
 has not been built: there is no CPU or PyTorch fallback on the product path.
 """
 from . import _native                                                  # noqa: F401  (fails loudly without the .so)
-from . import checkpoint, data, dist, engine, graph, optim, synthetic                     # noqa: F401
+from . import checkpoint, convnextv2, data, dist, engine, graph, optim, synthetic         # noqa: F401
 from .fcmae import (FCMAE, UncertaintyWeightingStrategy, convnextv2_atto, convnextv2_base, convnextv2_femto,  # noqa: F401
                     convnextv2_huge, convnextv2_large, convnextv2_nano, convnextv2_pico, convnextv2_tiny)
 

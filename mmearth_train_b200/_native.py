@@ -99,6 +99,10 @@ def _load():
         "mpmae_gemm_wgrad": (C.c_int, [I32, P, P, P, I64, I32, I32, P]),
         "mpmae_gemm_wgrad_act": (C.c_int, [I32, P, P, P, I64, I32, I32, I32, P]),
         "mpmae_raw_transform": (C.c_int, [C.POINTER(RawDesc), P]),
+        "mpmae_dense_im2col": (C.c_int, [P, P, I32, I32, I32, I32, I32, I32, I32, I32, P]),
+        "mpmae_ln_rows": (C.c_int, [P, P, P, P, I64, I32, C.c_float, I32, P]),
+        "mpmae_dense_dwconv": (C.c_int, [P, P, P, P, I32, I32, I32, I32, I32, I32, I32, I32, C.c_float, P]),
+        "mpmae_grn_apply": (C.c_int, [P, P, P, P, P, I64, I32, I32, C.c_float, P, P]),
         "mpmae_backward_step": (C.c_int, [P, C.POINTER(IO), I32, P, P, P, P]),
         "mpmae_adamw_step": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, I64, F, P]),
         "mpmae_adamw_step_dev": (C.c_int, [P, P, P, P, P, I64, F, F, F, F, F, P, P]),
@@ -114,7 +118,7 @@ EXPORTS = ["mpmae_last_error", "mpmae_version", "mpmae_plan_create", "mpmae_plan
            "mpmae_param_count", "mpmae_param_info", "mpmae_param_decay", "mpmae_visible_patches",
            "mpmae_workspace_bytes", "mpmae_pred_pixel_cols", "mpmae_pred_image_cols", "mpmae_pred_col_offset",
            "mpmae_tap_info", "mpmae_tap_count", "mpmae_tap_name", "mpmae_launch_count", "mpmae_profile_begin", "mpmae_profile_report", "mpmae_forward",
-           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_backward_step", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_gemm_wgrad_act", "mpmae_raw_transform", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
+           "mpmae_forward_encoder", "mpmae_forward_stages", "mpmae_backward", "mpmae_backward_part", "mpmae_backward_part_range", "mpmae_backward_step", "mpmae_encoder_features", "mpmae_gemm_rows", "mpmae_gemm_epi", "mpmae_gemm_wgrad", "mpmae_gemm_wgrad_act", "mpmae_raw_transform", "mpmae_dense_im2col", "mpmae_ln_rows", "mpmae_dense_dwconv", "mpmae_grn_apply", "mpmae_adamw_step", "mpmae_adamw_step_dev"]
 
 
 def check(rc: int, what: str = "") -> None:

@@ -59,6 +59,29 @@ def to_dense_state_dict(ckpt: Dict[str, torch.Tensor]) -> "OrderedDict[str, torc
     return out
 
 
+def load_pretrained_encoder(dense_model, checkpoint: dict, linear_probe: bool = True) -> list:
+    """``hubconf.load_custom_checkpoint`` (``hubconf.py:20-75``): put the encoder of a PRETRAINING checkpoint into the dense
+    ``convnextv2.ConvNeXtV2``.  A ``head`` of another shape, the decoder, mask token, projection, prediction heads (and the
+    loss / pooled-head parameters that only exist in pretraining) are dropped, the rest goes through the sparse -> dense
+    remapping; with ``linear_probe=False`` the classifier is re-initialised like the reference does for finetuning.  Returns
+    the keys of the dense model the checkpoint did not provide (normally the final ``norm`` and the ``head``)."""
+    ck = dict(checkpoint["model"] if "model" in checkpoint else checkpoint)
+    own = dense_model.state_dict()
+    for k in ("head.weight", "head.bias"):
+        if k in ck and ck[k].shape != own[k].shape:
+            del ck[k]
+    for k in list(ck.keys()):
+        if any(s in k for s in ("decoder", "mask_token", "proj", "pred", "loss_fn", "layer_norm_tmp")):
+            del ck[k]
+    res = dense_model.load_state_dict(to_dense_state_dict(ck), strict=False)
+    if res.unexpected_keys:
+        raise KeyError(f"checkpoint keys the dense model does not have: {res.unexpected_keys[:5]}")
+    if not linear_probe:
+        torch.nn.init.trunc_normal_(dense_model.head.weight, std=2e-5)
+        torch.nn.init.constant_(dense_model.head.bias, 0.0)
+    return list(res.missing_keys)
+
+
 def save_checkpoint(path: str, model, optimizer=None, epoch: Optional[int] = None, extra: Optional[dict] = None) -> None:
     """``{"model": state_dict, "optimizer": ..., "epoch": ...}`` -- the layout ``helpers.save_model`` writes (``helpers.py:541-547``)."""
     blob = {"model": {k: v.detach().cpu() for k, v in model.state_dict().items()}}

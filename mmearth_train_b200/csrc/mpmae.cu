@@ -18,6 +18,7 @@
 
 #include "../../include/mpmae.h"
 #include "common.cuh"
+#include "dense_ops.cuh"
 #include "dwconv.cuh"
 #include "dwconv_tiled.cuh"
 #include "dwconv_pipe.cuh"
@@ -1589,6 +1590,49 @@ int mpmae_gemm_wgrad_act(int32_t backend, const float *x, const float *y, float 
   }
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "wgrad: %s", cudaGetErrorString(e));
   return MPMAE_OK;
+}
+
+int mpmae_dense_im2col(const float *x, float *out, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s, int32_t kpad,
+                       int32_t nchw, void *cuda_stream) {
+  if (!x || !out || B <= 0 || C <= 0 || k <= 0 || s <= 0 || H < k || W < k || kpad < C * k * k || kpad % 8 != 0)
+    return fail(MPMAE_ERR_INVALID, "dense_im2col args");
+  const int Ho = (H - k) / s + 1, Wo = (W - k) / s + 1;
+  pdl(dense_im2col_kernel, ew_grid((int64_t)B * Ho * Wo * kpad / 4), 256, 0, static_cast<cudaStream_t>(cuda_stream))(x, out, B, C, H, W, k, s,
+                                                                                                                Ho, Wo, kpad, nchw);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MPMAE_OK : fail(MPMAE_ERR_CUDA, "dense_im2col: %s", cudaGetErrorString(e));
+}
+
+int mpmae_ln_rows(const float *x, const float *w, const float *b, float *out, int64_t R, int32_t C, float eps, int32_t gelu,
+                  void *cuda_stream) {
+  if (!x || !out || R <= 0 || C <= 0 || (w && !b)) return fail(MPMAE_ERR_INVALID, "ln_rows args");
+  pdl(ln_affine_rows_kernel, ew_grid(R * 8), 256, 0, static_cast<cudaStream_t>(cuda_stream))(x, w, b, out, R, C, eps, gelu);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MPMAE_OK : fail(MPMAE_ERR_CUDA, "ln_rows: %s", cudaGetErrorString(e));
+}
+
+int mpmae_dense_dwconv(const float *x, const float *w, const float *bias, float *out, int32_t B, int32_t H, int32_t W, int32_t C,
+                       int32_t k, int32_t s, int32_t p, int32_t ln, float eps, void *cuda_stream) {
+  if (!x || !w || !out || B <= 0 || C <= 0 || C > 1024 || k <= 0 || s <= 0 || p < 0 || H + 2 * p < k || W + 2 * p < k)
+    return fail(MPMAE_ERR_INVALID, "dense_dwconv args (C <= 1024)");
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  pdl(dense_dwconv_kernel, ew_grid((int64_t)B * Ho * Wo * 8), 256, 0, static_cast<cudaStream_t>(cuda_stream))(x, w, bias, out, B, H, W, C, k,
+                                                                                                         s, p, Ho, Wo, ln, eps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MPMAE_OK : fail(MPMAE_ERR_CUDA, "dense_dwconv: %s", cudaGetErrorString(e));
+}
+
+int mpmae_grn_apply(const float *h, const float *gsq, const float *gamma, const float *beta, float *out, int64_t R, int32_t D,
+                    int32_t group_rows, float eps, float *scratch, void *cuda_stream) {
+  if (!h || !gsq || !gamma || !beta || !out || !scratch || R <= 0 || D <= 0 || D % 4 != 0 || group_rows <= 0 || R % group_rows != 0)
+    return fail(MPMAE_ERR_INVALID, "grn_apply args (D % 4 == 0, R a multiple of group_rows)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int groups = (int)(R / group_rows);
+  float *nx = scratch, *scale = scratch + (int64_t)groups * D, *denom = scale + (int64_t)groups * D;
+  pdl(grn_scale_kernel, groups, 256, 0, st)(gsq, gamma, nx, scale, denom, D, eps);
+  pdl(grn_apply_kernel, ew_grid(R * (D / 4)), 256, 0, st)(h, scale, beta, out, R, D, group_rows);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MPMAE_OK : fail(MPMAE_ERR_CUDA, "grn_apply: %s", cudaGetErrorString(e));
 }
 
 int mpmae_raw_transform(const mpmae_raw_desc *d, void *cuda_stream) {
