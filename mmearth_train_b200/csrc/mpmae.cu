@@ -491,12 +491,20 @@ void fold(Ctx &c, FoldArgs a, const char *what);
 int ew_grid(int64_t n4);
 bool splitter_backend(Ctx &c);
 
+// single_pass: with the 3xBF16 / 3xTF32 backends, run THIS product as one TF32 pass on the fp32 operands (no operand split):
+// the prediction heads, whose outputs feed only the losses (experiment knob MPMAE_HEADS_TF32, see profiles/)
 template <int MODE>
-void gemm(Ctx &c, const GemmArgs &a_in, const char *what) {
+void gemm(Ctx &c, const GemmArgs &a_in, const char *what, bool single_pass = false) {
   if (!c.ok() || a_in.M <= 0) return;
   GemmArgs a = a_in;
   mpmae_plan *pl = c.pl;
   const bool use_tc = pl->cfg.gemm_backend != 0 && tc_gemm_supported(MODE, a);
+  if (single_pass && use_tc && pl->cfg.gemm_backend != 2) {
+    a.Bw_lo = nullptr; a.b16 = 0;
+    c.acct(4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), 2.0 * (double)a.M * a.N * a.K);
+    c.check(launch_gemm_rows_tc<MODE>(a, 2, c.st), what);
+    return;
+  }
   if (pl->cfg.gemm_backend == 3) a.b16 = a.Bw_lo ? 1 : 0;
   if (pl->cfg.gemm_backend == 1 || pl->cfg.gemm_backend == 3) {
     // 3xTF32: the weight operand is consumed as a (hi, lo) pair; folded weights were written that way by fold(),
@@ -1174,7 +1182,8 @@ static int forward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, i
     GemmArgs g{};
     g.A = d; use_slot(c, g, pl->pix_slot, false); g.bias = c.p(pl->pixb); g.out = io->pred_pixel;
     g.M = pl->cells; g.N = pl->npix; g.K = D; g.group_rows = 0x7fffffff;
-    gemm<EPI_STORE>(c, g, "pixel_heads");
+    static const bool heads_tf32 = getenv("MPMAE_HEADS_TF32") != nullptr;
+    gemm<EPI_STORE>(c, g, "pixel_heads", heads_tf32);
   }
   if (pl->nimg > 0) {
     pdl(pool_ln_fwd_kernel, geo.B, 256, (size_t)8 * D * 4, c.st)(d, c.p(pl->lnt_w), c.p(pl->lnt_b), c.w(pl->o_pooled),
@@ -1271,7 +1280,8 @@ static int backward_impl(mpmae_plan *pl, const mpmae_io *io, void *cuda_stream, 
     fold_slot(c, f, pl->pix_slot, "fold_pixT");   // loss seeds (known only now) scale the rows of the head matrix
     GemmArgs g{};
     g.A = c.w(pl->o_dpix); use_slot(c, g, pl->pix_slot, true); g.out = dd; g.M = pl->cells; g.N = D; g.K = pl->npix; g.group_rows = 0x7fffffff;
-    gemm<EPI_STORE>(c, g, "d_dec_pix");
+    static const bool heads_tf32 = getenv("MPMAE_HEADS_TF32") != nullptr;
+    gemm<EPI_STORE>(c, g, "d_dec_pix", heads_tf32);
     WgradArgs w{};
     w.X = c.w(pl->o_dpix); w.Y = dec_out; w.rs = c.w(pl->o_cs_pix); w.dW = c.g(pl->pixw); w.db = c.g(pl->pixb);
     w.R = pl->cells; w.N = pl->npix; w.K = D;
