@@ -638,7 +638,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               r = make_float4(acc.x + bv.x + pv.x, acc.y + bv.y + pv.y, acc.z + bv.z + pv.z, acc.w + bv.w + pv.w);
             } else if (MODE == EPI_GELU_SQ) {
               r = make_float4(acc.x + bv.x, acc.y + bv.y, acc.z + bv.z, acc.w + bv.w);
-              r2 = (TC_DBG(p) & 2) ? r : make_float4(gelu_f(r.x), gelu_f(r.y), gelu_f(r.z), gelu_f(r.w));
+              r2 = (TC_DBG(p) & 2) ? r : gelu4_f(r);
               s1[j] = r2.x * r2.x; s1[j + 1] = r2.y * r2.y; s1[j + 2] = r2.z * r2.z; s1[j + 3] = r2.w * r2.w;
             } else if (MODE == EPI_DG) {
               r = acc;
@@ -647,12 +647,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else {  // EPI_DH_GELU
               const float4 kgv = *reinterpret_cast<const float4 *>(vec_kg + c0 + j);
               const float4 asv = *reinterpret_cast<const float4 *>(vec_as + c0 + j);
-              float hx, hy, hz, hw, dx_, dy_, dz_, dw_;
-              gelu_both_f(pv.x, hx, dx_); gelu_both_f(pv.y, hy, dy_); gelu_both_f(pv.z, hz, dz_); gelu_both_f(pv.w, hw, dw_);
-              r.x = fmaf(kgv.x, hx, acc.x * asv.x) * dx_;
-              r.y = fmaf(kgv.y, hy, acc.y * asv.y) * dy_;
-              r.z = fmaf(kgv.z, hz, acc.z * asv.z) * dz_;
-              r.w = fmaf(kgv.w, hw, acc.w * asv.w) * dw_;
+              float4 hh, dd;
+              gelu_both4_f(pv, hh, dd);
+              r.x = fmaf(kgv.x, hh.x, acc.x * asv.x) * dd.x;
+              r.y = fmaf(kgv.y, hh.y, acc.y * asv.y) * dd.y;
+              r.z = fmaf(kgv.z, hh.z, acc.z * asv.z) * dd.z;
+              r.w = fmaf(kgv.w, hh.w, acc.w * asv.w) * dd.w;
               s2[j] = r.x; s2[j + 1] = r.y; s2[j + 2] = r.z; s2[j + 3] = r.w;
             }
             o[q4] = r; o2[q4] = r2;
@@ -906,8 +906,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (AGELU) {   // A = saved pre-activation: h = gelu(a), times the GRN scale of its column
                 const int k = kb * 64 + h * 32 + cc[i] * 4;
                 const float4 sc = k < g.K ? *reinterpret_cast<const float4 *>(a_sc + k) : make_float4(1.f, 1.f, 1.f, 1.f);
-                x[i].x = gelu_f(x[i].x) * sc.x; x[i].y = gelu_f(x[i].y) * sc.y;
-                x[i].z = gelu_f(x[i].z) * sc.z; x[i].w = gelu_f(x[i].w) * sc.w;
+                const float4 hv = gelu4_f(x[i]);
+                x[i] = make_float4(hv.x * sc.x, hv.y * sc.y, hv.z * sc.z, hv.w * sc.w);
               }
             }
             asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
@@ -930,7 +930,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (AGELU) {
             const int idx = i * kSplitThreads + stid, r = idx >> 3, k = kb * BK + (((idx & 7) ^ (r & 7)) << 2);
             const float4 sc = k < g.K ? *reinterpret_cast<const float4 *>(a_sc + k) : make_float4(1.f, 1.f, 1.f, 1.f);
-            x.x = gelu_f(x.x) * sc.x; x.y = gelu_f(x.y) * sc.y; x.z = gelu_f(x.z) * sc.z; x.w = gelu_f(x.w) * sc.w;
+            const float4 hv = gelu4_f(x);
+            x = make_float4(hv.x * sc.x, hv.y * sc.y, hv.z * sc.z, hv.w * sc.w);
           }
           float4 hi, lo;
           hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); lo.x = x.x - hi.x;
@@ -1215,7 +1216,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
     auto split_region = [&](float4 *src, float4 *lo, int n4, bool act) {
       for (int i = stid; i < n4; i += kTnSplitThreads) {
         float4 x = src[i];
-        if (act) { x.x = gelu_f(x.x); x.y = gelu_f(x.y); x.z = gelu_f(x.z); x.w = gelu_f(x.w); }
+        if (act) x = gelu4_f(x);
         float4 hi, l;
         hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - hi.x;
         hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - hi.y;

@@ -269,8 +269,8 @@ __global__ void gelu_scale_rows_kernel(const float *__restrict__ a, const float 
     const int d = (int)(i % (D >> 2)) * 4;
     const float4 av = *reinterpret_cast<const float4 *>(a + i * 4);
     const float4 sv = scale ? *reinterpret_cast<const float4 *>(scale + d) : make_float4(1.f, 1.f, 1.f, 1.f);
-    *reinterpret_cast<float4 *>(out + i * 4) = make_float4(gelu_f(av.x) * sv.x, gelu_f(av.y) * sv.y, gelu_f(av.z) * sv.z,
-                                                            gelu_f(av.w) * sv.w);
+    const float4 hv = gelu4_f(av);
+    *reinterpret_cast<float4 *>(out + i * 4) = make_float4(hv.x * sv.x, hv.y * sv.y, hv.z * sv.z, hv.w * sv.w);
   }
 }
 

@@ -502,8 +502,7 @@ __global__ void __launch_bounds__(256) stem_bwd_vec_kernel(StemBwdArgs a) { pdl_
         if (j >= s2) break;
         const float4 cj = ch[u][j];
         float4 gj, dgj;
-        gelu_both_f(fmaf(cj.x, w0.x, b0.x), gj.x, dgj.x); gelu_both_f(fmaf(cj.y, w0.y, b0.y), gj.y, dgj.y);
-        gelu_both_f(fmaf(cj.z, w0.z, b0.z), gj.z, dgj.z); gelu_both_f(fmaf(cj.w, w0.w, b0.w), gj.w, dgj.w);
+        gelu_both4_f(make_float4(fmaf(cj.x, w0.x, b0.x), fmaf(cj.y, w0.y, b0.y), fmaf(cj.z, w0.z, b0.z), fmaf(cj.w, w0.w, b0.w)), gj, dgj);
         fma4(part[5 + j], ds, gj);                       // d_kernel[j]
         const float4 dt = make_float4(ds.x * kj[j].x * dgj.x, ds.y * kj[j].y * dgj.y, ds.z * kj[j].z * dgj.z, ds.w * kj[j].w * dgj.w);
         fma4(part[3], dt, cj);
