@@ -534,6 +534,162 @@ inline cudaError_t launch_s2_wgrad_pipe(const DwWgradArgs &p, const int *vis_pat
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ merged backward
+// dX and dW of the depthwise convolution from ONE read of the du halo window (round 2).
+//   dx[i]       = dy[i] + sum_k du[i + k - 3] * w[6 - k]                       (transposed stencil + residual)
+//   dW[6 - k]  += sum_{i in this patch} x[i] * du[i + k - 3]                     (every (input, output) pair belongs to the
+//   db         += sum_{i in this patch} du[i]                                    patch of its INPUT pixel: counted once)
+// Both sums walk the same window values: a thread loads a window row once and issues two FMAs per (value, output) pair.
+// Needs the du halo window (as the dX kernel), the patch's own x rows (one bulk copy: they are contiguous) and nothing else;
+// the separate weight-gradient kernel fetched an x halo window AND the du tile.
+struct DwBwdArgs {
+  DwArgs a;               // a.x = du (conv input), a.w = forward taps, a.flip = 1, a.resid = dy, a.out = dx, a.colsum_out
+  const float *xfwd;      // [R, C] forward input of the depthwise convolution
+  float *dw;              // parameter-layout gradient (same strides as a.w)
+  float *dbias;           // [C]
+  const int *vis_patch;
+};
+
+template <int P, int TR, int C>
+__global__ void __launch_bounds__(C *(P / TR)) dwconv_patch_bwd_pipe_kernel(DwBwdArgs t, int units) { pdl_prologue();
+  constexpr int W = P + 6, NPIX = W * W, NOUT = P * P;
+  const DwArgs &p = t.a;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  constexpr size_t kBuf = (size_t)(NPIX + NOUT) * C;   // [du window | x tile]
+  float *ubuf = smem + 2 * kBuf;                       // [P*P][C]
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar[0], blockDim.x + 1);
+    tc::mbar_init(&bar[1], blockDim.x + 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int pu, int b) {
+    float *buf = smem + (size_t)b * kBuf;
+    issue_window<P, C>(p.x, p.slot_of, t.vis_patch, p.geo, pu, buf, &bar[b]);
+    if (threadIdx.x == 0) {   // the patch's x rows are contiguous: one bulk copy
+      tc::mbar_expect_tx(&bar[b], NOUT * C * 4);
+      bulk_g2s(buf + (size_t)NPIX * C, t.xfwd + (int64_t)pu * NOUT * C, NOUT * C * 4, &bar[b]);
+    }
+  };
+  int pu = blockIdx.x;
+  if (pu < units) issue(pu, 0);
+  const int c = threadIdx.x % C, y0 = (threadIdx.x / C) * TR;
+  float wreg[49], dw[49];
+  float db = 0.f;
+#pragma unroll
+  for (int k = 0; k < 49; ++k) {
+    const int kh = k / 7, kw = k % 7;
+    wreg[k] = __ldg(p.w + (6 - kh) * p.w_skh + (6 - kw) * p.w_skw + c * p.w_sc);   // transposed stencil
+    dw[k] = 0.f;
+  }
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; pu < units; pu += gridDim.x, ++i) {
+    const int b = i & 1;
+    const float *win = smem + (size_t)b * kBuf;
+    const float *xt = win + (size_t)NPIX * C;
+    const int pn = pu + gridDim.x;
+    if (pn < units) issue(pn, b ^ 1);
+    tc::mbar_wait(&bar[b], (uint32_t)(i >> 1) & 1u);
+    {
+      float acc[TR][P], xv[TR][P];
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int ox = 0; ox < P; ++ox) { acc[r][ox] = 0.f; xv[r][ox] = xt[(size_t)zorder3(y0 + r, ox) * C + c]; }
+#pragma unroll
+      for (int iy = 0; iy < TR + 6; ++iy) {
+        float in[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) in[j] = win[(size_t)((y0 + iy) * W + j) * C + c];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) {
+          const int kh = iy - r;
+          if (kh >= 0 && kh < 7) {
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+              for (int ox = 0; ox < P; ++ox) {
+                acc[r][ox] = fmaf(in[ox + kw], wreg[kh * 7 + kw], acc[r][ox]);
+                dw[kh * 7 + kw] = fmaf(xv[r][ox], in[ox + kw], dw[kh * 7 + kw]);   // slot (kh, kw) holds dW[6 - kh][6 - kw]
+              }
+            if (kh == 3) {
+#pragma unroll
+              for (int ox = 0; ox < P; ++ox) db += in[ox + 3];                      // du at the patch's own pixels
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int ox = 0; ox < P; ++ox) ubuf[(size_t)zorder3(y0 + r, ox) * C + c] = acc[r][ox];
+    }
+    __syncthreads();   // buffer b is free again, ubuf is complete
+    const int64_t row0 = (int64_t)pu * (P * P);
+    constexpr int n4 = P * P * C / 4;
+    float4 *dst = reinterpret_cast<float4 *>(p.out + row0 * C);
+    const float4 *res = p.resid ? reinterpret_cast<const float4 *>(p.resid + row0 * C) : nullptr;
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) {   // blockDim.x % (C/4) == 0: a thread keeps its 4 columns
+      float4 v = reinterpret_cast<const float4 *>(ubuf)[k];
+      if (res) { const float4 r = __ldg(res + k); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+      dst[k] = v;
+      csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+    }
+    __syncthreads();   // ubuf is free again
+  }
+  // reductions: column sums of dx (one atomic per channel), then the strips of each channel's dW / db
+  float *red = smem;  // [50][C] (+ [C] for the column sums behind it)
+  for (int k = threadIdx.x; k < 51 * C; k += blockDim.x) red[k] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 49; ++k) atomicAdd(&red[k * C + c], dw[k]);
+  atomicAdd(&red[49 * C + c], db);
+  if (p.colsum_out) {
+    const int c4 = (threadIdx.x % (C / 4)) * 4;
+    atomicAdd(&red[50 * C + c4], csum.x); atomicAdd(&red[50 * C + c4 + 1], csum.y);
+    atomicAdd(&red[50 * C + c4 + 2], csum.z); atomicAdd(&red[50 * C + c4 + 3], csum.w);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 49 * C; k += blockDim.x) {
+    const int tap = k / C, cc = k - tap * C;
+    const int kh = 6 - tap / 7, kw = 6 - tap % 7;          // slot (a, b) accumulated dW[6 - a][6 - b]
+    atomicAdd(&t.dw[kh * p.w_skh + kw * p.w_skw + cc * p.w_sc], red[k]);
+  }
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    if (t.dbias) atomicAdd(&t.dbias[cc], red[49 * C + cc]);
+    if (p.colsum_out) atomicAdd(&p.colsum_out[cc], red[50 * C + cc]);
+  }
+}
+
+template <int P, int TR, int C>
+inline cudaError_t launch_patch_bwd_pipe(const DwBwdArgs &t, cudaStream_t st) {
+  constexpr int threads = C * (P / TR);
+  constexpr size_t sm = ((size_t)2 * ((P + 6) * (P + 6) + P * P) + P * P) * C * sizeof(float);
+  static_assert(threads % 32 == 0 && threads <= 1024 && threads >= 64 && threads % (C / 4) == 0, "thread mapping");
+  static_assert(sm >= (size_t)51 * C * sizeof(float), "reduction buffer");
+  if (sm > 226 * 1024) return cudaErrorInvalidConfiguration;
+  static bool configured = false;
+  static int per_sm = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_patch_bwd_pipe_kernel<P, TR, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(dwconv_patch_bwd_pipe_kernel<P, TR, C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, dwconv_patch_bwd_pipe_kernel<P, TR, C>, threads, sm) != cudaSuccess || v < 1) {
+      (void)cudaGetLastError();
+      v = 1;
+    }
+    per_sm = v;
+    configured = true;
+  }
+  const int units = t.a.geo.B * t.a.geo.V;
+  int grid = 148 * per_sm;
+  if (grid > units) grid = units;
+  pdl(dwconv_patch_bwd_pipe_kernel<P, TR, C>, grid, threads, sm, st)(t, units);
+  return cudaGetLastError();
+}
+
 }  // namespace pipe
 
 // Dispatch for the instantiated (P, C) pairs; cudaErrorInvalidConfiguration = not taken (caller falls back)
@@ -546,6 +702,16 @@ inline cudaError_t launch_dwconv_pipe(const DwArgs &a, const int *vis_patch, cud
   if (a.P == 4 && a.C == 80) return pipe::launch_patch_pipe<4, 2, 80>(t, st);
   if (a.P == 4 && a.C == 192) return pipe::launch_patch_pipe<4, 2, 192>(t, st);
   if (a.P == 2) return pipe::launch_s2_pipe(a, vis_patch, st);
+  return cudaErrorInvalidConfiguration;
+}
+// merged dX + dW (+ db, + column sums of dX) for the patch stages; cudaErrorInvalidConfiguration = not taken
+inline cudaError_t launch_dwconv_bwd_pipe(const pipe::DwBwdArgs &t, cudaStream_t st) {
+  const DwArgs &a = t.a;
+  if (!t.vis_patch || !a.slot_of || a.do_ln || !a.flip || !t.xfwd || !t.dw) return cudaErrorInvalidConfiguration;
+  if (a.P == 8 && a.C == 40) return pipe::launch_patch_bwd_pipe<8, 2, 40>(t, st);
+  if (a.P == 8 && a.C == 96) return pipe::launch_patch_bwd_pipe<8, 2, 96>(t, st);
+  if (a.P == 4 && a.C == 80) return pipe::launch_patch_bwd_pipe<4, 2, 80>(t, st);
+  if (a.P == 4 && a.C == 192) return pipe::launch_patch_bwd_pipe<4, 2, 192>(t, st);
   return cudaErrorInvalidConfiguration;
 }
 inline cudaError_t launch_dwconv_wgrad_pipe(const DwWgradArgs &p, const int *vis_patch, cudaStream_t st) {

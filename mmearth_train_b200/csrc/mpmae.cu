@@ -874,13 +874,28 @@ void block_backward(Ctx &c, const BlockP &bp, const BlockW &bw, const float *x, 
   if (dense) d.geo.V = pl->geo.L;
   d.P = P; d.C = C; d.flip = 1; d.do_ln = 0; d.eps = 0.f;
   d.colsum_out = dense ? nullptr : dx_colsum;
-  c.acct(4.0 * (3.0 * R * C + 49.0 * C), 2.0 * 49 * (double)R * C);
-  if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_dx");
   DwWgradArgs dwg{};
   dwg.x = x; dwg.du = du; dwg.dw = c.g(bp.dw_k); dwg.w_skh = d.w_skh; dwg.w_skw = d.w_skw; dwg.w_sc = d.w_sc;
   dwg.dbias = c.g(bp.dw_b); dwg.slot_of = d.slot_of; dwg.geo = d.geo; dwg.P = P; dwg.C = C;
-  c.acct(4.0 * (2.0 * R * C + 50.0 * C), 2.0 * 50 * (double)R * C);
-  if (c.ok()) c.check(dw_wgrad_launch(dwg, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_wgrad");
+  bool merged = false;
+  if (c.ok() && !dense) {   // dX and dW from one read of the du halo window (patch stages)
+    static const bool no_merge = getenv("MPMAE_NO_DWMERGE") != nullptr;
+    pipe::DwBwdArgs mb{d, x, dwg.dw, dwg.dbias, reinterpret_cast<const int *>(c.w(pl->o_vis))};
+    cudaError_t e = no_merge ? cudaErrorInvalidConfiguration : launch_dwconv_bwd_pipe(mb, c.st);
+    if (e != cudaErrorInvalidConfiguration) {
+      c.acct(4.0 * (4.0 * R * C + 99.0 * C), 2.0 * 99 * (double)R * C);
+      c.check(e, "dwconv_bwd");
+      merged = true;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  if (!merged) {
+    c.acct(4.0 * (3.0 * R * C + 49.0 * C), 2.0 * 49 * (double)R * C);
+    if (c.ok()) c.check(dw_launch(d, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_dx");
+    c.acct(4.0 * (2.0 * R * C + 50.0 * C), 2.0 * 50 * (double)R * C);
+    if (c.ok()) c.check(dw_wgrad_launch(dwg, reinterpret_cast<const int *>(c.w(pl->o_vis)), c.st), "dwconv_wgrad");
+  }
 }
 
 InitConvArgs init_args(Ctx &c) {
