@@ -15,7 +15,7 @@ STAGE_MASK, STAGE_ENCODER, STAGE_DECODER, STAGE_LOSS = 1, 2, 4, 8
 BWD_LOSS, BWD_DECODER, BWD_ENCODER = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmpmae.so")
+LIB_PATH = os.environ.get("MPMAE_LIB") or os.path.join(_HERE, "lib", "libmpmae.so")   # MPMAE_LIB: experiment builds (tools/)
 
 
 class Cfg(C.Structure):

@@ -88,6 +88,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// DRAM -> L2 prefetch of a contiguous block (16-byte aligned, size a multiple of 16): no destination, no completion
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -227,6 +231,8 @@ struct TcParams {
   // wave-quantisation fix: the tiles beyond the last full wave of the persistent grid (tile index >= tail_start) are cut
   // into tail_S column slices of tail_ws columns each, one slice per otherwise idle CTA
   int tail_start, tail_items, tail_S, tail_ws;
+  uint32_t num_n_magic, tail_S_magic;   // fast_div() constants of num_n and tail_S
+  int l2_prefetch;   // the producer prefetches the epilogue's per-element operand of each item into L2
   int b_res;     // 3xBF16 with one K block and one N tile: the weight pair is loaded once and stays resident next to the
                  // ring, whose stages then hold only the activation tile
   uint32_t tmem_cols;
@@ -290,18 +296,22 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const float4 &v) {
 // (second buffer) by four splitter warps; the weight operand arrives pre-split (Bw = hi, Bw_lo = lo) as two TMA
 // tiles; D += Ahi.Bhi + Alo.Bhi + Ahi.Blo.
 struct WorkItem { int m_blk, n0, wn; };   // 128-row block, first column, column count of the MMA / epilogue
+// x / d for 0 <= x * d < 2^32 with magic = floor(2^32 / d) + 1 (host side: div_magic): one IMAD.HI instead of the ~20
+// instructions of an integer division -- every warp of the CTA runs get_work once per tile, and a stage-0 tile is only a
+// few hundred instructions of epilogue work per warp
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) { return (int)__umulhi((uint32_t)x, magic); }
 __device__ __forceinline__ bool get_work(const TcParams &p, int it, WorkItem &w) {
   const int idx = (int)blockIdx.x + it * (int)gridDim.x;
   if (idx < p.tail_start) {
-    w.m_blk = idx / p.num_n;
+    w.m_blk = p.num_n == 1 ? idx : fast_div(idx, p.num_n_magic);
     w.n0 = (idx - w.m_blk * p.num_n) * p.bn;
     w.wn = p.bn;
     return true;
   }
   const int t = idx - p.tail_start;
   if (t >= p.tail_items) return false;
-  const int tq = t / p.tail_S, tile = p.tail_start + tq;
-  w.m_blk = tile / p.num_n;
+  const int tq = p.tail_S > 1 ? fast_div(t, p.tail_S_magic) : t, tile = p.tail_start + tq;
+  w.m_blk = p.num_n == 1 ? tile : fast_div(tile, p.num_n_magic);
   w.n0 = (tile - w.m_blk * p.num_n) * p.bn + (t - tq * p.tail_S) * p.tail_ws;
   w.wn = p.tail_ws;
   return true;
@@ -413,11 +423,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_load_2d(b_resident, &map_b, bres_bar, 0, 0);
         tma_load_2d(b_resident + b_bytes, &map_b_lo, bres_bar, 0, 0);
       }
+      // The epilogue reads one more [128 x wn] fp32 operand per item straight from global memory (residual / LayerNorm
+      // input / saved pre-activation), one 64-byte piece per lane and chunk: ~24 KB in flight per SM, which at DRAM latency
+      // is < 2 TB/s for the whole chip (the stage-0 da kernel reads 199 MB of `a` that way).  The producer pulls the item's
+      // block into L2 when it issues the item's operand loads, a tile or two ahead of the epilogue.
+      const float *pf_src = !p.l2_prefetch ? nullptr
+                            : (MODE == EPI_STORE) ? (g.ln_xhat ? g.ln_xhat : g.resid)
+                            : (MODE == EPI_DG) ? g.aux : (MODE == EPI_DH_GELU) ? g.aux2 : nullptr;
       WorkItem w;
       for (int it = 0; get_work(p, it, w); ++it) {
         const int m_blk = w.m_blk;
         const bool tail = w.wn != bn;
         const uint32_t wb_bytes = (uint32_t)w.wn * BK * 4;   // bytes of one weight box of this item
+        if (pf_src) {
+          const int64_t r0 = (int64_t)m_blk * BM;
+          const int rows = (int)(g.M - r0 < BM ? g.M - r0 : BM);
+          const int cols = g.N - w.n0 < w.wn ? g.N - w.n0 : w.wn;
+          if (cols == g.N) {
+            bulk_prefetch_l2(pf_src + r0 * g.N, (uint32_t)rows * (uint32_t)g.N * 4u);
+          } else {
+            for (int r = 0; r < rows; ++r) bulk_prefetch_l2(pf_src + (r0 + r) * g.N + w.n0, (uint32_t)cols * 4u);
+          }
+        }
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           uint8_t *sa = smem + (size_t)stage * stage_bytes;
@@ -509,12 +536,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n_base = w.n0;
       const float *vec_bias = vec_bias_all + n_base, *vec_kg = vec_kg_all + n_base, *vec_as = vec_as_all + n_base;
       const bool has_out2 = MODE == EPI_GELU_SQ && g.out2 != nullptr;
-      const int64_t g_first = ((int64_t)m_blk * BM) / g.group_rows;
-      const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
-      const int gw_lo = (int)(mw0 / g.group_rows - g_first);
-      const int64_t mw_last = (mw0 + 31 < g.M ? mw0 + 31 : g.M - 1);
-      const int gw_hi = mw_last >= mw0 ? (int)(mw_last / g.group_rows - g_first) : gw_lo;
-      const int my_g = row_ok ? (int)(m / g.group_rows - g_first) : gw_lo;
+      // statistics groups touched by this tile / warp / lane (all 0 with one group: the sparse blocks; the divisions are
+      // skipped there -- they were a quarter of a stage-0 epilogue warp's instructions per tile)
+      int64_t g_first = 0;
+      int gw_lo = 0, gw_hi = 0, my_g = 0;
+      if (MODE != EPI_STORE && !single_group) {
+        const int64_t mw0 = (int64_t)m_blk * BM + q * 32;
+        const int64_t mw_last = (mw0 + 31 < g.M ? mw0 + 31 : g.M - 1);
+        g_first = ((int64_t)m_blk * BM) / g.group_rows;
+        gw_lo = (int)(mw0 / g.group_rows - g_first);
+        gw_hi = mw_last >= mw0 ? (int)(mw_last / g.group_rows - g_first) : gw_lo;
+        my_g = row_ok ? (int)(m / g.group_rows - g_first) : gw_lo;
+      }
       auto prefetch = [&](int c0, float4 *dst) {
         if (p.vec8_in) {
 #pragma unroll
@@ -819,7 +852,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // flush this tile's column statistics (epilogue warps only: named barrier 1)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         const int64_t m_last = ((int64_t)(m_blk + 1) * BM < g.M ? (int64_t)(m_blk + 1) * BM : g.M) - 1;
-        const int ng = (int)(m_last / g.group_rows - g_first) + 1;
+        const int ng = single_group ? 1 : (int)(m_last / g.group_rows - g_first) + 1;
         if ((MODE == EPI_GELU_SQ || MODE == EPI_DG) && g.colsum) {
           for (int i = et; i < ng * bn; i += kEpiThreads) {
             const int gg = i / bn, cidx = i - gg * bn;
@@ -1073,6 +1106,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
+constexpr int kTnStages = 8;   // ring depth cap: a stage is only 32 rows (<= 48 KB of operands), and the single-pass kernel is
+                               // bound by bytes in flight (ncu r2_s: 9 % warps active, tensor pipe 30 %, DRAM 28 %)
 constexpr int kTnThreads = 192, kTnSplitThreads = 512;   // 16 splitter warps: both operand tiles are split (one also through GELU) every chunk
 
 // SPLIT = 3xTF32: both operand tiles are split in shared memory (hi in place, remainder in a second buffer) by four
@@ -1089,9 +1124,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
   const uint32_t m_span = SPLIT ? 2 * m_bytes : m_bytes;
   const uint32_t stage_bytes = m_span + (SPLIT ? 2 : 1) * n_bytes;   // [M | Mlo | N | Nlo]
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)nstage * stage_bytes);
-  uint64_t *empty_bar = full_bar + STAGES;
-  uint64_t *split_bar = empty_bar + STAGES;
-  uint64_t *tfull_bar = split_bar + STAGES;
+  uint64_t *empty_bar = full_bar + kTnStages;
+  uint64_t *split_bar = empty_bar + kTnStages;
+  uint64_t *tfull_bar = split_bar + kTnStages;
   uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1099,7 +1134,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_m)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_n)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], kTnSplitThreads / 32); }
+    for (int s = 0; s < kTnStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], kTnSplitThreads / 32); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1343,6 +1378,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   // tail splitting (see TcParams): only when every tile takes the predicate-free epilogue path and N tiles are whole
   const int total = p.num_m * p.num_n;
   p.tail_start = total; p.tail_items = 0; p.tail_S = 1; p.tail_ws = p.bn;
+  auto div_magic = [](int d) { return (uint32_t)((1ull << 32) / (uint64_t)d + 1ull); };   // fast_div(): d >= 2 (d == 1 is branched)
   CUtensorMap mbt = mb, mbtl = mbl;
   {
     const bool single_group = (int64_t)a.group_rows >= a.M;
@@ -1369,6 +1405,11 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
       }
     }
   }
+  // measured (profiles/r2_x_sweep.txt): no gain, the stage-0 da kernel 5 % slower -- opt-in only
+  static const bool no_pf = getenv("MPMAE_TC_L2PF") == nullptr;
+  p.l2_prefetch = (!no_pf && a.N % 4 == 0 && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2 | (uintptr_t)a.ln_xhat) & 15) == 0) ? 1 : 0;
+  p.num_n_magic = div_magic(p.num_n > 1 ? p.num_n : 2);
+  p.tail_S_magic = p.tail_S > 1 ? div_magic(p.tail_S) : 0u;
   const size_t smem = smem_for(bn, p.stages);
   static bool configured = false;
   if (!configured) {
@@ -1438,7 +1479,9 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   // one item per CTA when the output tile is big (the epilogue's atomics dominate), two when it is small (the second
   // item's MMAs hide the first one's epilogue)
   const int items_target = ((int64_t)p.Msz * p.Nsz >= 32768) ? 148 : 296;
-  int splits = cdiv(items_target, tiles);
+  // floor, not ceil: 160 items on 148 persistent CTAs take two item times (stage 3: 20 tiles x 8 splits; decoder:
+  // 32 tiles x 5), 140 / 128 items take one
+  int splits = tiles >= items_target ? 1 : items_target / tiles;
   p.vec4 = (((uintptr_t)a.dW & 15) == 0 && a.K % 4 == 0) ? 1 : 0;
   static const int env_items = getenv("MPMAE_TN_ITEMS") ? atoi(getenv("MPMAE_TN_ITEMS")) : 0;
   if (env_items > 0) splits = cdiv(env_items, tiles);
@@ -1469,7 +1512,9 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   if (!get(&mm, msrc, a.R, p.Msz) || !get(&mn, nsrc, a.R, p.Nsz)) return cudaErrorInvalidValue;
   const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * 32 * 4 + (size_t)bn * 32 * 4);
   int stages = (int)((224 * 1024 - 2048) / stage_bytes);
-  if (stages > STAGES) stages = STAGES;
+  static const int env_tn_stages = getenv("MPMAE_TN_STAGES") ? atoi(getenv("MPMAE_TN_STAGES")) : 0;
+  const int cap = env_tn_stages >= 2 && env_tn_stages <= kTnStages ? env_tn_stages : kTnStages;
+  if (stages > cap) stages = cap;
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 256;

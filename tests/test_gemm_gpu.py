@@ -43,7 +43,10 @@ WG_SHAPES = [(2432, 40, 160), (2432, 160, 40), (608, 80, 320), (4096, 128, 128),
              (333, 96, 384), (5000, 2816, 512)]
 
 
-@pytest.mark.parametrize("backend,tol", [(0, 2e-6), (2, 2e-3), (1, 2e-5)])
+# 3xTF32 (backend 1): the tensor core truncates when it aligns a product to the fp32 accumulator, so the error grows with the
+# rows one work item accumulates (R / splits): 1.9e-5 at 2.5 k rows per item, 2.3e-5 at 3.1 k (the (12544, 2048, 512) case since
+# the split count is chosen to fill ONE wave of 148 CTAs: 32 tiles x 4 splits instead of 32 x 5 = 160 items in two waves).
+@pytest.mark.parametrize("backend,tol", [(0, 2e-6), (2, 2e-3), (1, 3e-5)])
 @pytest.mark.parametrize("shape", WG_SHAPES)
 def test_gemm_wgrad(native_lib, shape, backend, tol):
     """dW[N, K] += X[R, N]^T . Y[R, K]: contraction over rows (MN-major tcgen05 operands), accumulating."""
