@@ -153,7 +153,7 @@ int mpmae_backward_part_range(const mpmae_plan *plan, int32_t part, int64_t *lo,
 int mpmae_encoder_features(mpmae_plan *plan, const mpmae_io *io, float *out_nchw, void *cuda_stream);
 
 /* stand-alone GEMM entry (unit tests / microbench): out[M,N] = a[M,K] . b[N,K]^T (+bias).
- * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32, 3 = tcgen05 3xBF16 (1 and 3 need scratch of 2*N*K floats) */
+ * backend 0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32, 3 = tcgen05 3xBF16 (1 and 3 need scratch of 2*N*ceil32(K) floats, ceil32 = K rounded up to a multiple of 32) */
 int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float *bias, float *out,
                     int64_t M, int32_t N, int32_t K, float *scratch, void *cuda_stream);
 
@@ -162,7 +162,7 @@ int mpmae_gemm_rows(int32_t backend, const float *a, const float *b, const float
  *   mode 1  out = a.b^T + bias ; out2 = gelu(out) ; colsum[g, n] += out2^2           (pw1 + GELU + GRN statistic)
  *   mode 2  out = a.b^T ; colsum[g, n] += out * aux ; colsum2[n] += out              (decoder dg)
  *   mode 3  out = (a.b^T + kg[n] * gelu(aux2)) * gelu'(aux2) ; colsum2[n] += out    (GELU/GRN backward)
- * group_rows = rows per statistics group (>= M: one group).  scratch: 2*N*K floats (backends 1 and 3). */
+ * group_rows = rows per statistics group (>= M: one group).  scratch: 2*N*ceil32(K) floats (backends 1 and 3). */
 typedef struct mpmae_gemm_desc {
   const float *a, *b, *bias, *resid, *aux, *aux2, *kg;
   float *out, *out2, *colsum, *colsum2, *scratch;

@@ -56,6 +56,11 @@ class RawDesc(C.Structure):
                 ("std", (C.c_double * RAW_MAX_BANDS) * 2)]
 
 
+def gemm_scratch_floats(N: int, K: int) -> int:
+    """floats of scratch ``mpmae_gemm_rows`` / ``mpmae_gemm_epi`` need for the split weight (backends 1 and 3)"""
+    return 2 * N * (((K + 31) // 32) * 32)
+
+
 class NativeError(RuntimeError):
     pass
 

@@ -109,7 +109,7 @@ class ConvNeXtV2(nn.Module):
         d = nat.GemmDesc()
         M, K = a.shape
         N = w.shape[0]
-        scratch = torch.empty(2 * N * K, device=a.device)
+        scratch = torch.empty(nat.gemm_scratch_floats(N, K), device=a.device)
         for name, t in dict(a=a, b=w, bias=bias, resid=resid, out=out, out2=out2, colsum=colsum, scratch=scratch).items():
             if t is not None:
                 setattr(d, name, t.data_ptr())

@@ -215,6 +215,11 @@ __device__ __forceinline__ void gelu_both_f(float x, float &h, float &dgelu) {
   dgelu = fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
+// 3xBF16 weight operand: [rows][ceil(cols / 32)][32 bf16 high parts | 32 bf16 remainders], zero padded -- one 128-byte
+// group per 32 columns, which is one row of a tcgen05 operand tile (gemm_tc.cuh).  Sizes of that array:
+__host__ __device__ inline int bf16_pair_cols(int cols) { return ((cols + 31) / 32) * 64; }            // bf16 elements per row
+__host__ __device__ inline int64_t bf16_pair_floats(int64_t rows, int cols) { return rows * (bf16_pair_cols(cols) / 2); }
+
 // Geometry of the visible-patch row layout shared by all sparse kernels.
 //   rows of stage with patch side P:  row = (n*V + slot)*P*P + morton(py, px)
 //   slot_of[n*L + l] = slot of patch l (ascending patch index among visible ones) or -1

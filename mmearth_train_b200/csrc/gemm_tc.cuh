@@ -30,14 +30,20 @@
 // production build sees a constant 0 and the guarded code disappears.
 #ifdef MPMAE_TC_KNOBS
 #define TC_DBG(p) ((p).dbg)
+// event trace of CTA 0 (tools/tc_trace.py): role r appends clock64() to trace[r * 256 + n++]
+#define TC_TRACE_DECL int trace_n = 0
+#define TC_TRACE(p, role) \
+  do { if ((p).trace && blockIdx.x == 0 && trace_n < 255) { (p).trace[(role) * 256 + 1 + trace_n] = (unsigned long long)clock64(); (p).trace[(role) * 256] = ++trace_n; } } while (0)
 #else
 #define TC_DBG(p) 0
+#define TC_TRACE_DECL
+#define TC_TRACE(p, role) do { } while (0)
 #endif
 
 namespace mpmae {
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 4, ACC_STAGES = 2;
+constexpr int BM = 128, BK = 32, STAGES = 8, ACC_STAGES = 2;
 constexpr uint64_t kSpinLimit = 4000000000ull;  // ~2 s of SM clocks: a lost barrier traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,11 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // stage): its wake-up latency is off the critical path, so it sleeps between polls instead of spinning.  The ncu source page
 // of round 1's pw1 kernel showed 15 % of all issued instructions in the spin loops of these two warps (try_wait + clock read
 // + branch), issue slots taken from the epilogue warps that bound the kernel.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, bool spin = false) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(256);
+    if (!spin) __nanosleep(256);
     if ((uint64_t)(clock64() - t0) > kSpinLimit) __trap();
   }
 }
@@ -233,8 +239,8 @@ struct TcParams {
   int tail_start, tail_items, tail_S, tail_ws;
   uint32_t num_n_magic, tail_S_magic;   // fast_div() constants of num_n and tail_S
   int l2_prefetch;   // the producer prefetches the epilogue's per-element operand of each item into L2
-  int b_res;     // 3xBF16 with one K block and one N tile: the weight pair is loaded once and stays resident next to the
-                 // ring, whose stages then hold only the activation tile
+  int spin;          // the ahead-of-consumer roles spin instead of sleeping between polls (latency-bound shapes)
+  unsigned long long *trace;   // knob builds only (TC_TRACE)
   uint32_t tmem_cols;
   int dbg;       // MPMAE_TC_DBG timing experiments (results invalid): 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld,
                  // 32 no MMAs, 64 no operand split
@@ -317,10 +323,15 @@ __device__ __forceinline__ bool get_work(const TcParams &p, int it, WorkItem &w)
   return true;
 }
 
-// BF16 (with SPLIT) = 3xBF16: a ring stage covers 64 elements of K.  Two fp32 TMA boxes of A land in the stage and the
-// splitter warps convert them IN PLACE into a bf16 high tile and a bf16 remainder tile ([128 x 64] each, 128-byte
-// swizzle); the weight arrives pre-split as bf16 (hi, lo); D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with kind::f16 MMAs -- the
-// same stage bytes as 3xTF32 carry twice the K and the tensor pipe runs at twice the rate; |error| <= 2^-16 per product.
+// BF16 (with SPLIT) = 3xBF16: a ring stage covers 32 elements of K.  ONE fp32 TMA box of A ([128 x 32], 128-byte rows,
+// 128-byte swizzle) lands in the stage and the splitter warps convert every row IN PLACE into [32 bf16 high parts | 32 bf16
+// remainders] -- still one 128-byte-swizzled row, so the same K-major descriptor addresses the high half (bytes 0..63) and
+// the remainder half (bytes 64..127) of the tile by its start address alone.  The weight arrives pre-split in the same
+// interleaved form ([N][K/32][hi 32 | lo 32] bf16, written by fold_kernel: one [bn x 128 B] box per stage).
+// D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with kind::f16 MMAs (two K = 16 instructions per product and stage); |error| <= 2^-16
+// per product.  A row is converted by threads of ONE warp (no block-wide barrier), and a stage is 16 KB + bn * 128 B --
+// half of what a 64-element stage took -- so the ring is 4..8 deep where it was 2: the TMA load, the conversion and the
+// MMAs of consecutive k blocks overlap (profiles/r2_aa_trace.txt: with two stages they ran back to back).
 template <int MODE, bool SPLIT, bool WIDE, bool BF16, bool AGELU = false>
 __global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE, AGELU), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -334,19 +345,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
   constexpr uint32_t a_bytes = BM * BK * 4;
-  const uint32_t b_bytes = (uint32_t)bn * BK * 4;
-  const uint32_t a_span = SPLIT ? 2 * a_bytes : a_bytes;             // [A | Alo]
-  const bool b_res = BF16 && p.b_res;
-  const uint32_t stage_bytes = b_res ? a_span : a_span + (SPLIT ? 2 : 1) * b_bytes;   // [A | Alo | B | Blo]
-  uint8_t *b_resident = smem + (size_t)nstage * stage_bytes;         // [B | Blo] (b_res only)
-  uint8_t *stage_out = b_resident + (b_res ? 2 * b_bytes : 0);       // [kEpiWarps][out_arrays][32 x 16] TMA-store staging
+  const uint32_t b_bytes = (uint32_t)bn * BK * 4;                    // also one [bn x (32 hi | 32 lo)] bf16 tile
+  const uint32_t a_span = (SPLIT && !BF16) ? 2 * a_bytes : a_bytes;  // [A | Alo]; 3xBF16: one tile holds both halves
+  const uint32_t stage_bytes = BF16 ? a_bytes + b_bytes : a_span + (SPLIT ? 2 : 1) * b_bytes;   // [A | Alo | B | Blo]
+  uint8_t *stage_out = smem + (size_t)nstage * stage_bytes;          // [kEpiWarps][out_arrays][32 x 16] TMA-store staging
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_out + (size_t)kEpiWarps * out_arrays(MODE) * kStageOutBytes);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *split_bar = empty_bar + STAGES;
   uint64_t *tfull_bar = split_bar + STAGES;
   uint64_t *tempty_bar = tfull_bar + ACC_STAGES;
-  uint64_t *bres_bar = tempty_bar + ACC_STAGES;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bres_bar + 2);   // keeps the float4 vectors below 16-byte aligned
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tempty_bar + ACC_STAGES + 2);   // keeps the float4 vectors below 16-byte aligned
   float *colacc = reinterpret_cast<float *>(tmem_ptr + 4);           // [kTcGroups][bn]
   constexpr int kTcGroups = 4;                                       // a 128-row tile spans <= 4 groups of >= 32 rows
   float *colacc2 = colacc + kTcGroups * bn;                          // [bn]
@@ -366,7 +374,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_out)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], kSplitWarps > 0 ? kSplitWarps : 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
-    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
@@ -418,11 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (b_res && (int)blockIdx.x < total_tiles) {
-        mbar_expect_tx(bres_bar, 2 * b_bytes);
-        tma_load_2d(b_resident, &map_b, bres_bar, 0, 0);
-        tma_load_2d(b_resident + b_bytes, &map_b_lo, bres_bar, 0, 0);
-      }
+      TC_TRACE_DECL;
       // The epilogue reads one more [128 x wn] fp32 operand per item straight from global memory (residual / LayerNorm
       // input / saved pre-activation), one 64-byte piece per lane and chunk: ~24 KB in flight per SM, which at DRAM latency
       // is < 2 TB/s for the whole chip (the stage-0 da kernel reads 199 MB of `a` that way).  The producer pulls the item's
@@ -446,16 +449,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         for (int kb = 0; kb < p.num_k; ++kb) {
-          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin != 0);
+          TC_TRACE(p, 0);
           uint8_t *sa = smem + (size_t)stage * stage_bytes;
           if (BF16) {
-            mbar_expect_tx(&full_bar[stage], 2 * a_bytes + (b_res ? 0 : 2 * wb_bytes));
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * 64, m_blk * BM);
-            tma_load_2d(sa + a_bytes, &map_a, &full_bar[stage], kb * 64 + 32, m_blk * BM);
-            if (!b_res) {
-              tma_load_2d(sa + a_span, tail ? &map_bt : &map_b, &full_bar[stage], kb * 64, w.n0);
-              tma_load_2d(sa + a_span + b_bytes, tail ? &map_bt_lo : &map_b_lo, &full_bar[stage], kb * 64, w.n0);
-            }
+            mbar_expect_tx(&full_bar[stage], a_bytes + wb_bytes);
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa + a_bytes, tail ? &map_bt : &map_b, &full_bar[stage], kb * 64, w.n0);   // 64 bf16 = (hi | lo) of 32 k
           } else {
           mbar_expect_tx(&full_bar[stage], a_bytes + (SPLIT ? 2 : 1) * wb_bytes);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
@@ -471,29 +471,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      if (b_res && (int)blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
+      TC_TRACE_DECL;
       WorkItem w;
       for (int it = 0; get_work(p, it, w); ++it) {
         const uint32_t idesc = BF16 ? make_idesc_bf16(w.wn) : make_idesc(w.wn);
-        mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
+        mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1, p.spin != 0);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          TC_TRACE(p, 1);
           if (SPLIT) mbar_wait(&split_bar[stage], phase);
+          TC_TRACE(p, 2);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = b_res ? smem_u32(b_resident) : sa + a_span;
+          const uint32_t sb = BF16 ? sa + a_bytes : sa + a_span;
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
           if (BF16) {
-            const uint64_t dal = make_smem_desc(sa + a_bytes), dbl = make_smem_desc(sb + b_bytes);
+            // a 128-byte row = [hi k0..31 | lo k0..31]: descriptor start + 0 / + 2 (x16 B) = the two K = 16 halves of the
+            // high parts, + 4 / + 6 = of the remainders
             if (!(TC_DBG(p) & 32)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < 2; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 0; k < 2; ++k) umma_bf16(tmem_d, da + (uint64_t)(4 + 2 * k), db + (uint64_t)(2 * k), idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+            for (int k = 0; k < 2; ++k) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(4 + 2 * k), idesc, 1u);
             }
           } else {
           if (!(TC_DBG(p) & 32)) {
@@ -528,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool single_group = (int64_t)g.group_rows >= g.M;
     int as = 0;
     uint32_t aphase = 0;
+    TC_TRACE_DECL;
     WorkItem w;
     for (int it = 0; get_work(p, it, w); ++it) {
       const int m_blk = w.m_blk;
@@ -641,6 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int j = 0; j < 4; ++j) pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c0 < ncols) load_pre(c0, pre);
         mbar_wait(&tfull_bar[as], aphase);
+        if (warp == 2 && lane == 0) TC_TRACE(p, 3);
         tc_fence_after();
         if (c0 < ncols && !(TC_DBG(p) & 8)) tmem_ld16_issue(taddr + c0, vr);
         for (; c0 < ncols; c0 += 16 * kParts) {
@@ -741,6 +746,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (warp == 2 && lane == 0) TC_TRACE(p, 4);
         if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         continue;
       }
@@ -917,42 +923,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float4 *A = reinterpret_cast<float4 *>(smem + (size_t)stage * stage_bytes);
         float4 *Alo = A + a_bytes / 16;
         if (BF16) {
-          // raw: two [128 rows x 128 B] fp32 boxes (k halves h = 0, 1); result: bf16 hi tile over box 0, lo tile over
-          // box 1.  A pass handles a band of rows: read both boxes' chunks of the band into registers, barrier among the
-          // splitter warps, write the band of both bf16 tiles (rows are independent, so bands do not interfere).
+          // raw: one [128 rows x 128 B] fp32 box, physical 16-byte chunk pc of row r holds floats 4c .. 4c+3 with
+          // c = pc ^ (r & 7).  Result in place: bf16 (hi, hi) of chunk c -> logical chunk c >> 1, 8-byte half c & 1;
+          // (lo, lo) -> logical chunk 4 + (c >> 1).  A row belongs to kTPR consecutive threads of one warp: all of them read
+          // their chunks, __syncwarp, then write (rows are independent, so there is no block-wide barrier).
           constexpr int kST = kSplitThreads > 0 ? kSplitThreads : 32;
-          constexpr int kPer = (2048 / kST >= 8) ? 8 : 2048 / kST;   // 2 x 128 x 8 float4 in all, kPer per thread per pass
-          constexpr int kPasses = 2048 / (kPer * kST);
-          constexpr int kBandRows = 128 / kPasses;
+          constexpr int kTPR = kST >= 128 ? kST / 128 : 1;          // threads per row
+          constexpr int kPasses = kST >= 128 ? 1 : 128 / kST;       // rows per thread
+          constexpr int kCh = 8 / kTPR;                             // chunks per thread and row
           uint8_t *base = smem + (size_t)stage * stage_bytes;
 #pragma unroll 1
           for (int ps = 0; ps < ((TC_DBG(p) & 64) ? 0 : kPasses); ++ps) {
-            float4 x[kPer];
-            int rr[kPer], cc[kPer], hh[kPer];
+            const int r = kST >= 128 ? stid / kTPR : ps * kST + stid;
+            const int sub = kST >= 128 ? stid % kTPR : 0;
+            uint8_t *row = base + r * 128;
+            float4 x[kCh];
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) {
-              const int idx = i * kST + stid;                    // 0 .. kBandRows*16-1: (h, row in band, physical chunk)
-              const int h = idx / (kBandRows * 8), rem = idx - h * (kBandRows * 8);
-              const int r = ps * kBandRows + (rem >> 3), pc = rem & 7;
-              hh[i] = h; rr[i] = r; cc[i] = pc ^ (r & 7);        // logical 16-byte chunk: k = 32 h + 4 c .. + 3
-              x[i] = *reinterpret_cast<const float4 *>(base + h * a_bytes + r * 128 + pc * 16);
+            for (int j = 0; j < kCh; ++j) {
+              const int c = j * kTPR + sub;                         // logical chunk: k = kb * 32 + 4 c .. + 3
+              x[j] = *reinterpret_cast<const float4 *>(row + ((c ^ (r & 7)) << 4));
               if (AGELU) {   // A = saved pre-activation: h = gelu(a), times the GRN scale of its column
-                const int k = kb * 64 + h * 32 + cc[i] * 4;
+                const int k = kb * BK + c * 4;
                 const float4 sc = k < g.K ? *reinterpret_cast<const float4 *>(a_sc + k) : make_float4(1.f, 1.f, 1.f, 1.f);
-                const float4 hv = gelu4_f(x[i]);
-                x[i] = make_float4(hv.x * sc.x, hv.y * sc.y, hv.z * sc.z, hv.w * sc.w);
+                const float4 hv = gelu4_f(x[j]);
+                x[j] = make_float4(hv.x * sc.x, hv.y * sc.y, hv.z * sc.z, hv.w * sc.w);
               }
             }
-            asm volatile("bar.sync 2, %0;" ::"n"(kST) : "memory");
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < kPer; ++i) {
+            for (int j = 0; j < kCh; ++j) {
+              const int c = j * kTPR + sub;
               uint32_t h0, l0, h1, l1;
-              split_bf16x2(x[i].x, x[i].y, h0, l0);
-              split_bf16x2(x[i].z, x[i].w, h1, l1);
-              const int cb = hh[i] * 4 + (cc[i] >> 1);           // logical 16-byte chunk of the bf16 row
-              const uint32_t off = (uint32_t)rr[i] * 128u + (uint32_t)((cb ^ (rr[i] & 7)) << 4) + (uint32_t)(cc[i] & 1) * 8u;
-              *reinterpret_cast<uint2 *>(base + off) = make_uint2(h0, h1);
-              *reinterpret_cast<uint2 *>(base + a_bytes + off) = make_uint2(l0, l1);
+              split_bf16x2(x[j].x, x[j].y, h0, l0);
+              split_bf16x2(x[j].z, x[j].w, h1, l1);
+              const uint32_t off = (uint32_t)((((c >> 1) ^ (r & 7)) << 4) + (c & 1) * 8);
+              *reinterpret_cast<uint2 *>(row + off) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(row + (off ^ 64u)) = make_uint2(l0, l1);   // logical chunk + 4 = physical chunk ^ 4
             }
           }
         } else
@@ -1068,6 +1074,9 @@ struct MapCache {
 };
 inline MapCache &map_cache() { static MapCache c; return c; }
 
+#ifdef MPMAE_TC_KNOBS
+inline unsigned long long *&tc_trace_buffer() { static unsigned long long *b = nullptr; return b; }
+#endif
 inline int pick_bn(int N) {
   if (N <= 256) return ((N + 15) / 16) * 16;
   for (int bn = 256; bn >= 128; bn -= 16)
@@ -1320,16 +1329,14 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   using namespace tc;
   TcParams p{};
   p.g = a;
-  // resident weights: measured no faster (the epilogue, not the operand stream, bounds these shapes): opt-in only
-  static const bool env_bres = getenv("MPMAE_TC_BRES") != nullptr;      // environment knobs are read once per process
-  static const int env_bn = getenv("MPMAE_TC_BN") ? atoi(getenv("MPMAE_TC_BN")) : 0;
+  static const int env_bn = getenv("MPMAE_TC_BN") ? atoi(getenv("MPMAE_TC_BN")) : 0;   // environment knobs are read once per process
   static const bool env_dbg = getenv("MPMAE_TC_DBG") != nullptr;        // timing experiments re-read their mask per launch
-  auto b_resident = [&](int bn) { return BF16 && a.K <= 64 && a.N <= bn && env_bres; };
   auto smem_for = [&](int bn, int stages) {
-    const size_t a_stage = (size_t)(SPLIT ? 2 : 1) * BM * BK * 4, b_stage = (size_t)(SPLIT ? 2 : 1) * bn * BK * 4;
-    const size_t ring = b_resident(bn) ? (size_t)stages * a_stage + b_stage : (size_t)stages * (a_stage + b_stage);
+    // 3xBF16: one tile per operand holds the high parts and the remainders of 32 k; 3xTF32: separate hi / lo tiles
+    const size_t a_stage = (size_t)((SPLIT && !BF16) ? 2 : 1) * BM * BK * 4, b_stage = (size_t)((SPLIT && !BF16) ? 2 : 1) * bn * BK * 4;
+    const size_t ring = (size_t)stages * (a_stage + b_stage);
     const int num_n = cdiv(a.N, bn);
-    return 1024 + ring + (size_t)epi_warps(MODE, WIDE, AGELU) * out_arrays(MODE) * kStageOutBytes + 256 +
+    return 1024 + ring + (size_t)epi_warps(MODE, WIDE, AGELU) * out_arrays(MODE) * kStageOutBytes + 320 +
            (size_t)(5 * bn + (MODE == EPI_STORE ? 2 : 5) * num_n * bn + (AGELU ? a.K + 32 : 0)) * 4;
   };
   // N tile: the widest multiple of 16 (<= 256) that divides N and fits the shared-memory budget with a 2-stage ring,
@@ -1347,8 +1354,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   while (p.stages < STAGES && smem_for(bn, p.stages + 1) <= 226 * 1024) ++p.stages;
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
-  p.num_k = cdiv(a.K, BF16 ? 64 : BK);
-  p.b_res = b_resident(bn) ? 1 : 0;
+  p.num_k = cdiv(a.K, BK);
   p.vec8 = (a.N % 8 == 0) && (((uintptr_t)a.out | (uintptr_t)a.out2) & 31) == 0;
   p.vec8_in = (a.N % 8 == 0) && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2) & 31) == 0;
   uint32_t cols = 32;
@@ -1358,11 +1364,9 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   if (env_dbg) { const char *e = getenv("MPMAE_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   CUtensorMap ma, mb, mbl, mo, mo2;
   if (!map_cache().get(&ma, a.A, a.M, a.K, BM)) return cudaErrorInvalidValue;
-  if (BF16) {   // Bw_lo holds the packed bf16 pair: hi [N, K] then lo [N, K]
-    const uint16_t *b16 = reinterpret_cast<const uint16_t *>(a.Bw_lo);
-    if (!map_cache().get(&mb, reinterpret_cast<const float *>(b16), a.N, a.K, -p.bn) ||
-        !map_cache().get(&mbl, reinterpret_cast<const float *>(b16 + (int64_t)a.N * a.K), a.N, a.K, -p.bn))
-      return cudaErrorInvalidValue;
+  if (BF16) {   // Bw_lo holds the interleaved bf16 pair [N][ceil(K / 32)][hi 32 | lo 32] (bf16_pair_cols(K) columns per row)
+    if (!map_cache().get(&mb, a.Bw_lo, a.N, bf16_pair_cols(a.K), -p.bn)) return cudaErrorInvalidValue;
+    mbl = mb;
   } else {
     if (!map_cache().get(&mb, a.Bw, a.N, a.K, p.bn)) return cudaErrorInvalidValue;
     mbl = mb;
@@ -1384,7 +1388,7 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     const bool single_group = (int64_t)a.group_rows >= a.M;
     const float *pre = MODE == EPI_STORE ? a.resid : MODE == EPI_DG ? a.aux : MODE == EPI_DH_GELU ? a.aux2 : nullptr;
     const bool all_fast = p.tma_out && a.M % BM == 0 && (single_group || MODE == EPI_GELU_SQ || MODE == EPI_DG) &&
-                          (!pre || (a.N % 8 == 0 && p.vec8_in)) && !a.ln_rstd && a.N % p.bn == 0 && !p.b_res;
+                          (!pre || (a.N % 8 == 0 && p.vec8_in)) && !a.ln_rstd && a.N % p.bn == 0;
     const int full = (total / grid) * grid, rem = total - full;
     static const bool no_tail = getenv("MPMAE_TC_NO_TAIL") != nullptr;
     if (all_fast && !no_tail && total > grid && rem > 0 && rem * 2 <= grid) {
@@ -1392,9 +1396,8 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
         if (p.bn % ws != 0 || rem * (p.bn / ws) > grid) continue;
         bool ok;
         if (BF16) {
-          const uint16_t *b16 = reinterpret_cast<const uint16_t *>(a.Bw_lo);
-          ok = map_cache().get(&mbt, reinterpret_cast<const float *>(b16), a.N, a.K, -ws) &&
-               map_cache().get(&mbtl, reinterpret_cast<const float *>(b16 + (int64_t)a.N * a.K), a.N, a.K, -ws);
+          ok = map_cache().get(&mbt, a.Bw_lo, a.N, bf16_pair_cols(a.K), -ws);
+          mbtl = mbt;
         } else {
           ok = map_cache().get(&mbt, a.Bw, a.N, a.K, ws);
           mbtl = mbt;
@@ -1408,6 +1411,18 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   // measured (profiles/r2_x_sweep.txt): no gain, the stage-0 da kernel 5 % slower -- opt-in only
   static const bool no_pf = getenv("MPMAE_TC_L2PF") == nullptr;
   p.l2_prefetch = (!no_pf && a.N % 4 == 0 && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2 | (uintptr_t)a.ln_xhat) & 15) == 0) ? 1 : 0;
+  p.trace = nullptr;
+#ifdef MPMAE_TC_KNOBS
+  if (getenv("MPMAE_TC_TRACE")) {
+    static unsigned long long *buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 8 * 256 * sizeof(unsigned long long));
+    cudaMemsetAsync(buf, 0, 8 * 256 * sizeof(unsigned long long), st);
+    p.trace = buf;
+    tc_trace_buffer() = buf;
+  }
+#endif
+  static const int env_spin = getenv("MPMAE_TC_SPIN") ? atoi(getenv("MPMAE_TC_SPIN")) : -1;
+  p.spin = env_spin >= 0 ? env_spin : 0;
   p.num_n_magic = div_magic(p.num_n > 1 ? p.num_n : 2);
   p.tail_S_magic = p.tail_S > 1 ? div_magic(p.tail_S) : 0u;
   const size_t smem = smem_for(bn, p.stages);

@@ -325,12 +325,13 @@ struct FoldArgs {
   float grn_eps;
 };
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__device__ __forceinline__ void store_bf16_pair(float *lo_array, int64_t idx, int64_t nk, float wf) {
-  uint16_t *b = reinterpret_cast<uint16_t *>(lo_array);
+// element (row, col) of the interleaved bf16 pair array (common.cuh: bf16_pair_cols); col may lie in the zero padding
+__device__ __forceinline__ void store_bf16_pair(float *pair_array, int row, int col, int cols, float wf) {
+  uint16_t *b = reinterpret_cast<uint16_t *>(pair_array) + (int64_t)row * bf16_pair_cols(cols) + (col >> 5) * 64 + (col & 31);
   const __nv_bfloat16 h = __float2bfloat16_rn(wf);
   const __nv_bfloat16 l = __float2bfloat16_rn(wf - __bfloat162float(h));
-  b[idx] = __bfloat16_as_ushort(h);
-  b[nk + idx] = __bfloat16_as_ushort(l);
+  b[0] = __bfloat16_as_ushort(h);
+  b[32] = __bfloat16_as_ushort(l);
 }
 // 32 x 32 tiles through shared memory: the source is read along its contiguous axis and both orientations (Wf [N, K],
 // WfT [K, N]) leave with coalesced stores.  grid = (K tiles, N tiles), block = (32, 8).  The folded bias of a row block is
@@ -382,7 +383,6 @@ __device__ __forceinline__ void fold_tile(const FoldArgs &p, int bx, int by) {
   }
   __syncthreads();
   const bool split = (p.Wf_lo != nullptr || p.WfT_lo != nullptr) && !p.b16;
-  const int64_t nk = (int64_t)p.N * p.K;
   if (p.Wf) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -392,9 +392,11 @@ __device__ __forceinline__ void fold_tile(const FoldArgs &p, int bx, int by) {
         const float hi = tf32_hi(wf);
         p.Wf[(int64_t)n * p.K + k] = split ? hi : wf;
         if (p.Wf_lo) {
-          if (p.b16) store_bf16_pair(p.Wf_lo, (int64_t)n * p.K + k, nk, wf);
+          if (p.b16) store_bf16_pair(p.Wf_lo, n, k, p.K, wf);
           else p.Wf_lo[(int64_t)n * p.K + k] = wf - hi;
         }
+      } else if (n < p.N && p.Wf_lo && p.b16) {
+        store_bf16_pair(p.Wf_lo, n, k, p.K, 0.f);     // zero padding of the last 32-column group (the tile covers it)
       }
     }
   }
@@ -407,9 +409,11 @@ __device__ __forceinline__ void fold_tile(const FoldArgs &p, int bx, int by) {
         const float hi = tf32_hi(wf);
         p.WfT[(int64_t)k * p.N + n] = split ? hi : wf;
         if (p.WfT_lo) {
-          if (p.b16) store_bf16_pair(p.WfT_lo, (int64_t)k * p.N + n, nk, wf);
+          if (p.b16) store_bf16_pair(p.WfT_lo, k, n, p.N, wf);
           else p.WfT_lo[(int64_t)k * p.N + n] = wf - hi;
         }
+      } else if (k < p.K && p.WfT_lo && p.b16) {
+        store_bf16_pair(p.WfT_lo, k, n, p.N, 0.f);
       }
     }
   }

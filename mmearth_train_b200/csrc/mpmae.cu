@@ -263,7 +263,8 @@ void build_params(mpmae_plan *pl) {
 }
 
 void note_wf(mpmae_plan *pl, int64_t n, int64_t k) {
-  if (n * k > pl->max_wf) pl->max_wf = n * k;
+  const int64_t need = std::max(bf16_pair_floats(n, (int)k), bf16_pair_floats(k, (int)n));   // either orientation, padded pairs
+  if (need > pl->max_wf) pl->max_wf = need;
   if (n > pl->max_n) pl->max_n = n;
   if (k > pl->max_n) pl->max_n = k;
 }
@@ -272,9 +273,9 @@ WSlot alloc_slot(mpmae_plan *pl, int N, int K) {
   WSlot s{};
   s.N = N; s.K = K;
   s.wf = ws_alloc(pl, nullptr, N, K);
-  s.wf_lo = ws_alloc(pl, nullptr, N, K);
+  s.wf_lo = ws_alloc(pl, nullptr, 1, bf16_pair_floats(N, K));    // 3xTF32 remainder [N, K] or the (padded) 3xBF16 pair array
   s.wft = ws_alloc(pl, nullptr, K, N);
-  s.wft_lo = ws_alloc(pl, nullptr, K, N);
+  s.wft_lo = ws_alloc(pl, nullptr, 1, bf16_pair_floats(K, N));
   s.bf = ws_alloc(pl, nullptr, 1, N);
   return s;
 }
@@ -1593,6 +1594,15 @@ int mpmae_gemm_epi(int32_t mode, int32_t backend, const mpmae_gemm_desc *d, void
   if (e != cudaSuccess) return fail(MPMAE_ERR_CUDA, "gemm_epi: %s", cudaGetErrorString(e));
   return MPMAE_OK;
 }
+
+#ifdef MPMAE_TC_KNOBS
+// knob builds only (tools/tc_trace.py): the event trace of the last traced GEMM launch, 8 roles x 256 words
+extern "C" int mpmae_debug_tc_trace(unsigned long long *dst_host) {
+  if (!tc::tc_trace_buffer()) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(dst_host, tc::tc_trace_buffer(), 8 * 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 int mpmae_gemm_wgrad(int32_t backend, const float *x, const float *y, float *dw, int64_t R, int32_t N, int32_t K,
                      void *cuda_stream) {

@@ -11,12 +11,17 @@ SHAPES = [(1000, 160, 40), (4864, 40, 160), (300, 48, 64), (12544, 2816, 512), (
           (2500, 640, 160), (4864, 512, 320), (19456, 80, 320), (65, 1280, 320), (4097, 96, 384)]
 
 
+def _scratch(N, K):
+    from mmearth_train_b200._native import gemm_scratch_floats   # 2 * N * ceil32(K): the split weight is padded to 32-column groups
+    return gemm_scratch_floats(N, K)
+
+
 def run(nat, backend, a, b, bias):
     M, K = a.shape
     N = b.shape[0]
     out = torch.full((M, N), float("nan"), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    scratch = torch.empty(2 * N * K, device="cuda")
+    scratch = torch.empty(_scratch(N, K), device="cuda")
     nat.check(nat.lib.mpmae_gemm_rows(backend, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
                                       C.c_void_p(bias.data_ptr()) if bias is not None else None, C.c_void_p(out.data_ptr()),
                                       M, N, K, C.c_void_p(scratch.data_ptr()), C.c_void_p(st)), "gemm_rows")
@@ -112,7 +117,7 @@ def test_gemm_epilogues(native_lib, shape, backend, tol):
         nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(d), C.c_void_p(st)), "gemm_epi")
         torch.cuda.synchronize()
 
-    scratch = torch.empty(2 * N * K, device="cuda")
+    scratch = torch.empty(_scratch(N, K), device="cuda")
     # mode 1
     out, out2 = torch.full((M, N), float("nan"), device="cuda"), torch.full((M, N), float("nan"), device="cuda")
     colsum = torch.zeros(G, N, device="cuda")
@@ -153,7 +158,7 @@ def test_gemm_gelu_on_operand_and_acc_scale(native_lib, shape, backend, tol):
     resid = torch.randn(M, N, generator=g).cuda()
     a_scale = (1.0 + 0.3 * torch.randn(K, generator=g)).cuda()
     st = torch.cuda.current_stream().cuda_stream
-    scratch = torch.empty(2 * N * K, device="cuda")
+    scratch = torch.empty(_scratch(N, K), device="cuda")
 
     def call(mode, **kw):
         d = nat.GemmDesc()
@@ -180,7 +185,7 @@ def test_gemm_gelu_on_operand_and_acc_scale(native_lib, shape, backend, tol):
     acc_scale = (1.0 + 0.3 * torch.randn(N3, generator=g)).cuda()
     out3, cs2 = torch.full((M3, N3), float("nan"), device="cuda"), torch.zeros(N3, device="cuda")
     d = nat.GemmDesc()
-    for k, v in dict(a=dy, b=w, aux2=aux2, kg=kg, out=out3, colsum2=cs2, scratch=torch.empty(2 * N3 * K3, device="cuda"),
+    for k, v in dict(a=dy, b=w, aux2=aux2, kg=kg, out=out3, colsum2=cs2, scratch=torch.empty(_scratch(N3, K3), device="cuda"),
                      acc_scale=acc_scale).items():
         setattr(d, k, v.data_ptr())
     d.M, d.N, d.K, d.group_rows = M3, N3, K3, 0
@@ -217,7 +222,7 @@ def test_gemm_in_kernel_grn_scale(native_lib, shape, backend, tol):
     nx, scale = torch.full((K,), float("nan"), device="cuda"), torch.full((K,), float("nan"), device="cuda")
     denom = torch.full((1,), float("nan"), device="cuda")
     d = nat.GemmDesc()
-    for k, v in dict(a=a, b=b, bias=bias, resid=resid, out=out, scratch=torch.empty(2 * N * K, device="cuda"), grn_gsq=gsq.float(),
+    for k, v in dict(a=a, b=b, bias=bias, resid=resid, out=out, scratch=torch.empty(_scratch(N, K), device="cuda"), grn_gsq=gsq.float(),
                      grn_gamma=gamma, grn_nx=nx, grn_scale=scale, grn_denom=denom).items():
         setattr(d, k, v.data_ptr())
     d.M, d.N, d.K, d.group_rows, d.a_gelu, d.grn_eps = M, N, K, 0, 1, 1e-6

@@ -12,7 +12,7 @@ def bench(mode, backend, M, N, K, iters=10, group_rows=0):
     aux, aux2 = t(M, N), t(M, N)
     G = 1 if group_rows == 0 else (M + group_rows - 1) // group_rows
     kg, colsum, colsum2 = t(G, N), torch.zeros(G, N, device=dev), torch.zeros(N, device=dev)
-    scratch = torch.empty(2 * N * K, device=dev)
+    scratch = torch.empty(nat.gemm_scratch_floats(N, K), device=dev)
     d = nat.GemmDesc()
     for k, v in dict(a=a, b=b, bias=bias, aux=aux, aux2=aux2, kg=kg, out=out, out2=out2, colsum=colsum, colsum2=colsum2,
                      scratch=scratch).items():

@@ -27,7 +27,7 @@ def bench(mode, M, N, K, a_gelu=0, group_rows=0, iters=6, backend=3, resid=False
     b, bias = t(N, K) * 0.1, t(N)
     G = 1 if group_rows == 0 else (M + group_rows - 1) // group_rows
     kg, colsum, colsum2 = t(G, N), torch.zeros(G, N, device=dev), torch.zeros(N, device=dev)
-    scratch = torch.empty(2 * N * K, device=dev)
+    scratch = torch.empty(nat.gemm_scratch_floats(N, K), device=dev)
     gsq, gamma = torch.rand(K, device=dev) + 0.5, t(K)
     nx, sc, den = torch.empty(K, device=dev), torch.empty(K, device=dev), torch.empty(1, device=dev)
     ds = []
@@ -43,17 +43,44 @@ def bench(mode, M, N, K, a_gelu=0, group_rows=0, iters=6, backend=3, resid=False
             d.grn_gsq, d.grn_gamma, d.grn_nx, d.grn_scale, d.grn_denom = (x.data_ptr() for x in (gsq, gamma, nx, sc, den))
             d.grn_eps = 1e-6
         ds.append(d)
+    call = lambda i, st: nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(ds[i % nbuf]), C.c_void_p(st)), "gemm_epi")
+    return timed(call, iters)     # us; includes the (tiny) weight-split launch
+
+
+GRAPH = bool(os.environ.get("SWEEP_GRAPH"))
+
+
+def timed(call, iters):
+    """us per call: eager launches, or (SWEEP_GRAPH=1) a CUDA graph of `iters` calls replayed -- no host time in the number"""
     st = torch.cuda.current_stream().cuda_stream
     for i in range(2):
-        nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(ds[i % nbuf]), C.c_void_p(st)), "gemm_epi")
+        call(i, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if GRAPH:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            call(0, side.cuda_stream)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(iters):
+                    call(i, side.cuda_stream)
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
     e0.record()
     for i in range(iters):
-        nat.check(nat.lib.mpmae_gemm_epi(mode, backend, C.byref(ds[i % nbuf]), C.c_void_p(st)), "gemm_epi")
+        call(i, st)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3     # us; includes the (tiny) weight-split launch
+    return e0.elapsed_time(e1) / iters * 1e3
 
 
 def bench_tn(R, N, K, y_gelu, backend, iters=6):
@@ -62,18 +89,9 @@ def bench_tn(R, N, K, y_gelu, backend, iters=6):
     xs = [torch.randn(R, N, device=dev) for _ in range(nbuf)]
     ys = [torch.randn(R, K, device=dev) for _ in range(nbuf)]
     dw = torch.zeros(N, K, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    call = lambda i: nat.check(nat.lib.mpmae_gemm_wgrad_act(backend, xs[i % nbuf].data_ptr(), ys[i % nbuf].data_ptr(), dw.data_ptr(),
-                                                            R, N, K, y_gelu, C.c_void_p(st)), "wgrad")
-    call(0); call(1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        call(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+    call = lambda i, st: nat.check(nat.lib.mpmae_gemm_wgrad_act(backend, xs[i % nbuf].data_ptr(), ys[i % nbuf].data_ptr(), dw.data_ptr(),
+                                                                R, N, K, y_gelu, C.c_void_p(st)), "wgrad")
+    return timed(call, iters)
 
 
 if __name__ == "__main__":
