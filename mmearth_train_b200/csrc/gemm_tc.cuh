@@ -243,7 +243,7 @@ struct TcParams {
   unsigned long long *trace;   // knob builds only (TC_TRACE)
   uint32_t tmem_cols;
   int dbg;       // MPMAE_TC_DBG timing experiments (results invalid): 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld,
-                 // 32 no MMAs, 64 no operand split
+                 // 16 no per-element operand loads, 32 no MMAs, 64 no operand split
 };
 
 __device__ __forceinline__ void tmem_ld16v(uint32_t taddr, float *v) { tmem_ld16(taddr, v); }
@@ -273,11 +273,61 @@ __device__ __forceinline__ float warp_colsum16(float *v, int lane) {
 // AGELU (EPI_STORE only): the splitter warps also apply GELU and the GRN scale to every A element (pw2 of a sparse block
 // reading the saved pre-activation); that is ~3x their work per element while the epilogue covers only N = C columns, so
 // the roles become 4 epilogue + 16 splitter warps.
-__host__ __device__ constexpr int epi_warps(int mode, bool wide, bool agelu = false) {
-  return agelu ? 4 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 16) : 12));
+// (epilogue, splitter) warps per role set; -DTC_W_<set>_E= / _S= overrides for tuning runs (tools/role_sweep.sh)
+#define TC_ROLE_DEFAULT(name, e, s) \
+  constexpr int name##_E_default = e, name##_S_default = s;
+TC_ROLE_DEFAULT(TC_W_AG, 4, 16)    // GELU + GRN scale on the A operand (pw2 of a sparse block)
+TC_ROLE_DEFAULT(TC_W_ST, 8, 8)     // plain store / LayerNorm-backward epilogue
+TC_ROLE_DEFAULT(TC_W_SQ, 16, 2)    // forward GELU + statistics, narrow K
+TC_ROLE_DEFAULT(TC_W_SQW, 8, 8)    // ... wide K
+TC_ROLE_DEFAULT(TC_W_BW, 12, 4)    // backward epilogues (DG, DH_GELU), narrow K
+TC_ROLE_DEFAULT(TC_W_BWW, 12, 4)   // ... wide K
+#ifndef TC_W_AG_E
+#define TC_W_AG_E TC_W_AG_E_default
+#endif
+#ifndef TC_W_AG_S
+#define TC_W_AG_S TC_W_AG_S_default
+#endif
+#ifndef TC_W_ST_E
+#define TC_W_ST_E TC_W_ST_E_default
+#endif
+#ifndef TC_W_ST_S
+#define TC_W_ST_S TC_W_ST_S_default
+#endif
+#ifndef TC_W_SQ_E
+#define TC_W_SQ_E TC_W_SQ_E_default
+#endif
+#ifndef TC_W_SQ_S
+#define TC_W_SQ_S TC_W_SQ_S_default
+#endif
+#ifndef TC_W_SQW_E
+#define TC_W_SQW_E TC_W_SQW_E_default
+#endif
+#ifndef TC_W_SQW_S
+#define TC_W_SQW_S TC_W_SQW_S_default
+#endif
+#ifndef TC_W_BW_E
+#define TC_W_BW_E TC_W_BW_E_default
+#endif
+#ifndef TC_W_BW_S
+#define TC_W_BW_S TC_W_BW_S_default
+#endif
+#ifndef TC_W_BWW_E
+#define TC_W_BWW_E TC_W_BWW_E_default
+#endif
+#ifndef TC_W_BWW_S
+#define TC_W_BWW_S TC_W_BWW_S_default
+#endif
+__host__ __device__ constexpr int pick2(int which, int e, int s) { return which == 0 ? e : s; }
+__host__ __device__ constexpr int role_warps(int which, int mode, bool wide, bool agelu) {
+  return agelu ? pick2(which, TC_W_AG_E, TC_W_AG_S)
+         : mode == EPI_STORE ? pick2(which, TC_W_ST_E, TC_W_ST_S)
+         : mode == EPI_GELU_SQ ? (wide ? pick2(which, TC_W_SQW_E, TC_W_SQW_S) : pick2(which, TC_W_SQ_E, TC_W_SQ_S))
+                               : (wide ? pick2(which, TC_W_BWW_E, TC_W_BWW_S) : pick2(which, TC_W_BW_E, TC_W_BW_S));
 }
+__host__ __device__ constexpr int epi_warps(int mode, bool wide, bool agelu = false) { return role_warps(0, mode, wide, agelu); }
 __host__ __device__ constexpr int split_warps(int mode, bool split, bool wide, bool agelu = false) {
-  return !split ? 0 : agelu ? 16 : (mode == EPI_STORE ? 8 : (mode == EPI_GELU_SQ ? (wide ? 8 : 2) : 4));
+  return !split ? 0 : role_warps(1, mode, wide, agelu);
 }
 __host__ __device__ constexpr int tc_threads(int mode, bool split, bool wide, bool agelu = false) {
   return 64 + 32 * epi_warps(mode, wide, agelu) + 32 * split_warps(mode, split, wide, agelu);
@@ -430,7 +480,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // input / saved pre-activation), one 64-byte piece per lane and chunk: ~24 KB in flight per SM, which at DRAM latency
       // is < 2 TB/s for the whole chip (the stage-0 da kernel reads 199 MB of `a` that way).  The producer pulls the item's
       // block into L2 when it issues the item's operand loads, a tile or two ahead of the epilogue.
-      const float *pf_src = !p.l2_prefetch ? nullptr
+      const float *pf_src = p.l2_prefetch != 1 ? nullptr
                             : (MODE == EPI_STORE) ? (g.ln_xhat ? g.ln_xhat : g.resid)
                             : (MODE == EPI_DG) ? g.aux : (MODE == EPI_DH_GELU) ? g.aux2 : nullptr;
       WorkItem w;
@@ -584,7 +634,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t srow = sbuf + (uint32_t)lane * 64u, sx = (uint32_t)(lane >> 1) & 3u;
         const int row0 = m_blk * BM + q * 32;
         auto load_pre = [&](int c0, float4 *dst) {
-          if (prep) {
+          if (prep && !(TC_DBG(p) & 16)) {
             ld_global_v8(prep + c0, dst[0], dst[1]);
             if (c0 + 8 < ncols) ld_global_v8(prep + c0 + 8, dst[2], dst[3]);
           }
@@ -637,6 +687,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
           if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
           continue;
+        }
+        if (prep && p.l2_prefetch == 2) {   // experiment: every lane pulls its pieces of the NEXT item's operand into L2
+          WorkItem wn;
+          if (get_work(p, it + 1, wn)) {
+            const float *nx = pre_src + ((int64_t)wn.m_blk * BM + q * 32 + lane) * (int64_t)g.N + wn.n0;
+            const int nc = (g.N - wn.n0 < wn.wn) ? g.N - wn.n0 : wn.wn;
+            if ((int64_t)wn.m_blk * BM + q * 32 + lane < g.M)
+              for (int c = part * 16; c < nc; c += 16 * kParts) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + c));
+          }
         }
         int c0 = part * 16;
         float4 pre[4];
@@ -1351,7 +1410,11 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
   if (!bn) return cudaErrorInvalidConfiguration;
   p.bn = bn;
   p.stages = 2;
-  while (p.stages < STAGES && smem_for(bn, p.stages + 1) <= 226 * 1024) ++p.stages;
+  static const int env_stages = getenv("MPMAE_TC_STAGES") ? atoi(getenv("MPMAE_TC_STAGES")) : STAGES;
+  // the GELU-backward epilogue streams a second [M, N] operand through the LSU; a deep operand ring running ahead of it made
+  // that kernel SLOWER (stage 0: 126 us with 3 stages, 141 with 5 -- profiles/r2_ad_sweep.txt)
+  const int max_stages = MODE == EPI_DH_GELU ? 3 : STAGES;
+  while (p.stages < max_stages && p.stages < env_stages && smem_for(bn, p.stages + 1) <= 226 * 1024) ++p.stages;
   p.num_m = (int)cdiv64(a.M, BM);
   p.num_n = cdiv(a.N, p.bn);
   p.num_k = cdiv(a.K, BK);
@@ -1409,8 +1472,8 @@ inline cudaError_t launch_gemm_rows_tc_impl(const GemmArgs &a, cudaStream_t st) 
     }
   }
   // measured (profiles/r2_x_sweep.txt): no gain, the stage-0 da kernel 5 % slower -- opt-in only
-  static const bool no_pf = getenv("MPMAE_TC_L2PF") == nullptr;
-  p.l2_prefetch = (!no_pf && a.N % 4 == 0 && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2 | (uintptr_t)a.ln_xhat) & 15) == 0) ? 1 : 0;
+  static const int env_pf = getenv("MPMAE_TC_L2PF") ? atoi(getenv("MPMAE_TC_L2PF")) : 0;   // 1: bulk by the producer, 2: per lane
+  p.l2_prefetch = (env_pf > 0 && a.N % 4 == 0 && (((uintptr_t)a.resid | (uintptr_t)a.aux | (uintptr_t)a.aux2 | (uintptr_t)a.ln_xhat) & 15) == 0) ? env_pf : 0;
   p.trace = nullptr;
 #ifdef MPMAE_TC_KNOBS
   if (getenv("MPMAE_TC_TRACE")) {

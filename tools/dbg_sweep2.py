@@ -3,7 +3,7 @@
 Needs the knob build (results are invalid with knobs on; only the times mean something):
     nvcc ... -DMPMAE_TC_KNOBS=1 -o mmearth_train_b200/lib/libmpmae_knobs.so mmearth_train_b200/csrc/mpmae.cu
     MPMAE_LIB=mmearth_train_b200/lib/libmpmae_knobs.so python tools/dbg_sweep2.py
-dbg bits: 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld, 32 no MMA, 64 no operand split
+dbg bits: 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld, 16 no per-element operand loads, 32 no MMA, 64 no operand split
 """
 import ctypes as C
 import os
@@ -96,11 +96,11 @@ def bench_tn(R, N, K, y_gelu, backend, iters=6):
 
 if __name__ == "__main__":
     B = 256
-    knobs = [0, 1, 2, 4, 8, 32, 64, 96, 7, 15, 127]
+    knobs = [0, 1, 2, 4, 8, 16, 32, 64, 96, 7, 23, 127]
     have_knobs = "knobs" in (os.environ.get("MPMAE_LIB") or "")
     if not have_knobs:
         knobs = [0]
-    print("dbg bits: 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld, 32 no MMA, 64 no operand split")
+    print("dbg bits: 1 no stats, 2 no GELU, 4 no stores, 8 no tcgen05.ld, 16 no per-element operand loads, 32 no MMA, 64 no operand split")
     print("knob:      " + "  ".join(f"{k:6d}" for k in knobs))
     only = sys.argv[1:] or None
     for stage, (P2, Cc) in enumerate([(64, 40), (16, 80), (4, 160), (1, 320)]):
