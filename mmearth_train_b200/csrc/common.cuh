@@ -16,9 +16,11 @@ constexpr int kWarp = 32;
 // semantics are unchanged; what overlaps is launch latency, CTA scheduling and the drain of the previous grid.  Without
 // the launch attribute both instructions are no-ops.  pdl(...) is the launch side: the triple-chevron launch of `kernel`
 // with (g, b, s, st) is spelled pdl(kernel, g, b, s, st)(args); the attribute is set when MPMAE_PDL=1.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
 }
 inline bool pdl_enabled() {
   static const bool on = [] { const char *e = getenv("MPMAE_PDL"); return e ? atoi(e) != 0 : false; }();

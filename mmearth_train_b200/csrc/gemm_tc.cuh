@@ -387,7 +387,10 @@ __global__ void __launch_bounds__(tc_threads(MODE, SPLIT, WIDE, AGELU), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_b_lo, const __grid_constant__ CUtensorMap map_out,
                const __grid_constant__ CUtensorMap map_out2, const __grid_constant__ CUtensorMap map_bt,
-               const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) { pdl_prologue();
+               const __grid_constant__ CUtensorMap map_bt_lo, const TcParams p) {
+  // programmatic dependent launch: this CTA may become resident while the previous grid drains; what does not read that
+  // grid's results (barrier init, TMEM allocation, descriptor prefetch) runs before the wait
+  pdl_trigger();
   constexpr int kEpiWarps = epi_warps(MODE, WIDE, AGELU), kEpiThreads = 32 * kEpiWarps;
   constexpr int kSplitWarps = split_warps(MODE, SPLIT, WIDE, AGELU), kSplitThreads = 32 * kSplitWarps;
   constexpr int kThreadsNoSplit = 64 + kEpiThreads;
@@ -427,6 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
+  pdl_wait();
   if (warp >= 2 && warp < 2 + kEpiWarps) {
     float grnb_cross = 0.f, grnb_den = 1.f;
     if (MODE == EPI_DH_GELU && g.grnb_ds) {   // backward of the batch-global GRN statistic: the cross term is a sum over all N
@@ -1183,7 +1187,8 @@ constexpr int kTnThreads = 192, kTnSplitThreads = 512;   // 16 splitter warps: b
 // statistic gradient is derived from dW2f by the chain rule of the weight fold).
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) { pdl_prologue();
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
   const int bn = p.bn, nstage = p.stages;
@@ -1207,6 +1212,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_ptr, p.tmem_cols);
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
