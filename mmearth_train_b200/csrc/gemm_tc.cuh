@@ -98,6 +98,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -1168,6 +1175,8 @@ struct TnParams {
   int vec4;          // dW 16-byte aligned and Kw % 4 == 0: vector atomics when the M side is the dW row (swap == 0)
   int gelu_m, gelu_n;   // SPLIT only: the M- / N-side operand is consumed as gelu(operand) (dW2f = dy^T . gelu(a))
   uint32_t tmem_cols;
+  unsigned long long *trace;   // knob builds only (TC_TRACE)
+  int m3d, n3d;      // the operand's feature count is a multiple of 32: ONE 3-D TMA box per chunk brings all its 32-feature blocks
 };
 
 // MN-major TF32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte atomicity
@@ -1187,7 +1196,8 @@ constexpr int kTnThreads = 192, kTnSplitThreads = 512;   // 16 splitter warps: b
 // statistic gradient is derived from dW2f by the chain rule of the weight fold).
 template <bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n, const TnParams p) {
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n,
+                  const __grid_constant__ CUtensorMap map_m3, const __grid_constant__ CUtensorMap map_n3, const TnParams p) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
@@ -1224,6 +1234,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      TC_TRACE_DECL;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const int sp = item / (p.num_m * p.num_n), t = item - sp * (p.num_m * p.num_n);
         const int m_blk = t / p.num_n, n_blk = t - m_blk * p.num_n;
@@ -1231,12 +1242,23 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
         const int c_end = min(c_begin + p.chunks_per_split, total_chunks);
         for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
+          TC_TRACE(p, 0);
           uint8_t *sm = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(&full_bar[stage], m_bytes + n_bytes);
+          // (the single producer thread was the bottleneck of the single-pass kernel: 9 box loads per 32-row chunk took
+          // 0.41 us to issue, profiles/r2_aj_trace_tn.txt; a 3-D box [32 features][32 rows][blocks] lands in the same layout)
+          if (p.m3d) {
+            tma_load_3d(sm, &map_m3, &full_bar[stage], 0, ch * 32, m_blk * (BM / 32));
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sm + j * 4096, &map_m, &full_bar[stage], m_blk * BM + j * 32, ch * 32);
-          for (int j = 0; j < bn / 32; ++j)
-            tma_load_2d(sm + m_span + j * 4096, &map_n, &full_bar[stage], n_blk * bn + j * 32, ch * 32);
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sm + j * 4096, &map_m, &full_bar[stage], m_blk * BM + j * 32, ch * 32);
+          }
+          if (p.n3d) {
+            tma_load_3d(sm + m_span, &map_n3, &full_bar[stage], 0, ch * 32, n_blk * (bn / 32));
+          } else {
+            for (int j = 0; j < bn / 32; ++j)
+              tma_load_2d(sm + m_span + j * 4096, &map_n, &full_bar[stage], n_blk * bn + j * 32, ch * 32);
+          }
           if (++stage == nstage) { stage = 0; phase ^= 1; }
         }
       }
@@ -1246,6 +1268,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
       const uint32_t idesc = make_idesc(bn) | (1u << 15) | (1u << 16);   // A and B MN-major
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
+      TC_TRACE_DECL;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const int sp = item / (p.num_m * p.num_n);
         const int c_begin = sp * p.chunks_per_split;
@@ -1255,7 +1278,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * bn);
         for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait(&full_bar[stage], phase);
+          TC_TRACE(p, 1);
           if (SPLIT) mbar_wait(&split_bar[stage], phase);
+          TC_TRACE(p, 2);
           tc_fence_after();
           const uint32_t sm = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
@@ -1281,11 +1306,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
     const int q = warp & 3;
     int as = 0;
     uint32_t aphase = 0;
+    TC_TRACE_DECL;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       const int t = item % (p.num_m * p.num_n);
       const int m_blk = t / p.num_n, n_blk = t - m_blk * p.num_n;
       const int mi = m_blk * BM + q * 32 + lane;          // index on the M side
       mbar_wait(&tfull_bar[as], aphase);
+      if (warp == 2 && lane == 0) TC_TRACE(p, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * bn);
       for (int c0 = 0; c0 < bn; c0 += 16) {
@@ -1300,7 +1327,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               atomicAdd(dst + j, make_float4(sc * v[4 * j], sc * v[4 * j + 1], sc * v[4 * j + 2], sc * v[4 * j + 3]));
-          } else {
+          } else if (!p.swap || !p.vec4) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ni = ni0 + j;
@@ -1312,10 +1339,39 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_consta
             }
           }
         }
+        if (p.swap && p.vec4) {
+          // swapped roles: a lane holds ONE k (its TMEM lane) and 16 consecutive n, but dW rows run along k.  4 x 4 transposes
+          // inside lane quads (4 shuffles + 8 selects each) give every lane 4 consecutive k of one n: four 16-byte vector
+          // atomics per chunk instead of sixteen 4-byte ones (the scalar epilogue took 11 - 18 us of a 30 us item at stages
+          // 2 / 3, profiles/r2_aj_trace_tn.txt).  All lanes shuffle; only the atomics are guarded.
+          const int t = lane & 3;
+          const bool odd = (t & 1) != 0, hi = (t & 2) != 0;
+          const int kq = mi & ~3;                       // Msz % 4 == 0: a quad is inside or outside as a whole
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            float x0 = v[4 * b], x1 = v[4 * b + 1], x2 = v[4 * b + 2], x3 = v[4 * b + 3];
+            {
+              const float s0 = odd ? x0 : x1, s1 = odd ? x2 : x3;
+              const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+              if (odd) { x0 = r0; x2 = r1; } else { x1 = r0; x3 = r1; }
+            }
+            {
+              const float s0 = hi ? x0 : x2, s1 = hi ? x1 : x3;
+              const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2), r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+              if (hi) { x0 = r0; x1 = r1; } else { x2 = r0; x3 = r1; }
+            }
+            const int n = n_blk * bn + c0 + 4 * b + t;   // x0..x3 = (k = kq .. kq + 3, n)
+            if (kq < p.Msz && n < p.Nsz) {
+              const float sc = p.rs ? __ldg(p.rs + n) : 1.f;
+              atomicAdd(reinterpret_cast<float4 *>(p.dW + (int64_t)n * p.Kw + kq), make_float4(sc * x0, sc * x1, sc * x2, sc * x3));
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (warp == 2 && lane == 0) TC_TRACE(p, 4);
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   } else if (SPLIT) {
@@ -1369,6 +1425,20 @@ inline bool make_map_box32(CUtensorMap *map, const float *ptr, int64_t rows, int
   const cuuint32_t box[2] = {32, 32};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// the same [rows, cols] fp32 matrix (cols % 32 == 0) as a 3-D tensor (32 features, rows, cols / 32 blocks): one box
+// [32][32 rows][nblocks] = nblocks MN-major operand blocks of 4096 bytes, block indices beyond cols / 32 zero-filled
+inline bool make_map_box32_3d(CUtensorMap *map, const float *ptr, int64_t rows, int64_t cols, int nblocks) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || cols % 32 != 0) return false;
+  const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, 128};
+  const cuuint32_t box[3] = {32, 32, (cuuint32_t)nblocks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1543,6 +1613,8 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
     return (double)msz * nn + (double)nsz * nm;
   };
   p.swap = cost(a.K, a.N) < cost(a.N, a.K) ? 1 : 0;
+  static const int env_swap = getenv("MPMAE_TN_SWAP") ? atoi(getenv("MPMAE_TN_SWAP")) : -1;   // experiment: force 0 / 1
+  if (env_swap >= 0) p.swap = env_swap;
   p.Msz = p.swap ? a.K : a.N;
   p.Nsz = p.swap ? a.N : a.K;
   if (a.y_gelu && !SPLIT) return cudaErrorInvalidConfiguration;   // the activation is applied by the splitter warps
@@ -1594,6 +1666,33 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   };
   CUtensorMap mm, mn;
   if (!get(&mm, msrc, a.R, p.Msz) || !get(&mn, nsrc, a.R, p.Nsz)) return cudaErrorInvalidValue;
+  static std::map<std::tuple<const void *, int64_t, int64_t, int>, CUtensorMap> cache3;
+  auto get3 = [&](CUtensorMap *out, const float *ptr, int64_t rows, int64_t cols_, int nblocks) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple((const void *)ptr, rows, cols_, nblocks);
+    auto it = cache3.find(key);
+    if (it == cache3.end()) {
+      CUtensorMap m;
+      if (!make_map_box32_3d(&m, ptr, rows, cols_, nblocks)) return false;
+      it = cache3.emplace(key, m).first;
+    }
+    *out = it->second;
+    return true;
+  };
+  static const bool no3d = getenv("MPMAE_TN_NO3D") != nullptr;
+  CUtensorMap mm3 = mm, mn3 = mn;
+  p.m3d = (!no3d && p.Msz % 32 == 0 && get3(&mm3, msrc, a.R, p.Msz, BM / 32)) ? 1 : 0;
+  p.n3d = (!no3d && p.Nsz % 32 == 0 && get3(&mn3, nsrc, a.R, p.Nsz, bn / 32)) ? 1 : 0;
+  p.trace = nullptr;
+#ifdef MPMAE_TC_KNOBS
+  if (getenv("MPMAE_TC_TRACE")) {
+    static unsigned long long *buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 8 * 256 * sizeof(unsigned long long));
+    cudaMemsetAsync(buf, 0, 8 * 256 * sizeof(unsigned long long), st);
+    p.trace = buf;
+    tc_trace_buffer() = buf;
+  }
+#endif
   const size_t stage_bytes = (size_t)(SPLIT ? 2 : 1) * (BM * 32 * 4 + (size_t)bn * 32 * 4);
   int stages = (int)((224 * 1024 - 2048) / stage_bytes);
   static const int env_tn_stages = getenv("MPMAE_TN_STAGES") ? atoi(getenv("MPMAE_TN_STAGES")) : 0;
@@ -1610,7 +1709,7 @@ inline cudaError_t launch_gemm_wgrad_tc_impl(const WgradArgs &a, cudaStream_t st
   }
   int grid = tiles * p.splits;
   if (grid > 148) grid = 148;
-  pdl(gemm_tn_tc_kernel<SPLIT>, grid, SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, smem, st)(mm, mn, p);
+  pdl(gemm_tn_tc_kernel<SPLIT>, grid, SPLIT ? kTnThreads + kTnSplitThreads : kTnThreads, smem, st)(mm, mn, mm3, mn3, p);
   return cudaGetLastError();
 }
 

@@ -116,6 +116,12 @@ if __name__ == "__main__":
             print(f"s{stage} {name:6s} M={R:6d} N={N:4d} K={K:4d}: " + "  ".join(row), flush=True)
         os.environ["MPMAE_TC_DBG"] = "0"
         print(f"s{stage} dW2f(3xTF32,gelu) {bench_tn(R, Cc, 4 * Cc, 1, 3):6.1f}   dW1f(TF32) {bench_tn(R, 4 * Cc, Cc, 0, 2):6.1f}", flush=True)
+    if only and "tn" in only:
+        for R, N, K, name in ((311296, 40, 160, "s0"), (77824, 80, 320, "s1"), (19456, 160, 640, "s2"), (4864, 320, 1280, "s3")):
+            print(f"{name} dW2f(3xTF32,gelu) {bench_tn(R, N, K, 1, 3):6.1f}   dW1f(TF32) {bench_tn(R, K, N, 0, 2):6.1f}", flush=True)
+        M = B * 49
+        print(f"dec dW2(TF32) {bench_tn(M, 512, 2048, 0, 2):6.1f}   dW1f(TF32) {bench_tn(M, 2048, 512, 0, 2):6.1f}   dW_pix {bench_tn(M, 2816, 512, 0, 2):6.1f}", flush=True)
+        sys.exit(0)
     if not only or "dec" in only:
         M = B * 49
         for name, mode, N, K, gr in (("dec_pw1", 1, 2048, 512, 49), ("dec_pw2", 0, 512, 2048, 0), ("heads", 0, 2816, 512, 0),
