@@ -11,6 +11,7 @@ loss.backward() -> optimizer.step()).  `value` is measured with batches resident
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -343,6 +344,10 @@ class Workload:
 
     def close(self):
         import torch
+        torch.cuda.synchronize()
+        if self.graphed is not None:      # the CUDA graph holds NCCL's captured collectives: it must die before the communicator
+            self.graphed.close()
+        self.graphed = None
         self.model = self.opt = self.net = self.host = self.resident = self.prefetcher = self.reader = None
         self.raw_host = self.raw_prefetcher = self.raw_tf = None
         import gc
@@ -498,8 +503,21 @@ def main():
             line["ddp_leg"] = ddp
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown.  NCCL's communicator destruction waits until every CUDA graph that captured its collectives is gone (the
+        # 8-GPU run of 2026-10-17 printed its line and then sat in destroy_process_group until the box's time limit, with
+        # the headline GraphedStep still referenced): drop every graph first, and let a watchdog end the process should the
+        # teardown still not return -- the measurement is complete and printed at this point.
+        sys.stdout.flush()
+        watchdog = threading.Timer(45.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        wl = o = None   # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

@@ -62,6 +62,15 @@ class GraphedStep:
         self.loss_dict = {m: self.losses[i] for i, m in enumerate(model.out_modalities)}
         self.replays = 0
 
+    def close(self) -> None:
+        """Destroys the CUDA graph.  Under ``torch.distributed`` call this (or drop every reference to the object) BEFORE
+        ``destroy_process_group()``: NCCL's communicator teardown waits for every graph that captured its collectives."""
+        graph, self.graph = getattr(self, "graph", None), None
+        if graph is not None:
+            torch.cuda.synchronize()
+            graph.reset()
+            del graph
+
     def _iteration(self):
         model, opt = self.model, self.optimizer
         out = model(self.static, mask_ratio=self.mask_ratio)
@@ -81,6 +90,8 @@ class GraphedStep:
                     dst.copy_(src, non_blocking=True)
         if lr is not None:
             self.optimizer.lr = lr
+        if self.graph is None:
+            raise RuntimeError("this GraphedStep was closed")
         self.optimizer._dev_state[3] = float(self.optimizer.lr)
         self.graph.replay()
         self.replays += 1
