@@ -1,21 +1,26 @@
 // tcgen05 (5th-generation tensor core) GEMM for the pointwise / strided convolutions:
 //     out[M, N] = A[M, K] . Bw[N, K]^T   (+ fused epilogue, same EpiMode contract as gemm_simt.cuh)
+// and the weight-gradient product dW[N, K] += X[R, N]^T . Y[R, K] (gemm_tn_tc_kernel, contraction over rows).
 //
 // sm_100a only, written directly against the PTX ISA (no CUTLASS):
-//   * TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) streams [128 x 32] fp32 A tiles and [BN x 32] weight tiles
-//     into a 4-stage shared-memory ring; out-of-range rows / K-tail columns are zero-filled by the TMA unit, so
-//     ragged M, N and K (e.g. K = 40) need no padding in HBM;
-//   * ONE elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN <= 256, K = 8 per instruction),
-//     accumulating in TMEM; two accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of
-//     tile i+1; tcgen05.commit releases shared-memory slots / publishes accumulators through mbarriers;
-//   * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per warp), apply the fused
-//     epilogue (bias, GELU, residual, GRN statistics, GELU backward) and write rows straight to HBM;
-//   * persistent CTAs (one per SM) walk the tile list with N fastest so the A tile is re-used from L2.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//   * TMA (cp.async.bulk.tensor, 128-byte swizzle) streams [128 x 32] fp32 A tiles and [BN x 32] weight tiles into a
+//     shared-memory ring of up to 8 stages; out-of-range rows / K-tail columns are zero-filled by the TMA unit, so
+//     ragged M, N and K (e.g. K = 40) need no padding of the activations in HBM;
+//   * ONE elected thread issues tcgen05.mma.cta_group::1 (M = 128, N = BN <= 256; kind::f16 with K = 16 per instruction
+//     for the default 3xBF16 mode, kind::tf32 with K = 8 otherwise), accumulating in TMEM; two accumulator stages
+//     (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1; tcgen05.commit releases shared-memory
+//     slots / publishes accumulators through mbarriers;
+//   * 4 - 16 epilogue warps read the accumulator with tcgen05.ld (a lane quarter per warp, 16 columns at a time), apply
+//     the fused epilogue (bias, GELU, residual, GRN statistics, GELU / LayerNorm backward), stage the [32 x 16] result
+//     chunk in shared memory and hand it to the TMA unit (cp.async.bulk.tensor store);
+//   * 2 - 16 operand-splitter warps turn the fp32 A tile into its (bf16 hi | bf16 lo) or (tf32 hi, lo) form in place;
+//   * persistent CTAs (one per SM) walk the tile list with N fastest so the A tile is re-used from L2; the tiles
+//     beyond the last full wave are cut into column slices for the otherwise idle CTAs.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, then the epilogue warps, then the splitters.
 //
-// Precision: kind::tf32 keeps 10 mantissa bits of each operand.  backend 2 = single pass;
-// backend 1 = "3xTF32": weights pre-split into hi/lo parts by the caller, activations split in shared memory by the
-// epilogue-side splitter, D += Ahi.Bhi + Alo.Bhi + Ahi.Blo (fp32-faithful, 3x tensor work).
+// Precision: backend 3 (default) = "3xBF16", D += Ahi.Bhi + Alo.Bhi + Ahi.Blo with bf16 pairs (see gemm_tc_kernel);
+// backend 1 = "3xTF32", the same with TF32 pairs (weights pre-split by the caller); backend 2 = ONE TF32 pass
+// (kind::tf32 keeps 10 mantissa bits of each operand).
 #pragma once
 #include <cuda.h>
 
