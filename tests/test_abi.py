@@ -115,3 +115,16 @@ def test_entry_points_validate_their_arguments_before_touching_the_device(native
     assert nat.lib.mpmae_tap_info(plan.handle, b"no.such.tap", C.byref(lo), C.byref(hi), C.byref(C.c_int64())) < 0
     with pytest.raises(nat.NativeError, match="no.such.tap"):
         plan.tap("no.such.tap")
+
+
+def test_gemm_scratch_size_follows_the_header(native_lib):
+    """include/mpmae.h: backends 1 and 3 need scratch of 2*N*ceil32(K) floats (the split weight is padded to 32-column groups:
+    [N][ceil(K / 32)][32 bf16 high parts | 32 bf16 remainders] behind the fp32 copy)."""
+    hdr = open(os.path.join(ROOT, "include", "mpmae.h")).read()
+    assert "2*N*ceil32(K)" in hdr
+    for N, K in ((160, 40), (40, 160), (80, 320), (2816, 512), (8, 8), (100, 72)):
+        need_fp32 = N * K                                  # Wf
+        need_pair = N * ((K + 31) // 32) * 64 // 2         # bf16 pair array, in floats
+        got = native_lib.gemm_scratch_floats(N, K)
+        assert got == 2 * N * (((K + 31) // 32) * 32)
+        assert got >= need_fp32 + need_pair
