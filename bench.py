@@ -346,7 +346,10 @@ class Workload:
         import torch
         torch.cuda.synchronize()
         if self.graphed is not None:      # the CUDA graph holds NCCL's captured collectives: it must die before the communicator
-            self.graphed.close()
+            try:
+                self.graphed.close()
+            except Exception as e:        # never lose a finished measurement to a teardown problem
+                print(f"bench: GraphedStep.close() failed: {e!r}", file=sys.stderr)
         self.graphed = None
         self.model = self.opt = self.net = self.host = self.resident = self.prefetcher = self.reader = None
         self.raw_host = self.raw_prefetcher = self.raw_tf = None
@@ -511,12 +514,15 @@ def main():
         watchdog = threading.Timer(45.0, lambda: os._exit(0))
         watchdog.daemon = True
         watchdog.start()
-        wl = o = None   # noqa: F841
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        dist.destroy_process_group()
+        try:
+            wl = o = None   # noqa: F841
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+        except Exception as e:   # the line is printed: a teardown error must not turn into a failed run
+            print(f"bench: teardown: {e!r}", file=sys.stderr)
         watchdog.cancel()
 
 
