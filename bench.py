@@ -368,7 +368,7 @@ def main():
     ap.add_argument("--backend", type=int, default=None, help="GEMM backend override (0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32, 3 tcgen05 3xBF16 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--others", default=None, help="comma-separated configs measured briefly after the headline one "
-                    "(default: cfg3,cfg4,cfg5a,cfg5b when the headline is cfg2; 'none' to skip)")
+                    "(default when the headline is cfg2: cfg1,cfg3,cfg4,cfg5a,cfg5b on one GPU, cfg3,cfg4 under torchrun; 'none' to skip)")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -427,14 +427,20 @@ def main():
 
     # ---- the other BASELINE.json configurations, briefly: same protocol, 10 timed steps each
     others = {}
-    names = a.others.split(",") if a.others not in (None, "none") else ([] if a.others == "none" else
-                                                                        (["cfg1", "cfg3", "cfg4", "cfg5a", "cfg5b"] if a.config == "cfg2" else []))
+    # default: all of them on one GPU; under torchrun the two configurations BASELINE.json defines on 8 GPUs (cfg3, cfg4: the
+    # set that has run on 8 B200, profiles/r2_n8_final.json)
+    default_others = (["cfg1", "cfg3", "cfg4", "cfg5a", "cfg5b"] if world == 1 else ["cfg3", "cfg4"]) if a.config == "cfg2" else []
+    names = a.others.split(",") if a.others not in (None, "none") else ([] if a.others == "none" else default_others)
     for name in names:
-        o = Workload(name, dev, rank, world, a.backend, nb=3)
-        oms, oms_e2e = o.measure(10, 3)
-        others[name] = o.summary(10, oms, oms_e2e)
-        others[name]["launches_per_step"] = o.model.last_run["plan"].launches(False) + o.model.last_run["plan"].launches(True) + 1
-        o.close()
+        try:
+            o = Workload(name, dev, rank, world, a.backend, nb=3)
+            oms, oms_e2e = o.measure(10, 3)
+            others[name] = o.summary(10, oms, oms_e2e)
+            others[name]["launches_per_step"] = o.model.last_run["plan"].launches(False) + o.model.last_run["plan"].launches(True) + 1
+            o.close()
+        except Exception as e:      # a side measurement must not cost the headline line
+            others[name] = {"error": repr(e)[:300]}
+            print(f"bench: other config {name} failed: {e!r}", file=sys.stderr)
 
     if rank == 0:
         pk = peaks()

@@ -8,6 +8,9 @@ for k in r["kernels"]:
 if d.get("cpu_baseline"):
     print("cpu_baseline", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
 for k, v in (d.get("other_configs") or {}).items():
+    if "error" in v:
+        print(f"  {k}: FAILED {v['error']}")
+        continue
     print(f"  {k}: {v['samples_s']:.0f} samples/s {v['ms_per_step']:.3f} ms/step hbm_frac {v['step_hbm_frac']:.3f} e2e {v['e2e']['value']:.0f} launches {v.get('launches_per_step')} graph {v.get('cuda_graph')} eager {v.get('eager_ms_per_step')}")
 for k in ("e2e_raw", "step_api", "eager", "replica_check", "replica", "ddp_leg"):
     if k in d:
